@@ -1,0 +1,321 @@
+// C ABI of the rasterizer (include/ex4dgs_raster.h): host orchestration of the forward and
+// backward pipelines.  Mirrors the stage order of the reference's host code
+// (cuda_rasterizer/rasterizer_impl.cu:204-363 forward, :367-486 backward; rasterize_points.cu
+// for argument handling) on a caller-supplied stream, with caller-supplied scratch allocators.
+#include "../../include/ex4dgs_raster.h"
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// with `debug` the reference synchronises and checks after every stage (auxiliary.h:296-303)
+#define STAGE(debug, s, what)                                                                        \
+    do {                                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(s);                             \
+        if (_e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(_e));  \
+    } while (0)
+
+}  // namespace
+
+GeometryState carve_geometry(void* base, int P, size_t temp_bytes)
+{
+    GeometryState g;
+    Carver c(base);
+    const size_t n = (size_t)P;
+    g.key_in = c.take<uint32_t>(n);
+    g.val_in = c.take<uint32_t>(n);
+    g.key_sorted = c.take<uint32_t>(n);
+    g.order = c.take<uint32_t>(n);
+    g.tiles_touched = c.take<uint32_t>(n);
+    g.offsets = c.take<uint32_t>(n);
+    g.rec = c.take<SplatRec>(n);
+    g.clamped = c.take<uint8_t>(n);
+    g.gacc = c.take<GradAcc>(n);
+    g.meta = c.take<uint32_t>(64);
+    g.temp = c.take<char>(temp_bytes);
+    g.temp_bytes = temp_bytes;
+    g.total = c.off + 256;
+    return g;
+}
+
+BinningState carve_binning(void* base, int R, size_t temp_bytes)
+{
+    BinningState b;
+    Carver c(base);
+    const size_t n = (size_t)(R > 0 ? R : 0);
+    b.tile_unsorted = c.take<uint16_t>(n);
+    b.val_unsorted = c.take<uint32_t>(n);
+    b.tile_sorted = c.take<uint16_t>(n);
+    b.point_list = c.take<uint32_t>(n);
+    b.temp = c.take<char>(temp_bytes);
+    b.temp_bytes = temp_bytes;
+    b.total = c.off + 256;
+    return b;
+}
+
+ImageState carve_image(void* base, int width, int height)
+{
+    ImageState im;
+    Carver c(base);
+    const size_t n = (size_t)width * height;
+    const size_t tiles = (size_t)((width + EX_TILE - 1) / EX_TILE) * ((height + EX_TILE - 1) / EX_TILE);
+    im.final_T = c.take<float>(n);
+    im.n_contrib = c.take<uint32_t>(n);
+    im.ranges = c.take<uint2>(tiles);
+    im.tile_batches = c.take<uint32_t>(tiles);
+    im.total = c.off + 256;
+    return im;
+}
+
+extern "C" {
+
+int ex4dgs_abi_version(void) { return EX4DGS_ABI_VERSION; }
+const char* ex4dgs_last_error(void) { return g_err; }
+
+size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
+size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, binning_stage2_temp_bytes(R)).total; }
+size_t ex4dgs_image_bytes(int width, int height) { return carve_image(nullptr, width, height).total; }
+
+int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_desc* out, int max)
+{
+    const GeometryState g = carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1));
+    const BinningState b = carve_binning(nullptr, R, binning_stage2_temp_bytes(R));
+    const ImageState im = carve_image(nullptr, width, height);
+    const size_t n = (size_t)P, r = (size_t)(R > 0 ? R : 0), px = (size_t)width * height;
+    const size_t tiles = (size_t)((width + EX_TILE - 1) / EX_TILE) * ((height + EX_TILE - 1) / EX_TILE);
+    const ex4dgs_array_desc all[] = {
+        {"depth_key", 0, (size_t)g.key_in, 4, n},
+        {"depth_key_sorted", 0, (size_t)g.key_sorted, 4, n},
+        {"order", 0, (size_t)g.order, 4, n},
+        {"tiles_touched", 0, (size_t)g.tiles_touched, 4, n},
+        {"offsets", 0, (size_t)g.offsets, 4, n},
+        {"rec", 0, (size_t)g.rec, sizeof(SplatRec), n},
+        {"clamped", 0, (size_t)g.clamped, 1, n},
+        {"gacc", 0, (size_t)g.gacc, sizeof(GradAcc), n},
+        {"tile_unsorted", 1, (size_t)b.tile_unsorted, 2, r},
+        {"val_unsorted", 1, (size_t)b.val_unsorted, 4, r},
+        {"tile_sorted", 1, (size_t)b.tile_sorted, 2, r},
+        {"point_list", 1, (size_t)b.point_list, 4, r},
+        {"final_T", 2, (size_t)im.final_T, 4, px},
+        {"n_contrib", 2, (size_t)im.n_contrib, 4, px},
+        {"ranges", 2, (size_t)im.ranges, 8, tiles},
+        {"tile_batches", 2, (size_t)im.tile_batches, 4, tiles},
+    };
+    const int count = (int)(sizeof(all) / sizeof(all[0]));
+    for (int i = 0; i < count && i < max; i++) out[i] = all[i];
+    return count;
+}
+
+static void* align256(void* p) { return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
+
+int ex4dgs_forward(
+    ex4dgs_alloc_fn geometryBuffer, void* geometry_user,
+    ex4dgs_alloc_fn binningBuffer, void* binning_user,
+    ex4dgs_alloc_fn imageBuffer, void* image_user,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* dir3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, float kernel_size, const float* subpixel_offset, int prefiltered,
+    float* out_color, float min_depth, float max_depth, float* out_depth, float* out_acc, float* out_flow,
+    int* out_idx, int* radii, int debug, unsigned flags, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    g_err[0] = 0;
+    if (P < 0 || width <= 0 || height <= 0) return fail(EX4DGS_ERR_INVALID, "bad sizes P=%d W=%d H=%d", P, width, height);
+    if (!geometryBuffer || !binningBuffer || !imageBuffer) return fail(EX4DGS_ERR_INVALID, "allocator callbacks are required");
+    if (!background || !viewmatrix || !projmatrix || !cam_pos || !subpixel_offset)
+        return fail(EX4DGS_ERR_INVALID, "background/viewmatrix/projmatrix/cam_pos/subpixel_offset are required");
+    if (!out_color || !out_depth || !out_acc || !out_flow || !out_idx) return fail(EX4DGS_ERR_INVALID, "output pointers are required");
+    if (P > 0) {
+        if (!means3D || !opacities || !dir3D || !radii) return fail(EX4DGS_ERR_INVALID, "means3D/opacities/dir3D/radii are required");
+        if ((shs == nullptr) == (colors_precomp == nullptr))
+            return fail(EX4DGS_ERR_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
+        if (((scales == nullptr || rotations == nullptr) && cov3D_precomp == nullptr) ||
+            ((scales != nullptr || rotations != nullptr) && cov3D_precomp != nullptr))
+            return fail(EX4DGS_ERR_INVALID, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (shs != nullptr && (M <= 0 || M < (D + 1) * (D + 1) || D < 0 || D > 3))
+            return fail(EX4DGS_ERR_INVALID, "SH degree %d needs %d coefficients, got M=%d", D, (D + 1) * (D + 1), M);
+    }
+    const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
+    if ((long long)grid_x * grid_y > 65536)
+        return fail(EX4DGS_ERR_UNSUPPORTED, "more than 65536 tiles (%dx%d) is not supported (16-bit tile keys)", grid_x, grid_y);
+
+    // image-sized scratch
+    const size_t img_bytes = carve_image(nullptr, width, height).total;
+    void* img_base = imageBuffer(image_user, img_bytes);
+    if (!img_base) return fail(EX4DGS_ERR_ALLOC, "imageBuffer(%zu) returned NULL", img_bytes);
+    const ImageState img = carve_image(align256(img_base), width, height);
+
+    RenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.W = width; rp.H = height; rp.grid_x = grid_x;
+    rp.subpixel_offset = reinterpret_cast<const float2*>(subpixel_offset);
+    rp.min_depth = min_depth; rp.max_depth = max_depth;
+    rp.final_T = img.final_T; rp.n_contrib = img.n_contrib; rp.tile_batches = img.tile_batches; rp.ranges = img.ranges;
+    rp.out_color = out_color; rp.out_depth = out_depth; rp.out_acc = out_acc; rp.out_flow = out_flow; rp.out_idx = out_idx;
+
+    int R = 0;
+    GeometryState geom;
+    memset(&geom, 0, sizeof(geom));
+    BinningState bin;
+    memset(&bin, 0, sizeof(bin));
+
+    PreprocessParams pp;
+    memset(&pp, 0, sizeof(pp));
+    // camera constants stay on the device: the kernels stage them through shared memory
+    pp.view = viewmatrix; pp.proj = projmatrix; pp.cam = cam_pos;
+    rp.bg = background;
+
+    if (P > 0) {
+        const size_t temp1 = binning_stage1_temp_bytes(P);
+        const size_t geom_bytes = carve_geometry(nullptr, P, temp1).total;
+        void* geom_base = geometryBuffer(geometry_user, geom_bytes);
+        if (!geom_base) return fail(EX4DGS_ERR_ALLOC, "geometryBuffer(%zu) returned NULL", geom_bytes);
+        geom = carve_geometry(align256(geom_base), P, temp1);
+
+        pp.P = P; pp.D = D; pp.M = M;
+        pp.means3D = means3D; pp.dir3D = dir3D; pp.scales = scales; pp.rotations = rotations;
+        pp.opacities = opacities; pp.shs = shs; pp.cov3D_precomp = cov3D_precomp; pp.colors_precomp = colors_precomp;
+        pp.scale_modifier = scale_modifier;
+        pp.W = width; pp.H = height;
+        pp.tan_fovx = tan_fovx; pp.tan_fovy = tan_fovy;
+        pp.focal_y = height / (2.0f * tan_fovy);
+        pp.focal_x = width / (2.0f * tan_fovx);
+        pp.kernel_size = kernel_size;
+        pp.min_depth = min_depth; pp.max_depth = max_depth;
+        pp.grid_x = grid_x; pp.grid_y = grid_y;
+        pp.prefiltered = prefiltered; pp.flags = flags;
+        pp.radii = radii; pp.key_in = geom.key_in; pp.val_in = geom.val_in; pp.tiles_touched = geom.tiles_touched;
+        pp.rec = geom.rec; pp.clamped = geom.clamped;
+        launch_preprocess_fwd(pp, s);
+        STAGE(debug, s, "preprocess");
+
+        CK(binning_stage1(geom, P, s));
+        STAGE(debug, s, "depth sort + scan");
+        // the one blocking read-back of the pipeline (rasterizer_impl.cu:299)
+        uint32_t r32 = 0;
+        CK(cudaMemcpyAsync(&r32, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        R = (int)r32;
+    }
+
+    const size_t temp2 = binning_stage2_temp_bytes(R);
+    const size_t bin_bytes = carve_binning(nullptr, R, temp2).total;
+    void* bin_base = binningBuffer(binning_user, bin_bytes);
+    if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
+    bin = carve_binning(align256(bin_base), R, temp2);
+
+    if (P > 0) {
+        CK(binning_stage2(geom, bin, img, radii, P, R, grid_x, grid_y, flags, s));
+    } else {
+        CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
+    }
+    STAGE(debug, s, "duplicate + tile sort + ranges");
+
+    rp.point_list = bin.point_list;
+    rp.rec = geom.rec;
+    launch_render_fwd(rp, grid_x, grid_y, s);
+    STAGE(debug, s, "render");
+    return R;
+}
+
+int ex4dgs_backward(
+    int P, int D, int M, int R,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* scales, float scale_modifier, const float* rotations,
+    const float* acc_depth, const float* acc, float min_depth, float max_depth,
+    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float kernel_size, const float* subpixel_offset, const int* radii,
+    void* geom_buffer, void* binning_buffer, void* image_buffer,
+    const float* dL_dpix, const float* dL_ddepth, const float* dL_dflow, const float* dL_dacc,
+    float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+    float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_ddir,
+    int debug, unsigned flags, void* stream)
+{
+    (void)flags;
+    cudaStream_t s = (cudaStream_t)stream;
+    g_err[0] = 0;
+    if (P <= 0) return EX4DGS_OK;
+    if (!geom_buffer || !binning_buffer || !image_buffer) return fail(EX4DGS_ERR_INVALID, "scratch buffers of the forward are required");
+    if (!dL_dpix || !dL_ddepth || !dL_dflow || !dL_dacc) return fail(EX4DGS_ERR_INVALID, "upstream gradients are required");
+    if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_ddir) return fail(EX4DGS_ERR_INVALID, "gradient outputs are required");
+    if (shs && !dL_dsh) return fail(EX4DGS_ERR_INVALID, "dL_dsh is required when shs is given");
+    if (scales && (!dL_dscale || !dL_drot)) return fail(EX4DGS_ERR_INVALID, "dL_dscale/dL_drot are required when scales are given");
+
+    const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
+    const GeometryState geom = carve_geometry(align256(geom_buffer), P, binning_stage1_temp_bytes(P));
+    const BinningState bin = carve_binning(align256(binning_buffer), R, binning_stage2_temp_bytes(R));
+    const ImageState img = carve_image(align256(image_buffer), width, height);
+
+    PreprocessBwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.view = viewmatrix; bp.proj = projmatrix; bp.cam = campos;
+    CK(cudaMemsetAsync(geom.gacc, 0, sizeof(GradAcc) * (size_t)P, s));
+
+    RenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.ranges = img.ranges; rp.point_list = bin.point_list; rp.rec = geom.rec;
+    rp.W = width; rp.H = height; rp.grid_x = grid_x;
+    rp.subpixel_offset = reinterpret_cast<const float2*>(subpixel_offset);
+    rp.bg = background;
+    rp.min_depth = min_depth; rp.max_depth = max_depth;
+    rp.final_T = img.final_T; rp.n_contrib = img.n_contrib;
+    rp.out_depth = const_cast<float*>(acc_depth); rp.out_acc = const_cast<float*>(acc);
+    rp.dL_dpix = dL_dpix; rp.dL_ddepth = dL_ddepth; rp.dL_dflow = dL_dflow; rp.dL_dacc = dL_dacc;
+    rp.gacc = geom.gacc;
+    if (R > 0) launch_render_bwd(rp, grid_x, grid_y, s);
+    STAGE(debug, s, "render backward");
+
+    bp.P = P; bp.D = D; bp.M = M;
+    bp.means3D = means3D; bp.scales = scales; bp.rotations = rotations; bp.shs = shs;
+    bp.cov3D_precomp = cov3D_precomp; bp.colors_precomp = colors_precomp;
+    bp.scale_modifier = scale_modifier;
+    bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy;
+    bp.focal_y = height / (2.0f * tan_fovy);
+    bp.focal_x = width / (2.0f * tan_fovx);
+    bp.kernel_size = kernel_size;
+    bp.radii = radii; bp.clamped = geom.clamped; bp.gacc = geom.gacc;
+    bp.dL_dmean2D = dL_dmean2D; bp.dL_dopacity = dL_dopacity; bp.dL_dcolor = dL_dcolor; bp.dL_dmean3D = dL_dmean3D;
+    bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscale = dL_dscale; bp.dL_drot = dL_drot; bp.dL_ddir = dL_ddir;
+    launch_preprocess_bwd(bp, s);
+    STAGE(debug, s, "preprocess backward");
+    return EX4DGS_OK;
+}
+
+int ex4dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        float min_depth, float max_depth, uint8_t* present, void* stream)
+{
+    g_err[0] = 0;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present)))
+        return fail(EX4DGS_ERR_INVALID, "bad arguments");
+    launch_mark_visible(P, means3D, viewmatrix, projmatrix, min_depth, max_depth, present, (cudaStream_t)stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "mark_visible: %s", cudaGetErrorString(e));
+    return EX4DGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,537 @@
+// Per-Gaussian stages of the rasterizer for sm_100a: forward preprocess (cull, 3D->2D EWA
+// projection with mip filter, SH->RGB, tile-rectangle, depth key), the fused backward of those
+// steps, and the frustum test.
+//
+// Behavioural spec (reference, read for behaviour only):
+//   forward : cuda_rasterizer/forward.cu:20-71 (SH), :74-124 (cov2D + mip coef), :128-162 (cov3D),
+//             :165-269 (preprocessCUDA); auxiliary.h:41-56,68-87,267-294
+//   backward: cuda_rasterizer/backward.cu:20-139 (SH), :144-300 (computeCov2DCUDA), :304-367
+//             (cov3D), :372-423 (preprocessCUDA) including the deviations listed in SURVEY.md A.3
+//             (Q1: mip-coef gradient dropped, Q2: cov2D->mean term overwritten, Q6: no quaternion
+//             normalisation).
+#include "common.cuh"
+#include <math.h>
+#include <stdio.h>
+
+namespace {
+
+__device__ __constant__ float kC0 = 0.28209479177387814f;
+__device__ __constant__ float kC1 = 0.4886025119029199f;
+__device__ __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                        -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                        0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                        -0.5900435899266435f};
+
+// Sigma = (S R)^T (S R) from an UN-normalised quaternion (forward.cu:137), upper triangle.
+// Which sums are fused is pinned to the reference build.
+__device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float sz, float mod,
+                                                     float r, float x, float y, float z, float* c)
+{
+    sx = fm(mod, sx); sy = fm(mod, sy); sz = fm(mod, sz);
+    const float xz = fm(x, z), rx = fm(r, x), rz = fm(r, z), yy = fm(y, y), zz = fm(z, z);
+    // rotation matrix entries, R[c][r] in column-major (glm) naming
+    const float t_yyzz = fa(yy, zz);                 // y*y + z*z   (two rounded products, plain add)
+    const float t_xxzz = ff(x, x, zz);               // x*x + z*z
+    const float t_xxyy = ff(x, x, yy);               // x*x + y*y
+    const float R00 = fa(1.f, -fa(t_yyzz, t_yyzz));
+    const float R11 = fa(1.f, -fa(t_xxzz, t_xxzz));
+    const float R22 = fa(1.f, -fa(t_xxyy, t_xxyy));
+    float v;
+    v = ff(x, y, -rz); const float R01 = fa(v, v);   // 2(xy - rz)
+    v = ff(r, y, xz);  const float R02 = fa(v, v);   // 2(xz + ry)
+    v = ff(x, y, rz);  const float R10 = fa(v, v);   // 2(xy + rz)
+    v = ff(y, z, -rx); const float R12 = fa(v, v);   // 2(yz - rx)
+    v = ff(-r, y, xz); const float R20 = fa(v, v);   // 2(xz - ry)
+    v = ff(y, z, rx);  const float R21 = fa(v, v);   // 2(yz + rx)
+    // M = S * R : M[c][r] = s_r * R[c][r]
+    const float M00 = fm(sx, R00), M01 = fm(sy, R01), M02 = fm(sz, R02);
+    const float M10 = fm(sx, R10), M11 = fm(sy, R11), M12 = fm(sz, R12);
+    const float M20 = fm(sx, R20), M21 = fm(sy, R21), M22 = fm(sz, R22);
+    // Sigma[c][r] = sum_k M[r][k] * M[c][k]
+    c[0] = sum3(M00, M00, M01, M01, M02, M02);
+    c[1] = sum3(M00, M10, M01, M11, M02, M12);
+    c[2] = sum3(M00, M20, M01, M21, M02, M22);
+    c[3] = sum3(M10, M10, M11, M11, M12, M12);
+    c[4] = sum3(M10, M20, M11, M21, M12, M22);
+    c[5] = sum3(M20, M20, M21, M21, M22, M22);
+}
+
+// Upper 2x2 of J W Sigma W^T J^T (EWA), before the mip filter.  Also returns the two rows of T.
+struct Cov2D {
+    float a, b, c;          // cov[0][0], cov[0][1], cov[1][1]
+    float T0[3], T1[3];     // T[0][r], T[1][r]
+    float tx, ty, tz;       // clamped view-space mean
+    float txtz, tytz;
+};
+
+__device__ __forceinline__ Cov2D cov2d_project(float mx, float my, float mz, const float* __restrict__ V,
+                                               float focal_x, float focal_y, float tan_fovx, float tan_fovy,
+                                               const float* cov3D)
+{
+    Cov2D o;
+    float tx = xform_row(V, 0, mx, my, mz);
+    float ty = xform_row(V, 1, mx, my, mz);
+    const float tz = xform_row(V, 2, mx, my, mz);
+    const float limx = fm(1.3f, tan_fovx), limy = fm(1.3f, tan_fovy);
+    o.txtz = __fdiv_rn(tx, tz);
+    o.tytz = __fdiv_rn(ty, tz);
+    tx = fm(fminf(limx, fmaxf(-limx, o.txtz)), tz);
+    ty = fm(fminf(limy, fmaxf(-limy, o.tytz)), tz);
+    o.tx = tx; o.ty = ty; o.tz = tz;
+    const float tz2 = fm(tz, tz);
+    const float J00 = __fdiv_rn(focal_x, tz);
+    const float J02 = __fdiv_rn(-fm(focal_x, tx), tz2);
+    const float J11 = __fdiv_rn(focal_y, tz);
+    const float J12 = __fdiv_rn(-fm(focal_y, ty), tz2);
+    // T = W * J with W[k][r] = V[4r + k]:  T[0][r] = V[4r]*J00 + V[4r+2]*J02 ; T[1][r] = V[4r+1]*J11 + V[4r+2]*J12
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        o.T0[r] = ff(J02, V[4 * r + 2], fm(V[4 * r + 0], J00));
+        o.T1[r] = ff(J12, V[4 * r + 2], fm(V[4 * r + 1], J11));
+    }
+    const float c0 = cov3D[0], c1 = cov3D[1], c2 = cov3D[2], c3 = cov3D[3], c4 = cov3D[4], c5 = cov3D[5];
+    // X[k][r] = sum_j T[r][j] * Vrk[k][j]
+    const float X00 = sum3(o.T0[0], c0, o.T0[1], c1, o.T0[2], c2);
+    const float X10 = sum3(o.T0[0], c1, o.T0[1], c3, o.T0[2], c4);
+    const float X20 = sum3(o.T0[0], c2, o.T0[1], c4, o.T0[2], c5);
+    const float X01 = sum3(o.T1[0], c0, o.T1[1], c1, o.T1[2], c2);
+    const float X11 = sum3(o.T1[0], c1, o.T1[1], c3, o.T1[2], c4);
+    const float X21 = sum3(o.T1[0], c2, o.T1[1], c4, o.T1[2], c5);
+    // cov[c][r] = sum_k X[k][r] * T[c][k]
+    o.a = sum3(o.T0[0], X00, o.T0[1], X10, o.T0[2], X20);
+    o.b = sum3(o.T0[0], X01, o.T0[1], X11, o.T0[2], X21);
+    o.c = sum3(o.T1[0], X01, o.T1[1], X11, o.T1[2], X21);
+    return o;
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p)
+{
+    __shared__ float s_cam[36];   // view[16] | proj[16] | campos[3]
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(p.view + threadIdx.x);
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(p.proj + threadIdx.x - 16);
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(p.cam + threadIdx.x - 32);
+    __syncthreads();
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+
+    int radius_out = 0;
+    uint32_t tiles = 0, key = EX_INVISIBLE_KEY;
+    const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
+
+    do {
+        // ---- frustum test (auxiliary.h:267-294)
+        const float hx = xform_row(proj, 0, mx, my, mz);
+        const float hy = xform_row(proj, 1, mx, my, mz);
+        const float hw = xform_row(proj, 3, mx, my, mz);
+        const float pw = __fdiv_rn(1.0f, fa(hw, 0.0000001f));
+        const float ndc_x = fm(hx, pw), ndc_y = fm(hy, pw);
+        const float depth = xform_row(view, 2, mx, my, mz);
+        if ((depth <= p.min_depth) || (depth > p.max_depth) ||
+            ((double)ndc_x < -1.3 || (double)ndc_x > 1.3 || (double)ndc_y < -1.3 || (double)ndc_y > 1.3)) {
+            if (p.prefiltered) {
+                printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                __trap();
+            }
+            break;
+        }
+        // ---- 3D covariance
+        float cov3D[6];
+        if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cov3D[i] = __ldg(p.cov3D_precomp + 6 * idx + i);
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+            cov3d_from_scale_rot(__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2),
+                                 p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+        }
+        // ---- EWA projection + mip filter (forward.cu:74-124)
+        const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
+        const float bb = fm(cv.b, cv.b);
+        const float det0f = ff(cv.a, cv.c, -bb);
+        const float ak = fa(cv.a, p.kernel_size), ck = fa(cv.c, p.kernel_size);
+        const float det = ff(ak, ck, -bb);             // == det_1 before clamping == det of filtered cov
+        const float det_0 = (float)fmax(1e-6, (double)det0f);
+        const float det_1 = (float)fmax(1e-6, (double)det);
+        float coef = (float)sqrt((double)det_0 / ((double)det_1 + 1e-6) + 1e-6);
+        if ((double)det_0 <= 1e-6 || (double)det_1 <= 1e-6) coef = 0.0f;
+        if (det == 0.0f) break;
+        const float det_inv = __fdiv_rn(1.f, det);
+        const float conA = fm(ck, det_inv), conB = fm(-cv.b, det_inv), conC = fm(ak, det_inv);
+        // ---- extent (forward.cu:242-250)
+        const float mid = fm(0.5f, fa(ak, ck));
+        const float disc = __fsqrt_rn(fmaxf(0.1f, ff(mid, mid, -det)));
+        const float lam = fmaxf(fa(mid, disc), fa(mid, -disc));
+        const float radf = ceilf(fm(3.f, __fsqrt_rn(lam)));
+        const int radius = (int)radf;
+        // ndc2Pix in double: ((v + 1.0) * S - 1.0) * 0.5   (auxiliary.h:41-44)
+        const float px = (float)((((double)ndc_x + 1.0) * (double)p.W - 1.0) * 0.5);
+        const float py = (float)((((double)ndc_y + 1.0) * (double)p.H - 1.0) * 0.5);
+        int x0, y0, x1, y1;
+        tile_rect(px, py, radius, p.grid_x, p.grid_y, x0, y0, x1, y1);
+        const uint32_t area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        if (area == 0) break;
+
+        // ---- colour
+        float rgb[3];
+        uint8_t clamp_bits = 0;
+        if (p.colors_precomp == nullptr) {
+            float dx = fa(mx, -cam[0]), dy = fa(my, -cam[1]), dz = fa(mz, -cam[2]);
+            const float len = __fsqrt_rn(sum3(dx, dx, dy, dy, dz, dz));
+            dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            float b[16];
+            int nb = 1;
+            b[0] = kC0;
+            if (p.D > 0) {
+                b[1] = -kC1 * dy; b[2] = kC1 * dz; b[3] = -kC1 * dx; nb = 4;
+                if (p.D > 1) {
+                    const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+                    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy);
+                    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy); nb = 9;
+                    if (p.D > 2) {
+                        b[9] = kC3[0] * dy * (3.0f * xx - yy);
+                        b[10] = kC3[1] * xy * dz;
+                        b[11] = kC3[2] * dy * (4.0f * zz - xx - yy);
+                        b[12] = kC3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                        b[13] = kC3[4] * dx * (4.0f * zz - xx - yy);
+                        b[14] = kC3[5] * dz * (xx - yy);
+                        b[15] = kC3[6] * dx * (xx - 3.0f * yy);
+                        nb = 16;
+                    }
+                }
+            }
+            float acc[3] = {0.f, 0.f, 0.f};
+            if (p.M == 16) {
+                // 192-byte row, 16-byte aligned: twelve 128-bit loads
+                const float4* s4 = reinterpret_cast<const float4*>(sh);
+                float v[48];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const float4 t = __ldg(s4 + i);
+                    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k < nb) {
+                        acc[0] = fmaf(b[k], v[3 * k], acc[0]);
+                        acc[1] = fmaf(b[k], v[3 * k + 1], acc[1]);
+                        acc[2] = fmaf(b[k], v[3 * k + 2], acc[2]);
+                    }
+                }
+            } else {
+                for (int k = 0; k < nb; k++) {
+                    acc[0] = fmaf(b[k], __ldg(sh + 3 * k), acc[0]);
+                    acc[1] = fmaf(b[k], __ldg(sh + 3 * k + 1), acc[1]);
+                    acc[2] = fmaf(b[k], __ldg(sh + 3 * k + 2), acc[2]);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float v = acc[ch] + 0.5f;
+                if (v < 0.f) clamp_bits |= (1u << ch);
+                rgb[ch] = fmaxf(v, 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) rgb[ch] = __ldg(p.colors_precomp + 3 * idx + ch);
+        }
+        p.clamped[idx] = clamp_bits;
+
+        const float opac = fm(__ldg(p.opacities + idx), coef);
+        // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
+        const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
+
+        uint32_t count = area;
+        if (p.flags & 1u) {
+            // conservative per-tile culling; identical test in the duplicate kernel
+            count = 0;
+            for (int ty = y0; ty < y1; ty++)
+                for (int tx = x0; tx < x1; tx++)
+                    count += tile_cannot_contribute(px, py, conA, conB, conC, thr, tx, ty, 0.5f) ? 0u : 1u;
+        }
+
+        SplatRec rc;
+        rc.a = make_float4(px, py, depth, thr);
+        rc.b = make_float4(conA, conB, conC, opac);
+        rc.c = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(idx));
+        rc.d = make_float4(__ldg(p.dir3D + 3 * idx), __ldg(p.dir3D + 3 * idx + 1), __ldg(p.dir3D + 3 * idx + 2), 0.f);
+        p.rec[idx] = rc;
+
+        radius_out = radius;
+        tiles = count;
+        key = __float_as_uint(depth);
+    } while (false);
+
+    p.radii[idx] = radius_out;
+    p.tiles_touched[idx] = tiles;
+    p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
+    p.val_in[idx] = (uint32_t)idx;
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
+                                                           const float* __restrict__ view, const float* __restrict__ proj,
+                                                           float min_depth, float max_depth, uint8_t* __restrict__ present)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float mx = __ldg(means + 3 * idx), my = __ldg(means + 3 * idx + 1), mz = __ldg(means + 3 * idx + 2);
+    const float hx = xform_row(proj, 0, mx, my, mz);
+    const float hy = xform_row(proj, 1, mx, my, mz);
+    const float hw = xform_row(proj, 3, mx, my, mz);
+    const float pw = __fdiv_rn(1.0f, fa(hw, 0.0000001f));
+    const float ndc_x = fm(hx, pw), ndc_y = fm(hy, pw);
+    const float depth = xform_row(view, 2, mx, my, mz);
+    const bool out = (depth <= min_depth) || (depth > max_depth) ||
+                     ((double)ndc_x < -1.3 || (double)ndc_x > 1.3 || (double)ndc_y < -1.3 || (double)ndc_y > 1.3);
+    present[idx] = out ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused backward of the per-Gaussian steps (backward.cu computeCov2DCUDA + preprocessCUDA in one
+// pass, zero-fill of invisible Gaussians folded in).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p)
+{
+    __shared__ float s_cam[36];   // view[16] | proj[16] | campos[3]
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(p.view + threadIdx.x);
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(p.proj + threadIdx.x - 16);
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(p.cam + threadIdx.x - 32);
+    __syncthreads();
+    const float* view = s_cam;
+    const float* cam = s_cam + 32;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+
+    const GradAcc g = p.gacc[idx];
+    // pass-through gradients (zero for Gaussians the compositing loop never touched)
+    p.dL_dmean2D[3 * idx + 0] = g.g0.x; p.dL_dmean2D[3 * idx + 1] = g.g0.y; p.dL_dmean2D[3 * idx + 2] = g.g0.z;
+    p.dL_dopacity[idx] = g.g0.w;
+    p.dL_dcolor[3 * idx + 0] = g.g2.x; p.dL_dcolor[3 * idx + 1] = g.g2.y; p.dL_dcolor[3 * idx + 2] = g.g2.z;
+    p.dL_ddir[3 * idx + 0] = g.g3.x; p.dL_ddir[3 * idx + 1] = g.g3.y; p.dL_ddir[3 * idx + 2] = g.g3.z;
+
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float drot[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool visible = p.radii[idx] > 0;
+    float4* dsh4 = (p.dL_dsh != nullptr && p.M == 16) ? reinterpret_cast<float4*>(p.dL_dsh + (size_t)idx * 48) : nullptr;
+
+    if (visible) {
+        const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
+        float cov3D[6];
+        float sx = 0, sy = 0, sz = 0;
+        float4 q = make_float4(0, 0, 0, 0);
+        if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cov3D[i] = __ldg(p.cov3D_precomp + 6 * idx + i);
+        } else {
+            q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+            sx = __ldg(p.scales + 3 * idx); sy = __ldg(p.scales + 3 * idx + 1); sz = __ldg(p.scales + 3 * idx + 2);
+            cov3d_from_scale_rot(sx, sy, sz, p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+        }
+        // ---- conic -> cov2D -> cov3D (backward.cu:144-257)
+        {
+            const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
+            const float a = cv.a + p.kernel_size, b = cv.b, c = cv.c + p.kernel_size;
+            const float dcx = g.g1.x, dcy = g.g1.y, dcz = g.g1.z;
+            const float denom = a * c - b * b;
+            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+            if (denom2inv != 0) {
+                const float dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
+                const float dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
+                const float dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+                const float* T0 = cv.T0; const float* T1 = cv.T1;
+                dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
+                dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
+                dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
+                dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
+                dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
+                dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
+            }
+            // the cov2D -> mean term (backward.cu:259-299) is overwritten by the assignment at
+            // backward.cu:414 in the reference, so it is not computed.
+        }
+        // ---- mean2D -> mean3D through the projection (backward.cu:396-414)
+        {
+            const float* pr = s_cam + 16;
+            const float hw = pr[3] * mx + pr[7] * my + pr[11] * mz + pr[15];
+            const float m_w = 1.0f / (hw + 0.0000001f);
+            const float mul1 = (pr[0] * mx + pr[4] * my + pr[8] * mz + pr[12]) * m_w * m_w;
+            const float mul2 = (pr[1] * mx + pr[5] * my + pr[9] * mz + pr[13]) * m_w * m_w;
+            const float mul3 = (pr[2] * mx + pr[6] * my + pr[10] * mz + pr[14]) * m_w * m_w;
+            const float gx = g.g0.x, gy = g.g0.y, gz = g.g0.z;
+            dmean[0] = (pr[0] * m_w - pr[3] * mul1) * gx + (pr[1] * m_w - pr[3] * mul2) * gy + (pr[2] * m_w - pr[3] * mul3) * gz;
+            dmean[1] = (pr[4] * m_w - pr[7] * mul1) * gx + (pr[5] * m_w - pr[7] * mul2) * gy + (pr[6] * m_w - pr[7] * mul3) * gz;
+            dmean[2] = (pr[8] * m_w - pr[11] * mul1) * gx + (pr[9] * m_w - pr[11] * mul2) * gy + (pr[10] * m_w - pr[11] * mul3) * gz;
+        }
+        // ---- SH backward (backward.cu:20-139)
+        if (p.shs != nullptr) {
+            const float ox = mx - cam[0], oy = my - cam[1], oz = mz - cam[2];
+            const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+            const float x = ox / len, y = oy / len, z = oz / len;
+            const uint8_t cl = p.clamped[idx];
+            float dRGB[3] = {(cl & 1) ? 0.f : g.g2.x, (cl & 2) ? 0.f : g.g2.y, (cl & 4) ? 0.f : g.g2.z};
+            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            float b[16];
+            float dbx[16], dby[16], dbz[16];      // d basis_k / d(x,y,z)
+#pragma unroll
+            for (int k = 0; k < 16; k++) { b[k] = 0.f; dbx[k] = 0.f; dby[k] = 0.f; dbz[k] = 0.f; }
+            int nb = 1;
+            b[0] = kC0;
+            if (p.D > 0) {
+                nb = 4;
+                b[1] = -kC1 * y; b[2] = kC1 * z; b[3] = -kC1 * x;
+                dby[1] = -kC1; dbz[2] = kC1; dbx[3] = -kC1;
+                if (p.D > 1) {
+                    nb = 9;
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.f * zz - xx - yy);
+                    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy);
+                    dbx[4] = kC2[0] * y; dby[4] = kC2[0] * x;
+                    dby[5] = kC2[1] * z; dbz[5] = kC2[1] * y;
+                    dbx[6] = kC2[2] * 2.f * -x; dby[6] = kC2[2] * 2.f * -y; dbz[6] = kC2[2] * 2.f * 2.f * z;
+                    dbx[7] = kC2[3] * z; dbz[7] = kC2[3] * x;
+                    dbx[8] = kC2[4] * 2.f * x; dby[8] = kC2[4] * 2.f * -y;
+                    if (p.D > 2) {
+                        nb = 16;
+                        b[9] = kC3[0] * y * (3.f * xx - yy);
+                        b[10] = kC3[1] * xy * z;
+                        b[11] = kC3[2] * y * (4.f * zz - xx - yy);
+                        b[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                        b[13] = kC3[4] * x * (4.f * zz - xx - yy);
+                        b[14] = kC3[5] * z * (xx - yy);
+                        b[15] = kC3[6] * x * (xx - 3.f * yy);
+                        dbx[9] = kC3[0] * 3.f * 2.f * xy;          dby[9] = kC3[0] * 3.f * (xx - yy);
+                        dbx[10] = kC3[1] * yz;                     dby[10] = kC3[1] * xz;          dbz[10] = kC3[1] * xy;
+                        dbx[11] = kC3[2] * -2.f * xy;              dby[11] = kC3[2] * (-3.f * yy + 4.f * zz - xx); dbz[11] = kC3[2] * 4.f * 2.f * yz;
+                        dbx[12] = kC3[3] * -3.f * 2.f * xz;        dby[12] = kC3[3] * -3.f * 2.f * yz; dbz[12] = kC3[3] * 3.f * (2.f * zz - xx - yy);
+                        dbx[13] = kC3[4] * (-3.f * xx + 4.f * zz - yy); dby[13] = kC3[4] * -2.f * xy; dbz[13] = kC3[4] * 4.f * 2.f * xz;
+                        dbx[14] = kC3[5] * 2.f * xz;               dby[14] = kC3[5] * -2.f * yz;   dbz[14] = kC3[5] * (xx - yy);
+                        dbx[15] = kC3[6] * 3.f * (xx - yy);        dby[15] = kC3[6] * -3.f * 2.f * xy;
+                    }
+                }
+            }
+            float ddir[3] = {0.f, 0.f, 0.f};
+            if (p.M == 16) {
+                const float4* s4 = reinterpret_cast<const float4*>(sh);
+                float v[48], o[48];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const float4 t = __ldg(s4 + i);
+                    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const bool on = k < nb;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        o[3 * k + ch] = on ? b[k] * dRGB[ch] : 0.f;
+                        if (on) {
+                            const float s = v[3 * k + ch] * dRGB[ch];
+                            ddir[0] += dbx[k] * s; ddir[1] += dby[k] * s; ddir[2] += dbz[k] * s;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 12; i++) dsh4[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+                float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
+                for (int k = 0; k < p.M; k++) {
+                    const bool on = k < nb;
+                    for (int ch = 0; ch < 3; ch++) {
+                        dsh[3 * k + ch] = on ? b[k] * dRGB[ch] : 0.f;
+                        if (on) {
+                            const float s = __ldg(sh + 3 * k + ch) * dRGB[ch];
+                            ddir[0] += dbx[k] * s; ddir[1] += dby[k] * s; ddir[2] += dbz[k] * s;
+                        }
+                    }
+                }
+            }
+            // through dir = o/|o|  (auxiliary.h:235-245)
+            const float sum2 = ox * ox + oy * oy + oz * oz;
+            const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            dmean[0] += ((+sum2 - ox * ox) * ddir[0] - oy * ox * ddir[1] - oz * ox * ddir[2]) * invsum32;
+            dmean[1] += (-ox * oy * ddir[0] + (sum2 - oy * oy) * ddir[1] - oz * oy * ddir[2]) * invsum32;
+            dmean[2] += (-ox * oz * ddir[0] - oy * oz * ddir[1] + (sum2 - oz * oz) * ddir[2]) * invsum32;
+        }
+        // ---- cov3D -> scale / rotation (backward.cu:304-367), no normalisation Jacobian (A.3-Q6)
+        if (p.scales != nullptr) {
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            // R[c][r] column-major as in the forward
+            const float R[3][3] = {
+                {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+            const float s[3] = {p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
+            // M[c][r] = s_r R[c][r];  dL_dSigma symmetric with halved off-diagonals
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            // dL_dM = 2 M dL_dSigma : dL_dM[c][r] = 2 sum_k M[k][r] dS[c][k]
+            float dM[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                    dM[c][rr] = 2.0f * (s[rr] * R[0][rr] * dS[c][0] + s[rr] * R[1][rr] * dS[c][1] + s[rr] * R[2][rr] * dS[c][2]);
+            // dL_dMt[a][b] = dL_dM[b][a];  Rt[a][b] = R[b][a]
+            // dL_dscale_a = dot(Rt[a], dL_dMt[a]) = sum_b R[b][a] dM[b][a]
+#pragma unroll
+            for (int a = 0; a < 3; a++) dscale[a] = R[0][a] * dM[0][a] + R[1][a] * dM[1][a] + R[2][a] * dM[2][a];
+            // dL_dMt[a] *= s_a
+            float Mt[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 3; b2++) Mt[a][b2] = dM[b2][a] * s[a];
+            drot[0] = 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
+            drot[1] = 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r * (Mt[1][2] - Mt[2][1]) - 4 * x * (Mt[2][2] + Mt[1][1]);
+            drot[2] = 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) - 4 * y * (Mt[2][2] + Mt[0][0]);
+            drot[3] = 2 * r * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) - 4 * z * (Mt[1][1] + Mt[0][0]);
+        }
+    } else if (p.dL_dsh != nullptr) {
+        if (dsh4 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) dsh4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
+            for (int k = 0; k < p.M * 3; k++) dsh[k] = 0.f;
+        }
+    }
+
+    p.dL_dmean3D[3 * idx + 0] = dmean[0]; p.dL_dmean3D[3 * idx + 1] = dmean[1]; p.dL_dmean3D[3 * idx + 2] = dmean[2];
+    if (p.dL_dcov3D != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) p.dL_dcov3D[6 * idx + i] = dcov[i];
+    }
+    if (p.dL_dscale != nullptr) {
+        p.dL_dscale[3 * idx + 0] = dscale[0]; p.dL_dscale[3 * idx + 1] = dscale[1]; p.dL_dscale[3 * idx + 2] = dscale[2];
+    }
+    if (p.dL_drot != nullptr)
+        reinterpret_cast<float4*>(p.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+}
+
+}  // namespace
+
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
+{
+    if (p.P <= 0) return;
+    preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+}
+
+void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s)
+{
+    if (p.P <= 0) return;
+    preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
+                         float min_depth, float max_depth, uint8_t* present, cudaStream_t s)
+{
+    if (P <= 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, proj, min_depth, max_depth, present);
+}

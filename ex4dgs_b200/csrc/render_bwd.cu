@@ -1,0 +1,251 @@
+// Per-tile backward of the alpha compositing for sm_100a.
+//
+// Behavioural spec: cuda_rasterizer/backward.cu:426-682 (renderCUDA): back-to-front over the
+// tile's list, recomputing alpha and T, producing per-Gaussian gradients w.r.t. 2D mean (x, y and
+// the depth slot z), conic, opacity, colour and dir3D - including the reference's deviations from
+// the true derivative (Q3 depth term added before the `*= T`, Q4 cumulative
+// dL_dacc *= T entering only opacity, Q5 no alpha-gradient from flow).
+//
+// B200 design (DESIGN.md "render backward"):
+//  * the reference issues 14 float atomicAdd per contributing (pixel, splat) pair
+//    (backward.cu:613-679).  Here the 13 distinct values of a splat are first reduced across the
+//    32 pixels of a warp with a 16-value butterfly (16 SHFL instead of 13x5), the 8 warps of the
+//    tile deposit their partial sums in private shared-memory slices (no shared atomics), and one
+//    thread per (splat, 4-value group) folds the 8 slices and issues a single 16-byte vector
+//    reduction (REDG.E.ADD.F32x4) into a 64-byte per-Gaussian accumulator: at most 4 global
+//    reductions per (tile, splat) instead of 14 per (pixel, splat);
+//  * traversal starts at the tile's largest `n_contrib` instead of the end of the range
+//    (backward.cu:552-577 re-loads the whole range and skips entries one by one);
+//  * splat records are gathered with 16-byte asynchronous copies one sub-batch ahead.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSub = 64;   // splats per sub-batch
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// Reduce 16 per-lane values over the warp; afterwards lane L holds the total of value
+// k(L) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of L (both lanes of a pair hold the same total).
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float mine = hi ? v[i + 8] : v[i];
+        const float other = hi ? v[i] : v[i + 8];
+        v[i] = mine + __shfl_xor_sync(full, other, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float mine = hi ? v[i + 4] : v[i];
+        const float other = hi ? v[i] : v[i + 4];
+        v[i] = mine + __shfl_xor_sync(full, other, 8);
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float mine = hi ? v[i + 2] : v[i];
+        const float other = hi ? v[i] : v[i + 2];
+        v[i] = mine + __shfl_xor_sync(full, other, 4);
+    }
+    hi = lane & 2;
+    {
+        const float mine = hi ? v[1] : v[0];
+        const float other = hi ? v[0] : v[1];
+        v[0] = mine + __shfl_xor_sync(full, other, 2);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+    return v[0];
+}
+
+__global__ void __launch_bounds__(256, 2) render_bwd_kernel(const __grid_constant__ RenderParams p)
+{
+    __shared__ float4 s_rec[2][kSub * 3];
+    __shared__ __align__(16) float s_part[8][kSub][16];
+    __shared__ unsigned long long s_mask[8];
+    __shared__ int s_start;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.y * p.grid_x + blockIdx.x;
+    const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
+    const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = pix_x < p.W && pix_y < p.H;
+    const int pix_id = p.W * pix_y + pix_x;
+    const size_t HW = (size_t)p.H * p.W;
+
+    const uint2 range = p.ranges[tile];
+    if (tid == 0) s_start = 0;
+    __syncthreads();
+
+    float pxf = (float)pix_x, pyf = (float)pix_y;
+    float T_final = 0.f, final_acc = 0.f, final_depth = 0.f;
+    int last_contributor = 0;
+    float dL_ddepth = 0.f, dL_dacc = 0.f;
+    float dflow0 = 0.f, dflow1 = 0.f, dflow2 = 0.f;
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f;
+    if (inside) {
+        const float2 so = __ldg(p.subpixel_offset + pix_id);
+        pxf = fa(pxf, so.x);
+        pyf = fa(pyf, so.y);
+        T_final = p.final_T[pix_id];
+        last_contributor = (int)p.n_contrib[pix_id];
+        final_acc = __ldg(p.out_acc + pix_id);
+        final_depth = __ldg(p.out_depth + pix_id);
+        dL_ddepth = __ldg(p.dL_ddepth + pix_id);
+        if (final_acc > 0.0f) {
+            dL_ddepth = dL_ddepth / final_acc;
+            dflow0 = __ldg(p.dL_dflow + pix_id) / final_acc;
+            dflow1 = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
+            dflow2 = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
+            dL_dacc = __ldg(p.dL_dacc + pix_id);
+        }
+        dpix0 = __ldg(p.dL_dpix + pix_id);
+        dpix1 = __ldg(p.dL_dpix + HW + pix_id);
+        dpix2 = __ldg(p.dL_dpix + 2 * HW + pix_id);
+    }
+    {
+        const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+        if (lane == 0 && wmax > 0) atomicMax(&s_start, wmax);
+    }
+    __syncthreads();
+    const int start = s_start;            // positions >= start contribute to no pixel of the tile
+    if (start == 0) return;
+    const int rounds = (start + kSub - 1) / kSub;
+
+    const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
+    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
+    float T = T_final;
+    float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
+    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
+
+    // staging: thread -> (splat jj, 16-byte part v)
+    const int st_j = tid >> 2, st_v = tid & 3;
+    auto list_id = [&](int r) -> int {
+        const int q = start - 1 - (r * kSub + st_j);
+        return (q >= 0 && st_v < 3) ? (int)__ldg(p.point_list + range.x + q) : -1;
+    };
+    auto stage = [&](int buf, int id) {
+        if (id >= 0) cp_async16(&s_rec[buf][st_j * 3 + st_v], reinterpret_cast<const float4*>(p.rec + id) + st_v);
+    };
+    stage(0, list_id(0));
+    cp_async_commit();
+    int id_next = (rounds > 1) ? list_id(1) : -1;
+
+    for (int r = 0; r < rounds; r++) {
+        cp_async_wait_all();
+        __syncthreads();                       // (A) batch r landed; s_part / buffer (r+1)&1 free
+        if (r + 1 < rounds) {
+            stage((r + 1) & 1, id_next);
+            cp_async_commit();
+            id_next = (r + 2 < rounds) ? list_id(r + 2) : -1;
+        }
+        const float4* __restrict__ s = s_rec[r & 1];
+        const int cnt = min(kSub, start - r * kSub);
+        unsigned long long mask = 0ull;
+        for (int j = 0; j < cnt; j++) {
+            const int q = start - 1 - (r * kSub + j);
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = 0.f;
+            bool contributes = false;
+            if (q < last_contributor) {
+                const float4 a = s[j * 3 + 0];
+                const float4 b = s[j * 3 + 1];
+                const float dx = fa(a.x, -pxf), dy = fa(a.y, -pyf);
+                const float power = ff(ff(dx, fm(dx, b.x), fm(fm(b.z, dy), dy)), -0.5f, -fm(fm(b.y, dx), dy));
+                if (!(power > 0.0f) && !(power < a.w)) {
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, fm(b.w, G));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        contributes = true;
+                        const float4 c = s[j * 3 + 2];
+                        T = T / (1.f - alpha);
+                        const float w = alpha * T;               // dchannel_dcolor
+                        float dL_dalpha = 0.0f;
+                        const float dep = a.z;
+                        if ((dep > p.min_depth) & (w > 0.0f)) {
+                            v[2] = dL_ddepth * w;
+                            dL_dalpha += (final_depth - dep) * dL_ddepth * T;
+                        }
+                        accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
+                        accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
+                        accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
+                        last_c0 = c.x; last_c1 = c.y; last_c2 = c.z;
+                        dL_dalpha += (c.x - accum_rec0) * dpix0;
+                        dL_dalpha += (c.y - accum_rec1) * dpix1;
+                        dL_dalpha += (c.z - accum_rec2) * dpix2;
+                        v[8] = w * dpix0; v[9] = w * dpix1; v[10] = w * dpix2;
+                        v[12] = w * dflow0; v[13] = w * dflow1; v[14] = w * dflow2;
+                        dL_dalpha *= T;
+                        dL_dacc *= T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        const float dL_dG = b.w * dL_dalpha;
+                        const float gdx = G * dx, gdy = G * dy;
+                        const float dG_ddelx = -gdx * b.x - gdy * b.y;
+                        const float dG_ddely = -gdy * b.z - gdx * b.y;
+                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                        v[1] = dL_dG * dG_ddely * ddely_dy;
+                        v[4] = -0.5f * gdx * dx * dL_dG;
+                        v[5] = -0.5f * gdx * dy * dL_dG;
+                        v[6] = -0.5f * gdy * dy * dL_dG;
+                        v[3] = G * dL_dalpha + G * dL_dacc;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, contributes)) {
+                const float tot = butterfly16(v, lane);
+                if (!(lane & 1)) {
+                    const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    s_part[warp][j][k] = tot;
+                }
+                mask |= 1ull << j;
+            }
+        }
+        if (lane == 0) s_mask[warp] = mask;
+        __syncthreads();                       // (B) partial sums of all warps complete
+        {
+            const int jj = tid >> 2, qd = tid & 3;
+            if (jj < cnt) {
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool any = false;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    if ((s_mask[w] >> jj) & 1ull) {
+                        const float4 t = *reinterpret_cast<const float4*>(&s_part[w][jj][4 * qd]);
+                        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+                        any = true;
+                    }
+                }
+                if (any) {
+                    const int id = __float_as_int(s[jj * 3 + 2].w);
+                    red_add_v4(reinterpret_cast<float*>(p.gacc + id) + 4 * qd, sum);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
+{
+    dim3 grid(grid_x, grid_y, 1);
+    render_bwd_kernel<<<grid, 256, 0, s>>>(p);
+}

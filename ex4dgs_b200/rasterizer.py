@@ -1,0 +1,328 @@
+"""Python surface of the rasterizer: the reference's L1 API, bound to the C ABI with ctypes.
+
+Mirrors submodules/diff_gaussian_rasterization_df/diff_gaussian_rasterization_df/__init__.py
+(reference file:line in each docstring) - same class names, argument names and order, output
+tuple order, gradient slots, empty-tensor conventions and exceptions - so that
+gaussian_renderer/__init__.py:15,41-109 runs unchanged against it.  PyTorch is used only for
+device memory, streams and autograd plumbing; all compute is in libex4dgs_raster.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+# Process-wide default for the exact-output tile culling (include/ex4dgs_raster.h,
+# EX4DGS_FLAG_TILE_CULL).  Outputs and gradients are identical either way; with 0 the internal
+# tile lists are bit-identical to the reference's.  Override with EX4DGS_TILE_CULL=0/1.
+_DEFAULT_FLAGS = int(os.environ.get("EX4DGS_TILE_CULL", "0")) & 1
+
+
+def set_default_flags(tile_cull: bool) -> None:
+    global _DEFAULT_FLAGS
+    _DEFAULT_FLAGS = _lib.FLAG_TILE_CULL if tile_cull else 0
+
+
+def get_default_flags() -> int:
+    return _DEFAULT_FLAGS
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    """__init__.py:18-20"""
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
+def _ptr(t):
+    """Device pointer of a tensor, NULL for the reference's 'absent' 0-element tensors
+    (rasterize_points.cu passes data_ptr of a CPU empty tensor == nullptr)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, dev) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if t.device != dev:
+        raise RuntimeError("ex4dgs_b200: tensor on %s, expected %s" % (t.device, dev))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Scratch:
+    """Allocator callbacks handing out torch byte tensors (the C form of
+    rasterize_points.cu:27-33 resizeFunctional)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensors = [None, None, None]
+        self.cbs = [_lib.ALLOC_FN(self._make(i)) for i in range(3)]
+
+    def _make(self, i):
+        def alloc(_user, nbytes):
+            t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            self.tensors[i] = t
+            return t.data_ptr()
+        return alloc
+
+
+def rasterize_gaussians(means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    """__init__.py:22-45"""
+    return _RasterizeGaussians.apply(means3D, means2D, dir3D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """__init__.py:47-178.  forward returns (color, radii, depth, flow, acc, idxs); backward returns
+    the 10 slots (means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
+    cov3Ds_precomp, None)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:62-64
+        if not means3D.is_cuda:
+            raise RuntimeError("ex4dgs_b200: the rasterizer is CUDA-only (as is the reference, "
+                               "rasterize_points.cu:80); got a %s tensor" % means3D.device)
+        lib = _lib.load()
+        dev = means3D.device
+        flags = int(getattr(rs, "_flags", _DEFAULT_FLAGS))
+
+        args = (rs.bg, means3D, dir3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
+                rs.subpixel_offset, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos,
+                rs.prefiltered, rs.min_depth, rs.max_depth, rs.debug)
+        cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None     # __init__.py:91-93
+
+        P = means3D.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+        means3D_c = _f32c(means3D, dev)
+        dir3D_c = _f32c(dir3D, dev)
+        sh_c = _f32c(sh, dev)
+        colors_c = _f32c(colors_precomp, dev)
+        opac_c = _f32c(opacities, dev)
+        scales_c = _f32c(scales, dev)
+        rot_c = _f32c(rotations, dev)
+        cov_c = _f32c(cov3Ds_precomp, dev)
+        bg = _f32c(rs.bg, dev)
+        view = _f32c(rs.viewmatrix, dev)
+        proj = _f32c(rs.projmatrix, dev)
+        campos = _f32c(rs.campos, dev)
+        sub = _f32c(rs.subpixel_offset, dev)
+        M = sh_c.size(1) if sh_c.numel() != 0 else 0        # rasterize_points.cu:92-96
+
+        iopt = dict(dtype=torch.int32, device=dev)
+        fopt = dict(dtype=torch.float32, device=dev)
+        if P == 0:
+            # rasterize_points.cu:73-90: nothing runs, outputs keep their fill values
+            color = torch.zeros(3, H, W, **fopt)
+            radii = torch.zeros(0, **iopt)
+            depth = torch.zeros(1, H, W, **fopt)
+            acc = torch.zeros(1, H, W, **fopt)
+            flow = torch.zeros(3, H, W, **fopt)
+            idxs = torch.full((1, H, W), -1, **iopt)
+            empty = torch.empty(0, dtype=torch.uint8, device=dev)
+            ctx.raster_settings = rs
+            ctx.num_rendered = 0
+            ctx.flags = flags
+            ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, empty, empty, empty, depth, acc)
+            return color, radii, depth, flow, acc, idxs
+
+        color = torch.empty(3, H, W, **fopt)
+        radii = torch.empty(P, **iopt)
+        depth = torch.empty(1, H, W, **fopt)
+        acc = torch.empty(1, H, W, **fopt)
+        flow = torch.empty(3, H, W, **fopt)
+        idxs = torch.empty(1, H, W, **iopt)
+        scratch = _Scratch(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        try:
+            with torch.cuda.device(dev):
+                R = lib.ex4dgs_forward(
+                    scratch.cbs[0], None, scratch.cbs[1], None, scratch.cbs[2], None,
+                    P, int(rs.sh_degree), int(M),
+                    _ptr(bg), W, H,
+                    _ptr(means3D_c), _ptr(dir3D_c), _ptr(sh_c), _ptr(colors_c),
+                    _ptr(opac_c), _ptr(scales_c), float(rs.scale_modifier), _ptr(rot_c),
+                    _ptr(cov_c), _ptr(view), _ptr(proj), _ptr(campos),
+                    float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), int(bool(rs.prefiltered)),
+                    _ptr(color), float(rs.min_depth), float(rs.max_depth), _ptr(depth), _ptr(acc), _ptr(flow),
+                    _ptr(idxs), _ptr(radii), int(bool(rs.debug)), flags, C.c_void_p(stream))
+            if R < 0:
+                raise RuntimeError("ex4dgs_forward failed (%d): %s" % (R, _lib.last_error()))
+        except Exception as ex:
+            if rs.debug:                                             # __init__.py:94-99
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            raise ex
+
+        geomBuffer, binningBuffer, imgBuffer = scratch.tensors
+        ctx.raster_settings = rs
+        ctx.num_rendered = int(R)
+        ctx.flags = flags
+        ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c,
+                              geomBuffer, binningBuffer, imgBuffer, depth, acc)
+        ctx.mark_non_differentiable(radii, idxs)
+        return color, radii, depth, flow, acc, idxs
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_flow, grad_out_acc, grad_out_idx):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
+         geomBuffer, binningBuffer, imgBuffer, depth, acc) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = means3D.device
+        P = means3D.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+        M = sh.size(1) if sh.numel() != 0 else 0
+        fopt = dict(dtype=torch.float32, device=dev)
+
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, depth, acc, rs.min_depth, rs.max_depth,
+                rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                rs.kernel_size, rs.subpixel_offset, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc,
+                sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug)
+        cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None   # __init__.py:151-153
+
+        use_sr = scales.numel() != 0
+        g_means2D = torch.empty(P, 3, **fopt)
+        g_colors = torch.empty(P, 3, **fopt)
+        g_opac = torch.empty(P, 1, **fopt)
+        g_means3D = torch.empty(P, 3, **fopt)
+        g_cov3D = torch.empty(P, 6, **fopt) if not use_sr else torch.empty(0, **fopt)
+        g_sh = torch.empty(P, M, 3, **fopt)
+        g_scales = torch.empty(P, 3, **fopt) if use_sr else torch.zeros(P, 3, **fopt)
+        g_rot = torch.empty(P, 4, **fopt) if use_sr else torch.zeros(P, 4, **fopt)
+        g_dir = torch.empty(P, 3, **fopt)
+
+        if P != 0:
+            gc = _f32c(grad_out_color, dev)
+            gd = _f32c(grad_out_depth, dev)
+            gf = _f32c(grad_out_flow, dev)
+            ga = _f32c(grad_out_acc, dev)
+            bg = _f32c(rs.bg, dev)
+            view = _f32c(rs.viewmatrix, dev)
+            proj = _f32c(rs.projmatrix, dev)
+            campos = _f32c(rs.campos, dev)
+            sub = _f32c(rs.subpixel_offset, dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            try:
+                with torch.cuda.device(dev):
+                    rc = lib.ex4dgs_backward(
+                        P, int(rs.sh_degree), int(M), int(ctx.num_rendered),
+                        _ptr(bg), W, H,
+                        _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
+                        _ptr(scales), float(rs.scale_modifier), _ptr(rotations),
+                        _ptr(depth), _ptr(acc), float(rs.min_depth), float(rs.max_depth),
+                        _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos),
+                        float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), _ptr(radii),
+                        _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+                        _ptr(gc), _ptr(gd), _ptr(gf), _ptr(ga),
+                        _ptr(g_means2D), _ptr(g_opac), _ptr(g_colors), _ptr(g_means3D), _ptr(g_cov3D),
+                        _ptr(g_sh), _ptr(g_scales) if use_sr else None, _ptr(g_rot) if use_sr else None, _ptr(g_dir),
+                        int(bool(rs.debug)), int(ctx.flags), C.c_void_p(stream))
+                if rc < 0:
+                    raise RuntimeError("ex4dgs_backward failed (%d): %s" % (rc, _lib.last_error()))
+            except Exception as ex:
+                if rs.debug:                                         # __init__.py:156-159
+                    torch.save(cpu_args, "snapshot_bw.dump")
+                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+
+        # slots whose forward input was "absent" get None (autograd ignores them in the reference too)
+        return (g_means3D, g_means2D, g_dir,
+                g_sh if M != 0 else None,
+                g_colors if colors_precomp.numel() != 0 else None,
+                g_opac,
+                g_scales if use_sr else None,
+                g_rot if use_sr else None,
+                g_cov3D if not use_sr else None,
+                None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    """__init__.py:180-196 (field order is part of the contract)."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    kernel_size: float
+    subpixel_offset: torch.Tensor
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    min_depth: float
+    max_depth: float
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    """__init__.py:198-251."""
+
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Frustum test per Gaussian (rasterizer_impl.cu:54-68).  The reference's Python wrapper
+        passes 4 arguments to a 5-argument native function (__init__.py:207-211 vs
+        rasterize_points.h:78-83) and therefore raises TypeError; this one works and uses the
+        settings' min_depth / max_depth."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            lib = _lib.load()
+            dev = positions.device
+            if not positions.is_cuda:
+                raise RuntimeError("ex4dgs_b200: markVisible is CUDA-only")
+            pos = _f32c(positions, dev)
+            P = pos.size(0)
+            present = torch.zeros(P, dtype=torch.bool, device=dev)
+            if P != 0:
+                view = _f32c(rs.viewmatrix, dev)
+                proj = _f32c(rs.projmatrix, dev)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                with torch.cuda.device(dev):
+                    rc = lib.ex4dgs_mark_visible(P, _ptr(pos), _ptr(view), _ptr(proj), float(rs.min_depth),
+                                                 float(rs.max_depth), present.data_ptr(), C.c_void_p(stream))
+                if rc < 0:
+                    raise RuntimeError("ex4dgs_mark_visible failed: " + _lib.last_error())
+        return present
+
+    def forward(self, means3D, means2D, dir3D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        if dir3D is None:
+            dir3D = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, dir3D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings)

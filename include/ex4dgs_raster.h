@@ -1,0 +1,230 @@
+/*
+ * ex4dgs_raster.h - C ABI of the B200-native differentiable 4D-Gaussian rasterizer.
+ *
+ * Drop-in boundary for the hot path of juno181/Ex4DGS: every entry point below replaces one
+ * method of the reference's native interface `CudaRasterizer::Rasterizer`
+ * (submodules/diff_gaussian_rasterization_df/cuda_rasterizer/rasterizer.h:23-107), which the
+ * reference binds to Python through rasterize_points.cu:36-259 + ext.cpp:15-19.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and scalars only; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer (float32 unless stated) valid on the current CUDA device,
+ *     except callbacks / `user` cookies / the stream handle.
+ *   - "absent" optional inputs are passed as NULL (the reference passes the data_ptr of a CPU
+ *     0-element tensor, which is nullptr: rasterize_points.cu:103-130, forward.cu:218,254).
+ *   - matrices are 16 floats in the reference's transposed storage (auxiliary.h:68-87).
+ *   - all work is enqueued on `stream` (a cudaStream_t cast to void*; NULL = legacy default stream,
+ *     which is what the reference uses).  ex4dgs_forward performs ONE blocking 4-byte read-back
+ *     (num_rendered) exactly like rasterizer_impl.cu:299.
+ *   - functions return a negative ex4dgs_status on failure; ex4dgs_last_error() has the message.
+ *   - the library is re-entrant per device/stream: no global mutable state besides the
+ *     thread-local error string.
+ */
+#ifndef EX4DGS_RASTER_H_
+#define EX4DGS_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EX4DGS_ABI_VERSION 1
+
+typedef enum ex4dgs_status {
+    EX4DGS_OK = 0,
+    EX4DGS_ERR_INVALID = -1,   /* bad argument combination (mirrors the Python-side Exceptions)   */
+    EX4DGS_ERR_CUDA = -2,      /* CUDA runtime error (message carries cudaGetErrorString)          */
+    EX4DGS_ERR_ALLOC = -3,     /* an allocator callback returned NULL                              */
+    EX4DGS_ERR_UNSUPPORTED = -4
+} ex4dgs_status;
+
+/* flags for ex4dgs_forward / ex4dgs_backward (must be identical in both calls of one frame) */
+#define EX4DGS_FLAG_NONE 0u
+/* Drop (Gaussian,tile) instances that provably cannot reach alpha >= 1/255 in any pixel of the
+ * tile.  Outputs (image, depth, acc, flow, idx, radii, all gradients) are unchanged; only the
+ * internal tile lists get shorter.  With the flag clear the tile lists (point_list, ranges,
+ * n_contrib) are bit-identical to the reference's (rasterizer_impl.cu:72-140). */
+#define EX4DGS_FLAG_TILE_CULL 1u
+
+/* Resizable scratch buffers, the C form of `std::function<char*(size_t)>` in
+ * rasterizer.h:38-40 / rasterize_points.cu:27-33: called at most once per buffer per forward;
+ * must return a device pointer to at least `nbytes` bytes, 256-byte aligned, that stays valid
+ * until the matching ex4dgs_backward (the Python layer keeps the torch byte tensors alive
+ * through autograd exactly like ctx.save_for_backward in __init__.py:106). */
+typedef void* (*ex4dgs_alloc_fn)(void* user, size_t nbytes);
+
+/* ---- replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:37-66, rasterizer_impl.cu:204-363)
+ * Returns num_rendered (R >= 0) = number of (Gaussian,tile) instances in the sorted tile lists,
+ * or a negative ex4dgs_status.
+ *   P            number of Gaussians;  D active SH degree (0..3);  M SH coefficients per Gaussian
+ *   background   [3]           means3D [P,3]      dir3D [P,3] (must be non-NULL when P > 0)
+ *   shs          [P,M,3] or NULL (then colors_precomp [P,3] must be given)
+ *   opacities    [P]           scales [P,3] + rotations [P,4]  xor  cov3D_precomp [P,6]
+ *   subpixel_offset [H,W,2]
+ *   outputs (every element is written by the call, no pre-fill needed):
+ *     out_color [3,H,W], out_depth [H,W], out_acc [H,W], out_flow [3,H,W], out_idx [H,W] (int32,
+ *     -1 = no contributor), radii [P] (int32, 0 = culled)
+ */
+int ex4dgs_forward(
+    ex4dgs_alloc_fn geometryBuffer, void* geometry_user,
+    ex4dgs_alloc_fn binningBuffer, void* binning_user,
+    ex4dgs_alloc_fn imageBuffer, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* dir3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    float kernel_size,
+    const float* subpixel_offset,
+    int prefiltered,
+    float* out_color,
+    float min_depth,
+    float max_depth,
+    float* out_depth,
+    float* out_acc,
+    float* out_flow,
+    int* out_idx,
+    int* radii,
+    int debug,
+    unsigned flags,
+    void* stream);
+
+/* ---- replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:68-106, rasterizer_impl.cu:367-486)
+ * geom/binning/image buffers are the ones handed out by the allocator callbacks of the matching
+ * forward; R is its return value.  Gradient outputs (all fully written, no pre-fill needed):
+ *   dL_dmean2D [P,3]  dL_dopacity [P]  dL_dcolor [P,3]  dL_dmean3D [P,3]  dL_dsh [P,M,3] (NULL if M==0)
+ *   dL_dscale [P,3]  dL_drot [P,4] (NULL when cov3D_precomp is used)  dL_dcov3D [P,6] (may be NULL)
+ *   dL_ddir [P,3]
+ * The reference's intermediate dL_dconic [P,2,2] (rasterize_points.cu:181) lives inside the
+ * scratch buffers here.  The backward reproduces the reference's deviations from the true
+ * derivative.  Returns EX4DGS_OK or a negative status. */
+int ex4dgs_backward(
+    int P, int D, int M, int R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* acc_depth,      /* forward out_depth */
+    const float* acc,            /* forward out_acc   */
+    float min_depth,
+    float max_depth,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    float kernel_size,
+    const float* subpixel_offset,
+    const int* radii,
+    void* geom_buffer,
+    void* binning_buffer,
+    void* image_buffer,
+    const float* dL_dpix,        /* [3,H,W] */
+    const float* dL_ddepth,      /* [H,W]   */
+    const float* dL_dflow,       /* [3,H,W] */
+    const float* dL_dacc,        /* [H,W]   */
+    float* dL_dmean2D,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    float* dL_ddir,
+    int debug,
+    unsigned flags,
+    void* stream);
+
+/* ---- replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:27-35, rasterizer_impl.cu:143-159)
+ * present [P] bytes (0/1) = in_frustum (auxiliary.h:267-294). */
+int ex4dgs_mark_visible(
+    int P,
+    const float* means3D,
+    const float* viewmatrix,
+    const float* projmatrix,
+    float min_depth,
+    float max_depth,
+    uint8_t* present,
+    void* stream);
+
+/* ---- fused model front-end ("next" row N1 of SURVEY.md section 8f): the per-frame getters of
+ * CGaussianModel (scene/c_gaussian_model.py:170-215,330-375; utils/interpolations.py:33-61,81-93)
+ * evaluated in one pass straight from the model's native static / dynamic tensors into the flat
+ * [P,.] rasterizer inputs (static Gaussians first), replacing ~40 PyTorch kernels and five
+ * torch.cat copies per frame.
+ *   static : xyz [Ns,3], xyz_disp [Ns,3], rotation [Ns,4] (raw), scaling [Ns,3] (log), opacity [Ns] (logit)
+ *   dynamic: xyz_motion [Nd,K,3], rotation_motion [Nd,K,4], scaling_motion [Nd,3] (log),
+ *            opacity_motion [Nd] (logit), opacity_center [Nd,2], opacity_var [Nd,2]
+ *   t timestamp; duration, interval, time_shift, var_min (= var_pad/interval) as in the model.
+ *   outputs: means3D [P,3], rotations [P,4], scales [P,3], opacities [P]   (P = Ns + Nd)
+ */
+int ex4dgs_frontend_forward(
+    int Ns, int Nd, int K,
+    const float* xyz, const float* xyz_disp, const float* rotation,
+    const float* scaling, const float* opacity,
+    const float* xyz_motion, const float* rotation_motion, const float* scaling_motion,
+    const float* opacity_motion, const float* opacity_center, const float* opacity_var,
+    float t, float duration, float interval, float time_shift, float var_min,
+    float* means3D, float* rotations, float* scales, float* opacities,
+    void* stream);
+
+/* Backward of ex4dgs_frontend_forward.  Gradient outputs for the keyframe tensors
+ * (dL_dxyz_motion [Nd,K,3], dL_drotation_motion [Nd,K,4]) are fully written (zeros outside the
+ * 4 / 2 keyframes that the frame touches). */
+int ex4dgs_frontend_backward(
+    int Ns, int Nd, int K,
+    const float* xyz_disp_unused, const float* rotation_motion,
+    const float* scaling, const float* opacity,
+    const float* scaling_motion, const float* opacity_motion,
+    const float* opacity_center, const float* opacity_var,
+    float t, float duration, float interval, float time_shift, float var_min,
+    const float* dL_dmeans3D, const float* dL_drotations, const float* dL_dscales, const float* dL_dopacities,
+    float* dL_dxyz, float* dL_dxyz_disp, float* dL_drotation, float* dL_dscaling, float* dL_dopacity,
+    float* dL_dxyz_motion, float* dL_drotation_motion, float* dL_dscaling_motion,
+    float* dL_dopacity_motion, float* dL_dopacity_center, float* dL_dopacity_var,
+    void* stream);
+
+/* ---- introspection (used by the parity tests to look inside the opaque scratch buffers) ------- */
+typedef struct ex4dgs_array_desc {
+    const char* name;    /* e.g. "point_list"                                  */
+    int buffer;          /* 0 = geometry, 1 = binning, 2 = image               */
+    size_t offset;       /* byte offset from the (256-B aligned) buffer base   */
+    size_t elem_size;    /* bytes per element                                  */
+    size_t count;        /* number of elements                                 */
+} ex4dgs_array_desc;
+
+/* Fills `out` (capacity `max`) with the layout the library uses for (P, R, width, height);
+ * returns the number of arrays described. */
+int ex4dgs_describe_buffers(int P, int R, int width, int height,
+                            ex4dgs_array_desc* out, int max);
+
+/* Size in bytes each allocator callback will be asked for. */
+size_t ex4dgs_geometry_bytes(int P);
+size_t ex4dgs_binning_bytes(int R);
+size_t ex4dgs_image_bytes(int width, int height);
+
+int ex4dgs_abi_version(void);
+const char* ex4dgs_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EX4DGS_RASTER_H_ */

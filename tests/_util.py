@@ -1,0 +1,225 @@
+"""Shared helpers for the parity tests (test infrastructure only).
+
+run_impl() pushes one seeded scene through a rasterizer implementation's public API
+(GaussianRasterizer of either ex4dgs_b200 or the compiled reference in oracle/_ref) and returns
+outputs, gradients and the internal tile lists as numpy arrays.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ex4dgs_b200 import synth  # noqa: E402
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_gpu() -> bool:
+    return torch.cuda.is_available()
+
+
+_ref_mod = None
+
+
+def reference_module():
+    """The UNMODIFIED reference package built by oracle/build_ref.py, or None."""
+    global _ref_mod
+    if _ref_mod is not None:
+        return _ref_mod
+    so = os.path.join(REF_DIR, "diff_gaussian_rasterization_df", "_C.so")
+    if not os.path.exists(so):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_diff_gaussian_rasterization_df",
+        os.path.join(REF_DIR, "diff_gaussian_rasterization_df", "__init__.py"),
+        submodule_search_locations=[os.path.join(REF_DIR, "diff_gaussian_rasterization_df")])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_diff_gaussian_rasterization_df"] = mod
+    spec.loader.exec_module(mod)
+    _ref_mod = mod
+    return mod
+
+
+def ours_module():
+    import ex4dgs_b200
+    return ex4dgs_b200
+
+
+def settings_for(mod, sc: synth.Scene, dev, subpixel: Optional[torch.Tensor] = None, debug=False):
+    cam = sc.cam
+    if subpixel is None:
+        subpixel = torch.zeros(cam.H, cam.W, 2)
+    return mod.GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        kernel_size=cam.kernel_size, subpixel_offset=subpixel.to(dev), bg=sc.bg.to(dev),
+        scale_modifier=1.0, viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev),
+        sh_degree=sc.sh_degree, campos=cam.campos.to(dev), prefiltered=False,
+        min_depth=cam.min_depth, max_depth=cam.max_depth, debug=debug)
+
+
+def _ref_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
+    """Views into the reference's opaque buffers (layout: rasterizer_impl.cu:161-200, 128-byte
+    aligned sub-allocations in declaration order)."""
+    saved = grad_fn.saved_tensors
+    geom, binning, img = saved[7], saved[8], saved[9]
+    R = int(grad_fn.num_rendered)
+
+    def carve(buf, specs):
+        out, off = {}, 0
+        base = buf.data_ptr()
+        for name, dtype, count in specs:
+            a = (base + off + 127) & ~127
+            off = a - base
+            nbytes = np.dtype(dtype).itemsize * count
+            out[name] = buf[off:off + nbytes].cpu().numpy().view(dtype).copy()
+            off += nbytes
+        return out
+
+    g = carve(geom, [("depths", np.float32, P), ("clamped", np.uint8, 3 * P), ("internal_radii", np.int32, P),
+                     ("means2D", np.float32, 2 * P), ("cov3D", np.float32, 6 * P),
+                     ("conic_opacity", np.float32, 4 * P), ("rgb", np.float32, 3 * P),
+                     ("tiles_touched", np.uint32, P)])
+    b = carve(binning, [("point_list", np.uint32, R), ("point_list_unsorted", np.uint32, R),
+                        ("point_list_keys", np.uint64, R)]) if R > 0 else \
+        {"point_list": np.zeros(0, np.uint32), "point_list_keys": np.zeros(0, np.uint64)}
+    im = carve(img, [("final_T", np.float32, W * H), ("n_contrib", np.uint32, W * H), ("ranges", np.uint32, 2 * W * H)])
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    return dict(R=R, depths=g["depths"], means2D=g["means2D"].reshape(P, 2), conic_opacity=g["conic_opacity"].reshape(P, 4),
+                rgb=g["rgb"].reshape(P, 3), clamped=g["clamped"].reshape(P, 3), cov3D=g["cov3D"].reshape(P, 6),
+                tiles_touched=g["tiles_touched"], point_list=b["point_list"], point_list_keys=b["point_list_keys"],
+                final_T=im["final_T"], n_contrib=im["n_contrib"], ranges=im["ranges"][:2 * tiles].reshape(tiles, 2))
+
+
+def _our_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
+    from ex4dgs_b200 import _lib
+    saved = grad_fn.saved_tensors
+    bufs = [saved[7], saved[8], saved[9]]
+    R = int(grad_fn.num_rendered)
+    desc = _lib.describe_buffers(P, R, W, H)
+
+    def view(name, dtype):
+        b, off, es, cnt = desc[name]
+        t = bufs[b]
+        base = t.data_ptr()
+        a = ((base + 255) & ~255) - base
+        raw = t[a + off:a + off + es * cnt].cpu().numpy()
+        return raw.view(dtype).copy()
+
+    rec = view("rec", np.float32).reshape(P, 16)
+    key = view("depth_key", np.uint32)
+    vis = key != 0xFFFFFFFF
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    out = dict(R=R, rec=rec, visible=vis, depth_key=key, tiles_touched=view("tiles_touched", np.uint32),
+               order=view("order", np.uint32), clamped_bits=view("clamped", np.uint8),
+               final_T=view("final_T", np.float32), n_contrib=view("n_contrib", np.uint32),
+               ranges=view("ranges", np.uint32).reshape(tiles, 2), tile_batches=view("tile_batches", np.uint32))
+    if R > 0:
+        out["point_list"] = view("point_list", np.uint32)
+        out["tile_sorted"] = view("tile_sorted", np.uint16)
+    else:
+        out["point_list"] = np.zeros(0, np.uint32)
+        out["tile_sorted"] = np.zeros(0, np.uint16)
+    out["depths"] = rec[:, 2]
+    out["means2D"] = rec[:, 0:2]
+    out["conic_opacity"] = rec[:, 4:8]
+    out["rgb"] = rec[:, 8:11]
+    return out
+
+
+def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Optional[torch.Tensor] = None,
+             use_colors_precomp: bool = False, use_cov3D_precomp: bool = False, intermediates: bool = True,
+             grad_kind: str = "train", is_ref: bool = False) -> Dict[str, np.ndarray]:
+    """One forward (+ backward) through `mod.GaussianRasterizer`; everything returned as numpy."""
+    inp = synth.flat_inputs(sc)
+    P = inp["means3D"].shape[0]
+    cam = sc.cam
+    t = {k: v.to(dev).requires_grad_(grads) for k, v in inp.items()}
+    means2D = torch.zeros(P, 3, device=dev, requires_grad=grads)
+    rs = settings_for(mod, sc, dev, subpixel)
+    rast = mod.GaussianRasterizer(rs)
+    kw = dict(means3D=t["means3D"], means2D=means2D, dir3D=t["dir3D"], opacities=t["opacities"])
+    extra = {}
+    if use_colors_precomp:
+        g = torch.Generator().manual_seed(11)
+        extra["colors"] = torch.rand(P, 3, generator=g).to(dev).requires_grad_(grads)
+        kw["colors_precomp"] = extra["colors"]
+    else:
+        kw["shs"] = t["shs"]
+    if use_cov3D_precomp:
+        # world-space covariances from the same scales / rotations (un-normalised quaternion, like the CUDA code)
+        extra["cov3D"] = cov3d_torch(inp["scales"], inp["rotations"]).to(dev).requires_grad_(grads)
+        kw["cov3D_precomp"] = extra["cov3D"]
+    else:
+        kw["scales"] = t["scales"]
+        kw["rotations"] = t["rotations"]
+    color, radii, depth, flow, acc, idxs = rast(**kw)
+    out = dict(color=color, radii=radii, depth=depth, flow=flow, acc=acc, idxs=idxs)
+    res = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    if intermediates and color.grad_fn is not None:
+        fn = color.grad_fn
+        res["inter"] = (_ref_intermediates if is_ref else _our_intermediates)(fn, P, cam.W, cam.H)
+    if grads:
+        go = synth.grad_outputs(sc)
+        if grad_kind == "all":      # exercise the depth / acc gradient paths too
+            g = torch.Generator().manual_seed(99)
+            go["grad_depth"] = torch.randn(1, cam.H, cam.W, generator=g) * 1e-3
+            go["grad_acc"] = torch.randn(1, cam.H, cam.W, generator=g) * 1e-3
+        torch.autograd.backward([color, depth, flow, acc],
+                                [go["grad_color"].to(dev), go["grad_depth"].to(dev), go["grad_flow"].to(dev), go["grad_acc"].to(dev)])
+        gr = dict(means3D=t["means3D"].grad, means2D=means2D.grad, dir3D=t["dir3D"].grad, opacities=t["opacities"].grad)
+        if use_colors_precomp:
+            gr["colors"] = extra["colors"].grad
+        else:
+            gr["shs"] = t["shs"].grad
+        if use_cov3D_precomp:
+            gr["cov3D"] = extra["cov3D"].grad
+        else:
+            gr["scales"] = t["scales"].grad
+            gr["rotations"] = t["rotations"].grad
+        res["grads"] = {k: v.detach().cpu().numpy() for k, v in gr.items()}
+    if str(dev).startswith("cuda"):
+        torch.cuda.synchronize()
+    return res
+
+
+def cov3d_torch(scales: torch.Tensor, rot: torch.Tensor, mod: float = 1.0) -> torch.Tensor:
+    """Sigma = (S R)^T (S R), un-normalised quaternion, upper triangle [P,6] (forward.cu:128-162)."""
+    r, x, y, z = rot[:, 0], rot[:, 1], rot[:, 2], rot[:, 3]
+    R = torch.stack([
+        1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).reshape(-1, 3, 3)
+    # R[i][k] above is R_glm[i][k] (glm fills columns), and Sigma_glm[c][r] = sum_k s_k^2 R_glm[r][k] R_glm[c][k]
+    S = torch.diag_embed(mod * scales)
+    Mm = R @ S
+    Sig = Mm @ Mm.transpose(1, 2)
+    return torch.stack([Sig[:, 0, 0], Sig[:, 0, 1], Sig[:, 0, 2], Sig[:, 1, 1], Sig[:, 1, 2], Sig[:, 2, 2]], dim=1).contiguous()
+
+
+def rel_err(a: np.ndarray, b: np.ndarray, floor: float) -> float:
+    """max |a-b| / max(|b|, floor)"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def grad_floor(ref: np.ndarray) -> float:
+    """Absolute floor for the 1e-3 relative gradient tolerance: a gradient entry much smaller
+    than the typical magnitude of its tensor is compared absolutely (float atomics in the
+    reference make tiny entries noisy)."""
+    r = np.abs(np.asarray(ref, np.float64))
+    nz = r[r > 0]
+    if nz.size == 0:
+        return 1e-12
+    return float(max(np.percentile(nz, 99) * 1e-2, 1e-12))
