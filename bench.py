@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py - headline metric of BASELINE.json: rasterizer fwd+bwd frames/s at config C3
+(2.0M static+dynamic Gaussians, 1352x1014), plus the render-forward roofline figure.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" = one frame: GaussianRasterizer forward + backward on the pre-interpolated [P,.] tensors
+(the drop-in boundary).  With N GPUs every rank renders its own frame per step
+(frames shard one-per-GPU, Gaussians replicated: weak scaling), the only collective is one NCCL
+all-reduce of the scalar loss in the end-to-end leg.  Prints ONE JSON line (rank 0).
+
+  value   frames/s, inputs resident in HBM, upstream gradients resident (device-timed, max over ranks)
+  e2e     frames/s through the public API with the per-frame HOST inputs (camera + ground-truth image,
+          pinned) copied H2D inside the timed region, L1 loss, backward, loss copied D2H.  The
+          Gaussian parameters are model state and stay resident (as weights do in a training step).
+  roofline  render-forward kernel: algorithmic bytes (56*R_eff + 52*W*H + 8*tiles) / its
+          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (oracle/cpu_raster.c, a port of the reference algorithm: the reference
+          has no CPU path) on one full frame of the same workload, all host threads.
+
+--impl reference runs the UNMODIFIED reference CUDA extension (oracle/_ref, built by
+oracle/build_ref.py) on the same GPU, same workload and step definition; if that build is absent it
+falls back to the CPU oracle port (see DESIGN.md "reference arm").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from ex4dgs_b200 import synth  # noqa: E402
+
+METRIC = "fwd+bwd frames/sec @2.0M Gaussians 1352x1014"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def dist_env():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.06 or ts > t1 + 0.06:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": smax or None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_reference():
+    so = os.path.join(ROOT, "oracle", "_ref", "diff_gaussian_rasterization_df", "_C.so")
+    if not os.path.exists(so):
+        return None
+    import importlib.util
+    d = os.path.dirname(so)
+    spec = importlib.util.spec_from_file_location("ref_diff_gaussian_rasterization_df", os.path.join(d, "__init__.py"),
+                                                  submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_diff_gaussian_rasterization_df"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class Frame:
+    """Resident inputs of one rank + the step functions."""
+
+    def __init__(self, mod, sc: synth.Scene, dev, seed_off: int):
+        self.mod, self.sc, self.dev = mod, sc, dev
+        cam = sc.cam
+        inp = synth.flat_inputs(sc)
+        self.P = inp["means3D"].shape[0]
+        self.t = {k: v.to(dev).requires_grad_(True) for k, v in inp.items()}
+        self.means2D = torch.zeros(self.P, 3, device=dev, requires_grad=True)
+        go = synth.grad_outputs(sc, seed_offset=7 + seed_off)
+        self.go = {k: v.to(dev) for k, v in go.items()}
+        self.sub = torch.zeros(cam.H, cam.W, 2, device=dev)
+        self.bg = sc.bg.to(dev)
+        # resident camera (device-timed leg) and pinned host copies (end-to-end leg)
+        self.view, self.proj, self.campos = cam.viewmatrix.to(dev), cam.projmatrix.to(dev), cam.campos.to(dev)
+        g = torch.Generator().manual_seed(1234 + seed_off)
+        self.h_gt = torch.rand(3, cam.H, cam.W, generator=g).pin_memory()
+        self.h_cam = torch.cat([cam.viewmatrix.flatten(), cam.projmatrix.flatten(), cam.campos.flatten()]).pin_memory()
+        self.d_gt = torch.empty(3, cam.H, cam.W, device=dev)
+        self.d_cam = torch.empty(35, device=dev)
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.R = -1
+        self.last = None
+
+    def settings(self, view, proj, campos):
+        cam = self.sc.cam
+        return self.mod.GaussianRasterizationSettings(
+            image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, kernel_size=cam.kernel_size,
+            subpixel_offset=self.sub, bg=self.bg, scale_modifier=1.0, viewmatrix=view, projmatrix=proj,
+            sh_degree=self.sc.sh_degree, campos=campos, prefiltered=False, min_depth=cam.min_depth,
+            max_depth=cam.max_depth, debug=False)
+
+    def _raster(self, rs):
+        t = self.t
+        return self.mod.GaussianRasterizer(rs)(means3D=t["means3D"], means2D=self.means2D, dir3D=t["dir3D"],
+                                                opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
+                                                rotations=t["rotations"])
+
+    def _zero(self):
+        for v in list(self.t.values()) + [self.means2D]:
+            v.grad = None
+
+    def step_device(self):
+        color, radii, depth, flow, acc, idxs = self._raster(self.settings(self.view, self.proj, self.campos))
+        go = self.go
+        torch.autograd.backward([color, depth, flow, acc], [go["grad_color"], go["grad_depth"], go["grad_flow"], go["grad_acc"]])
+        self.last = color
+        if color.grad_fn is not None and hasattr(color.grad_fn, "num_rendered"):
+            self.R = int(color.grad_fn.num_rendered)
+        self._zero()
+
+    def step_e2e(self, group=None):
+        self.d_cam.copy_(self.h_cam, non_blocking=True)
+        self.d_gt.copy_(self.h_gt, non_blocking=True)
+        c = self.d_cam
+        rs = self.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
+        color, radii, depth, flow, acc, idxs = self._raster(rs)
+        loss = (color - self.d_gt).abs().mean()
+        torch.autograd.backward([loss, flow], [None, self.go["grad_flow"]])
+        l = loss.detach().reshape(1)
+        if group is not None:
+            torch.distributed.all_reduce(l)
+        self.h_loss.copy_(l, non_blocking=True)
+        self._zero()
+
+
+def frame_stats(frame: Frame):
+    """R, P_vis and R_eff = sum_tiles min(range_len, 256*batches fetched) from the scratch buffers."""
+    from ex4dgs_b200 import _lib
+    t = frame.t
+    color, radii, depth, flow, acc, idxs = frame._raster(frame.settings(frame.view, frame.proj, frame.campos))
+    fn = color.grad_fn
+    R = int(fn.num_rendered)
+    img = fn.saved_tensors[9]
+    cam = frame.sc.cam
+    desc = _lib.describe_buffers(frame.P, R, cam.W, cam.H)
+
+    def view(name, dtype):
+        b, off, es, cnt = desc[name]
+        base = img.data_ptr()
+        a = ((base + 255) & ~255) - base
+        return img[a + off:a + off + es * cnt].cpu().numpy().view(dtype)
+
+    ranges = view("ranges", np.uint32).reshape(-1, 2).astype(np.int64)
+    batches = view("tile_batches", np.uint32).astype(np.int64)
+    rl = ranges[:, 1] - ranges[:, 0]
+    r_eff = int(np.minimum(rl, 256 * batches).sum())
+    n_contrib = view("n_contrib", np.uint32)
+    return dict(R=R, P_vis=int((radii > 0).sum().item()), R_eff=r_eff, tiles=int(ranges.shape[0]),
+                mean_n_contrib=float(n_contrib.mean()))
+
+
+def cpu_oracle_baseline(sc: synth.Scene):
+    """One full fwd+bwd frame of the same workload on the CPU oracle port, all host threads."""
+    from oracle import oracle as orc
+    inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
+    go = {k: v.numpy() for k, v in synth.grad_outputs(sc).items()}
+    cam = sc.cam
+    o = orc.Oracle()
+    t0 = time.time()
+    o.forward(bg=sc.bg.numpy(), W=cam.W, H=cam.H, means3D=inp["means3D"], dir3D=inp["dir3D"], opacities=inp["opacities"],
+              shs=inp["shs"], scales=inp["scales"], rotations=inp["rotations"], viewmatrix=cam.viewmatrix.numpy(),
+              projmatrix=cam.projmatrix.numpy(), campos=cam.campos.numpy(), tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+              kernel_size=cam.kernel_size, subpixel_offset=None, min_depth=cam.min_depth, max_depth=cam.max_depth,
+              sh_degree=sc.sh_degree)
+    o.backward(go["grad_color"], go["grad_depth"], go["grad_flow"], go["grad_acc"])
+    dt = time.time() - t0
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 full frame (fwd+bwd) of the same workload, oracle/cpu_raster.c with OpenMP, %.1f s" % dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "0")))
+    args = ap.parse_args()
+    rank, local_rank, ws = dist_env()
+    K, W = args.steps, max(args.warmup, 3)
+    sc = synth.make_config(args.workload)
+    cam = sc.cam
+    cfg = {"workload": "%s: %d static + %d dynamic Gaussians (K=36 keyframes, pre-interpolated at t=137), %dx%d, SH degree 3, "
+                       "fwd+bwd at the GaussianRasterizer boundary" % (args.workload, sc.xyz.shape[0], sc.xyz_motion.shape[0], cam.W, cam.H),
+           "parallelism": "frame-parallel x%d (Gaussians replicated, one frame per GPU per step)" % ws,
+           "l2": "inputs (496 MB at C3) larger than the 126 MB L2; no explicit flush"}
+
+    # ---------------- reference arm on the CPU (fallback when oracle/_ref is absent) ----------------
+    ref_mod = None
+    if args.impl != "ours":
+        ref_mod = load_reference() if args.impl == "reference" and torch.cuda.is_available() else None
+        if ref_mod is None:
+            if rank != 0:
+                return
+            cb = cpu_oracle_baseline(sc)
+            line = {"metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                    "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32", "data": "synthetic", "config": cfg, "impl": "reference", "cpu_baseline": cb,
+                    "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0,
+                    "note": "reference CUDA extension not available in oracle/_ref; CPU oracle port timed instead"}
+            print(json.dumps(line), flush=True)
+            return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if ws > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        group = torch.distributed.group.WORLD
+
+    if args.impl == "ours":
+        import ex4dgs_b200 as mod
+        from ex4dgs_b200 import _lib
+        mod.set_default_flags(bool(args.tile_cull))
+        lib = _lib.load()
+    else:
+        mod, lib = ref_mod, None
+
+    frame = Frame(mod, sc, dev, seed_off=rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if ws > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ws > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # warm-up: W steps of each leg, then keep going until the clocks have ramped (~1 s of work)
+    for _ in range(W):
+        frame.step_device()
+    t_spin = time.time()
+    while time.time() - t_spin < 1.0:
+        frame.step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0.0)
+    for _ in range(3):
+        frame.step_device()
+    launches0 = lib.ex4dgs_launch_count() if lib else 0
+    if lib:
+        lib.ex4dgs_profile_enable(1)
+    ms_total, t0, t1 = timed(frame.step_device, K)
+    stage_ms = None
+    if lib:
+        lib.ex4dgs_profile_enable(0)
+        arr = (C.c_double * 6)()
+        nf, nb = C.c_int(0), C.c_int(0)
+        lib.ex4dgs_profile_read(arr, C.byref(nf), C.byref(nb))
+        stage_ms = [arr[i] / max(1, (nf.value if i < 4 else nb.value)) for i in range(6)]
+    launches = (lib.ex4dgs_launch_count() - launches0) if lib else 0
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # end-to-end leg
+    for _ in range(W):
+        frame.step_e2e(group)
+    ms_e2e, _, _ = timed(lambda: frame.step_e2e(group), K)
+
+    value = ws * K / (ms_total / 1000.0)
+    e2e_value = ws * K / (ms_e2e / 1000.0)
+    if rank != 0:
+        if ws > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    h2d = frame.h_gt.numel() * 4 + frame.h_cam.numel() * 4
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K,
+                    "what": "per frame: H2D camera (35 floats) + ground-truth image from pinned memory, forward, L1 loss, "
+                            "backward, loss (all-reduced over ranks) D2H; Gaussian parameters resident"},
+            "clocks": clocks}
+    if args.impl == "ours":
+        st = frame_stats(frame)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+        alg_bytes = 56 * st["R_eff"] + 52 * cam.W * cam.H + 8 * st["tiles"]
+        t_render = stage_ms[3] / 1000.0
+        achieved = alg_bytes / t_render / 1e9
+        line["gpu_launches"] = int(launches)
+        line["config"].update({"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"],
+                               "tile_cull": int(args.tile_cull), "mean_n_contrib": st["mean_n_contrib"]})
+        line["roofline"] = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None,
+                            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[3],
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                            "note": "traffic (dram bytes) comes from the ncu capture under profiles/"}
+        line["stage_ms"] = dict(zip(["preprocess_fwd", "depth_sort_scan", "sync_duplicate_tilesort_ranges", "render_fwd",
+                                     "render_bwd", "preprocess_bwd"], stage_ms))
+        if not args.no_cpu_baseline and ws == 1:
+            line["cpu_baseline"] = cpu_oracle_baseline(sc)
+    else:
+        line["impl"] = "reference"
+        line["gpu_launches"] = 0
+        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+                                "sample": "the unmodified reference CUDA extension (oracle/_ref) on the same GPU - the reference "
+                                          "path has no CPU implementation (rasterize_points.cu:80)"}
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

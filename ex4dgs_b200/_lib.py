@@ -54,6 +54,9 @@ SIGNATURES = {
                              _P, _P, _P, _P, _P,  # dL_dmean2D dL_dopacity dL_dcolor dL_dmean3D dL_dcov3D
                              _P, _P, _P, _P,     # dL_dsh dL_dscale dL_drot dL_ddir
                              _I, C.c_uint, _P]),  # debug flags stream
+    "ex4dgs_profile_enable": (None, [_I]),
+    "ex4dgs_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(_I)]),
+    "ex4dgs_launch_count": (C.c_ulonglong, []),
     "ex4dgs_mark_visible": (_I, [_I, _P, _P, _P, _F, _F, _P, _P]),
     "ex4dgs_frontend_forward": (_I, [_I, _I, _I,
                                      _P, _P, _P, _P, _P,

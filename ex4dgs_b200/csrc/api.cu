@@ -8,10 +8,30 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local bool g_prof = false;
+thread_local unsigned long long g_launches = 0;
+struct ProfFrame { cudaEvent_t ev[5]; int n; bool bwd; };
+thread_local std::vector<ProfFrame> g_frames;
+
+struct Prof {
+    ProfFrame f;
+    bool on;
+    cudaStream_t s;
+    Prof(bool bwd, cudaStream_t st) : on(g_prof), s(st) { f.n = 0; f.bwd = bwd; }
+    void mark()
+    {
+        if (!on || f.n >= 5) return;
+        cudaEventCreate(&f.ev[f.n]);
+        cudaEventRecord(f.ev[f.n], s);
+        f.n++;
+    }
+    void done() { if (on) g_frames.push_back(f); }
+};
 
 int fail(int code, const char* fmt, ...)
 {
@@ -91,6 +111,27 @@ ImageState carve_image(void* base, int width, int height)
 extern "C" {
 
 int ex4dgs_abi_version(void) { return EX4DGS_ABI_VERSION; }
+
+void ex4dgs_profile_enable(int on) { g_prof = on != 0; }
+unsigned long long ex4dgs_launch_count(void) { return g_launches; }
+
+int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
+{
+    int nf = 0, nb = 0;
+    for (ProfFrame& f : g_frames) {
+        if (f.n > 0) cudaEventSynchronize(f.ev[f.n - 1]);
+        for (int i = 0; i + 1 < f.n; i++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, f.ev[i], f.ev[i + 1]) == cudaSuccess && ms) ms[(f.bwd ? 4 : 0) + i] += t;
+        }
+        for (int i = 0; i < f.n; i++) cudaEventDestroy(f.ev[i]);
+        if (f.bwd) nb++; else nf++;
+    }
+    g_frames.clear();
+    if (frames_fwd) *frames_fwd += nf;
+    if (frames_bwd) *frames_bwd += nb;
+    return EX4DGS_OK;
+}
 const char* ex4dgs_last_error(void) { return g_err; }
 
 size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
@@ -144,6 +185,7 @@ int ex4dgs_forward(
 {
     cudaStream_t s = (cudaStream_t)stream;
     g_err[0] = 0;
+    Prof prof(false, s);
     if (P < 0 || width <= 0 || height <= 0) return fail(EX4DGS_ERR_INVALID, "bad sizes P=%d W=%d H=%d", P, width, height);
     if (!geometryBuffer || !binningBuffer || !imageBuffer) return fail(EX4DGS_ERR_INVALID, "allocator callbacks are required");
     if (!background || !viewmatrix || !projmatrix || !cam_pos || !subpixel_offset)
@@ -210,12 +252,16 @@ int ex4dgs_forward(
         pp.prefiltered = prefiltered; pp.flags = flags;
         pp.radii = radii; pp.key_in = geom.key_in; pp.val_in = geom.val_in; pp.tiles_touched = geom.tiles_touched;
         pp.rec = geom.rec; pp.clamped = geom.clamped;
+        prof.mark();
         launch_preprocess_fwd(pp, s);
+        g_launches += 1;
         STAGE(debug, s, "preprocess");
+        prof.mark();
 
         CK(binning_stage1(geom, P, s));
         STAGE(debug, s, "depth sort + scan");
         // the one blocking read-back of the pipeline (rasterizer_impl.cu:299)
+        prof.mark();
         uint32_t r32 = 0;
         CK(cudaMemcpyAsync(&r32, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -230,6 +276,7 @@ int ex4dgs_forward(
 
     if (P > 0) {
         CK(binning_stage2(geom, bin, img, radii, P, R, grid_x, grid_y, flags, s));
+        g_launches += (R > 0) ? 2 : 0;
     } else {
         CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
     }
@@ -237,8 +284,12 @@ int ex4dgs_forward(
 
     rp.point_list = bin.point_list;
     rp.rec = geom.rec;
+    prof.mark();
     launch_render_fwd(rp, grid_x, grid_y, s);
+    g_launches += 1;
     STAGE(debug, s, "render");
+    prof.mark();
+    prof.done();
     return R;
 }
 
@@ -259,6 +310,7 @@ int ex4dgs_backward(
     (void)flags;
     cudaStream_t s = (cudaStream_t)stream;
     g_err[0] = 0;
+    Prof prof(true, s);
     if (P <= 0) return EX4DGS_OK;
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(EX4DGS_ERR_INVALID, "scratch buffers of the forward are required");
     if (!dL_dpix || !dL_ddepth || !dL_dflow || !dL_dacc) return fail(EX4DGS_ERR_INVALID, "upstream gradients are required");
@@ -274,6 +326,7 @@ int ex4dgs_backward(
     PreprocessBwdParams bp;
     memset(&bp, 0, sizeof(bp));
     bp.view = viewmatrix; bp.proj = projmatrix; bp.cam = campos;
+    prof.mark();
     CK(cudaMemsetAsync(geom.gacc, 0, sizeof(GradAcc) * (size_t)P, s));
 
     RenderParams rp;
@@ -287,8 +340,9 @@ int ex4dgs_backward(
     rp.out_depth = const_cast<float*>(acc_depth); rp.out_acc = const_cast<float*>(acc);
     rp.dL_dpix = dL_dpix; rp.dL_ddepth = dL_ddepth; rp.dL_dflow = dL_dflow; rp.dL_dacc = dL_dacc;
     rp.gacc = geom.gacc;
-    if (R > 0) launch_render_bwd(rp, grid_x, grid_y, s);
+    if (R > 0) { launch_render_bwd(rp, grid_x, grid_y, s); g_launches += 1; }
     STAGE(debug, s, "render backward");
+    prof.mark();
 
     bp.P = P; bp.D = D; bp.M = M;
     bp.means3D = means3D; bp.scales = scales; bp.rotations = rotations; bp.shs = shs;
@@ -302,7 +356,10 @@ int ex4dgs_backward(
     bp.dL_dmean2D = dL_dmean2D; bp.dL_dopacity = dL_dopacity; bp.dL_dcolor = dL_dcolor; bp.dL_dmean3D = dL_dmean3D;
     bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscale = dL_dscale; bp.dL_drot = dL_drot; bp.dL_ddir = dL_ddir;
     launch_preprocess_bwd(bp, s);
+    g_launches += 1;
     STAGE(debug, s, "preprocess backward");
+    prof.mark();
+    prof.done();
     return EX4DGS_OK;
 }
 

@@ -54,6 +54,11 @@ def ours_module():
     return ex4dgs_b200
 
 
+def oracle_module():
+    from oracle import oracle
+    return oracle
+
+
 def settings_for(mod, sc: synth.Scene, dev, subpixel: Optional[torch.Tensor] = None, debug=False):
     cam = sc.cam
     if subpixel is None:
@@ -137,8 +142,9 @@ def _our_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
 
 def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Optional[torch.Tensor] = None,
              use_colors_precomp: bool = False, use_cov3D_precomp: bool = False, intermediates: bool = True,
-             grad_kind: str = "train", is_ref: bool = False) -> Dict[str, np.ndarray]:
+             grad_kind: str = "train", is_ref: bool = False, kind: Optional[str] = None) -> Dict[str, np.ndarray]:
     """One forward (+ backward) through `mod.GaussianRasterizer`; everything returned as numpy."""
+    kind = kind or ("ref" if is_ref else "ours")
     inp = synth.flat_inputs(sc)
     P = inp["means3D"].shape[0]
     cam = sc.cam
@@ -166,7 +172,10 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
     res = {k: v.detach().cpu().numpy() for k, v in out.items()}
     if intermediates and color.grad_fn is not None:
         fn = color.grad_fn
-        res["inter"] = (_ref_intermediates if is_ref else _our_intermediates)(fn, P, cam.W, cam.H)
+        if kind == "oracle":
+            res["inter"] = fn.oracle.state()
+        else:
+            res["inter"] = (_ref_intermediates if kind == "ref" else _our_intermediates)(fn, P, cam.W, cam.H)
     if grads:
         go = synth.grad_outputs(sc)
         if grad_kind == "all":      # exercise the depth / acc gradient paths too
