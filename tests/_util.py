@@ -148,7 +148,7 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
     inp = synth.flat_inputs(sc)
     P = inp["means3D"].shape[0]
     cam = sc.cam
-    t = {k: v.to(dev).requires_grad_(grads) for k, v in inp.items()}
+    t = {k: v.detach().clone().to(dev).requires_grad_(grads) for k, v in inp.items()}
     means2D = torch.zeros(P, 3, device=dev, requires_grad=grads)
     rs = settings_for(mod, sc, dev, subpixel)
     rast = mod.GaussianRasterizer(rs)
@@ -156,13 +156,13 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
     extra = {}
     if use_colors_precomp:
         g = torch.Generator().manual_seed(11)
-        extra["colors"] = torch.rand(P, 3, generator=g).to(dev).requires_grad_(grads)
+        extra["colors"] = torch.rand(P, 3, generator=g).clone().to(dev).requires_grad_(grads)
         kw["colors_precomp"] = extra["colors"]
     else:
         kw["shs"] = t["shs"]
     if use_cov3D_precomp:
         # world-space covariances from the same scales / rotations (un-normalised quaternion, like the CUDA code)
-        extra["cov3D"] = cov3d_torch(inp["scales"], inp["rotations"]).to(dev).requires_grad_(grads)
+        extra["cov3D"] = cov3d_torch(inp["scales"], inp["rotations"]).detach().clone().to(dev).requires_grad_(grads)
         kw["cov3D_precomp"] = extra["cov3D"]
     else:
         kw["scales"] = t["scales"]
