@@ -62,7 +62,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -231,6 +231,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--profile-in-timed", type=int, default=1,
+                    help="record per-stage CUDA events inside the timed region (1) or in a separate pass (0)")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "0")))
     args = ap.parse_args()
     rank, local_rank, ws = dist_env()
@@ -307,22 +310,29 @@ def main():
         frame.step_device()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0.0)
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+    time.sleep(0.5 if sampler else 0.0)
     for _ in range(3):
         frame.step_device()
-    launches0 = lib.ex4dgs_launch_count() if lib else 0
-    if lib:
-        lib.ex4dgs_profile_enable(1)
-    ms_total, t0, t1 = timed(frame.step_device, K)
-    stage_ms = None
-    if lib:
+
+    def read_stages():
         lib.ex4dgs_profile_enable(0)
         arr = (C.c_double * 6)()
         nf, nb = C.c_int(0), C.c_int(0)
         lib.ex4dgs_profile_read(arr, C.byref(nf), C.byref(nb))
-        stage_ms = [arr[i] / max(1, (nf.value if i < 4 else nb.value)) for i in range(6)]
+        return [arr[i] / max(1, (nf.value if i < 4 else nb.value)) for i in range(6)]
+
+    launches0 = lib.ex4dgs_launch_count() if lib else 0
+    if lib and args.profile_in_timed:
+        lib.ex4dgs_profile_enable(1)
+    ms_total, t0, t1 = timed(frame.step_device, K)
     launches = (lib.ex4dgs_launch_count() - launches0) if lib else 0
+    stage_ms = None
+    if lib:
+        if not args.profile_in_timed:
+            lib.ex4dgs_profile_enable(1)
+            timed(frame.step_device, min(K, 20))
+        stage_ms = read_stages()
     clocks = sampler.stop(t0, t1) if sampler else None
 
     # end-to-end leg

@@ -8,29 +8,52 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local bool g_prof = false;
-thread_local unsigned long long g_launches = 0;
+// Measurement state is process-wide: autograd runs the backward on its own thread.
+std::atomic<bool> g_prof{false};
+std::atomic<unsigned long long> g_launches{0};
 struct ProfFrame { cudaEvent_t ev[5]; int n; bool bwd; };
-thread_local std::vector<ProfFrame> g_frames;
+std::mutex g_prof_mu;
+std::vector<ProfFrame> g_frames;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t pool_get()
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
 
 struct Prof {
     ProfFrame f;
     bool on;
     cudaStream_t s;
-    Prof(bool bwd, cudaStream_t st) : on(g_prof), s(st) { f.n = 0; f.bwd = bwd; }
+    Prof(bool bwd, cudaStream_t st) : on(g_prof.load()), s(st) { f.n = 0; f.bwd = bwd; }
     void mark()
     {
         if (!on || f.n >= 5) return;
-        cudaEventCreate(&f.ev[f.n]);
+        f.ev[f.n] = pool_get();
         cudaEventRecord(f.ev[f.n], s);
         f.n++;
     }
-    void done() { if (on) g_frames.push_back(f); }
+    void done()
+    {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_frames.push_back(f);
+    }
 };
 
 int fail(int code, const char* fmt, ...)
@@ -112,22 +135,29 @@ extern "C" {
 
 int ex4dgs_abi_version(void) { return EX4DGS_ABI_VERSION; }
 
-void ex4dgs_profile_enable(int on) { g_prof = on != 0; }
-unsigned long long ex4dgs_launch_count(void) { return g_launches; }
+void ex4dgs_profile_enable(int on) { g_prof.store(on != 0); }
+unsigned long long ex4dgs_launch_count(void) { return g_launches.load(); }
 
 int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
 {
     int nf = 0, nb = 0;
-    for (ProfFrame& f : g_frames) {
+    std::vector<ProfFrame> frames;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        frames.swap(g_frames);
+    }
+    for (ProfFrame& f : frames) {
         if (f.n > 0) cudaEventSynchronize(f.ev[f.n - 1]);
         for (int i = 0; i + 1 < f.n; i++) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, f.ev[i], f.ev[i + 1]) == cudaSuccess && ms) ms[(f.bwd ? 4 : 0) + i] += t;
         }
-        for (int i = 0; i < f.n; i++) cudaEventDestroy(f.ev[i]);
+        {
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            for (int i = 0; i < f.n; i++) g_event_pool.push_back(f.ev[i]);
+        }
         if (f.bwd) nb++; else nf++;
     }
-    g_frames.clear();
     if (frames_fwd) *frames_fwd += nf;
     if (frames_bwd) *frames_bwd += nb;
     return EX4DGS_OK;
