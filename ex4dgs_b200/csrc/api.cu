@@ -282,6 +282,9 @@ int ex4dgs_forward(
         pp.prefiltered = prefiltered; pp.flags = flags;
         pp.radii = radii; pp.key_in = geom.key_in; pp.val_in = geom.val_in; pp.tiles_touched = geom.tiles_touched;
         pp.rec = geom.rec; pp.clamped = geom.clamped;
+        pp.pad_ptr = reinterpret_cast<const float*>(geom.meta);
+        if (flags & EX4DGS_FLAG_TILE_CULL)
+            CK(launch_subpixel_absmax(subpixel_offset, (size_t)width * height * 2, geom.meta, s));
         prof.mark();
         launch_preprocess_fwd(pp, s);
         g_launches += 1;

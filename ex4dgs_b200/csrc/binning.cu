@@ -20,19 +20,30 @@ struct TilesInOrder {
     __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles_touched[id]; }
 };
 
-// One warp handles 32 consecutive entries of `order`; Gaussians with few tiles are written by
-// their own lane, large rectangles are spread over the whole warp (the per-thread serial loop of
-// rasterizer_impl.cu:100-111 is badly imbalanced for big splats).
-__global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* __restrict__ order,
-                                                        const uint32_t* __restrict__ key_sorted,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ tiles_touched,
-                                                        const SplatRec* __restrict__ rec, const int* __restrict__ radii,
-                                                        int grid_x, int grid_y, unsigned flags,
-                                                        uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out)
+constexpr int kDupThreads = 128;
+constexpr int kDupCap = 1024;   // staged (tile, id) pairs per warp
+
+// One warp handles 32 consecutive entries of `order`.  The serial per-thread rectangle loop of
+// rasterizer_impl.cu:100-111 writes 2- and 4-byte items at 32 unrelated addresses per instruction;
+// here every lane deposits its run in a per-warp shared-memory window and the warp then streams
+// the window to global memory with fully coalesced stores.  Warps whose 32 Gaussians emit more
+// than the window holds (huge splats) fall back to direct writes, large rectangles spread over
+// the whole warp.
+__global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ key_sorted,
+                                                                const uint32_t* __restrict__ offsets,
+                                                                const uint32_t* __restrict__ tiles_touched,
+                                                                const SplatRec* __restrict__ rec, const int* __restrict__ radii,
+                                                                int grid_x, int grid_y, unsigned flags, const float* __restrict__ pad_ptr,
+                                                                uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out)
 {
+    __shared__ uint16_t s_tile[kDupThreads / 32][kDupCap];
+    __shared__ uint32_t s_val[kDupThreads / 32][kDupCap];
+    const unsigned full = 0xffffffffu;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool cull = (flags & 1u) != 0;
+    const float pad = cull ? __ldg(pad_ptr) : 0.f;
     uint32_t id = 0, cnt = 0, off = 0;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     float px = 0, py = 0, A = 0, B = 0, C = 0, thr = 0;
@@ -43,31 +54,56 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
         const float4 a = rec[id].a;
         px = a.x; py = a.y; thr = a.w;
         tile_rect(px, py, radii[id], grid_x, grid_y, x0, y0, x1, y1);
-        if (flags & 1u) {
+        if (cull) {
             const float4 b = rec[id].b;
             A = b.x; B = b.y; C = b.z;
         }
     }
-    const bool cull = (flags & 1u) != 0;
+    // the warp's output window [wbase, wbase + wtotal): offsets are an inclusive scan in this order
+    const int jw = (j & ~31);
+    const uint32_t wbase = (jw == 0) ? 0u : ((jw < P) ? offsets[jw - 1] : 0u);
+    const int jl = min(jw + 31, P - 1);
+    const uint32_t wtotal = (jw < P) ? (offsets[jl] - wbase) : 0u;
+    if (wtotal == 0) return;
+
+    if (wtotal <= (uint32_t)kDupCap) {
+        uint32_t o = off - wbase;
+        if (cnt) {
+            for (int ty = y0; ty < y1; ty++)
+                for (int tx = x0; tx < x1; tx++) {
+                    if (cull && tile_cannot_contribute(px, py, A, B, C, thr, tx, ty, pad)) continue;
+                    s_tile[warp][o] = (uint16_t)(ty * grid_x + tx);
+                    s_val[warp][o] = id;
+                    o++;
+                }
+        }
+        __syncwarp();
+        for (uint32_t t = lane; t < wtotal; t += 32) {
+            tile_out[wbase + t] = s_tile[warp][t];
+            val_out[wbase + t] = s_val[warp][t];
+        }
+        return;
+    }
+
+    // ---- fallback: direct writes
     const bool big = cnt > 32;
     if (cnt && !big) {
         for (int ty = y0; ty < y1; ty++)
             for (int tx = x0; tx < x1; tx++) {
-                if (cull && tile_cannot_contribute(px, py, A, B, C, thr, tx, ty, 0.5f)) continue;
+                if (cull && tile_cannot_contribute(px, py, A, B, C, thr, tx, ty, pad)) continue;
                 tile_out[off] = (uint16_t)(ty * grid_x + tx);
                 val_out[off] = id;
                 off++;
             }
     }
-    // cooperative path for large rectangles
-    unsigned todo = __ballot_sync(0xffffffffu, big);
+    unsigned todo = __ballot_sync(full, big);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
-        const uint32_t boff = __shfl_sync(0xffffffffu, off, src);
-        const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-        const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
+        const uint32_t bid = __shfl_sync(full, id, src);
+        const uint32_t boff = __shfl_sync(full, off, src);
+        const int bx0 = __shfl_sync(full, x0, src), by0 = __shfl_sync(full, y0, src);
+        const int bx1 = __shfl_sync(full, x1, src), by1 = __shfl_sync(full, y1, src);
         const int w = bx1 - bx0, n = w * (by1 - by0);
         if (!cull) {
             for (int t = lane; t < n; t += 32) {
@@ -76,9 +112,9 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
                 val_out[boff + t] = bid;
             }
         } else {
-            const float bpx = __shfl_sync(0xffffffffu, px, src), bpy = __shfl_sync(0xffffffffu, py, src);
-            const float bA = __shfl_sync(0xffffffffu, A, src), bB = __shfl_sync(0xffffffffu, B, src);
-            const float bC = __shfl_sync(0xffffffffu, C, src), bthr = __shfl_sync(0xffffffffu, thr, src);
+            const float bpx = __shfl_sync(full, px, src), bpy = __shfl_sync(full, py, src);
+            const float bA = __shfl_sync(full, A, src), bB = __shfl_sync(full, B, src);
+            const float bC = __shfl_sync(full, C, src), bthr = __shfl_sync(full, thr, src);
             uint32_t base = boff;
             for (int t0 = 0; t0 < n; t0 += 32) {
                 const int t = t0 + lane;
@@ -86,9 +122,9 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
                 int ty = 0, tx = 0;
                 if (t < n) {
                     ty = by0 + t / w; tx = bx0 + t % w;
-                    keep = !tile_cannot_contribute(bpx, bpy, bA, bB, bC, bthr, tx, ty, 0.5f);
+                    keep = !tile_cannot_contribute(bpx, bpy, bA, bB, bC, bthr, tx, ty, pad);
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const unsigned m = __ballot_sync(full, keep);
                 if (keep) {
                     const uint32_t o = base + __popc(m & ((1u << lane) - 1u));
                     tile_out[o] = (uint16_t)(ty * grid_x + tx);
@@ -100,21 +136,51 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, const uint32_t* _
     }
 }
 
+// ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
+// eight 16-bit keys per thread from one 128-bit load.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = tiles[idx];
-    if (idx == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = tiles[idx - 1];
-        if (cur != prev) {
-            ranges[prev].y = idx;
-            ranges[cur].x = idx;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = g * 8;
+    if (base >= L) return;
+    uint16_t t[8];
+    if (base + 8 <= L) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(tiles) + g);
+        t[0] = v.x & 0xffff; t[1] = v.x >> 16; t[2] = v.y & 0xffff; t[3] = v.y >> 16;
+        t[4] = v.z & 0xffff; t[5] = v.z >> 16; t[6] = v.w & 0xffff; t[7] = v.w >> 16;
+    } else {
+        for (int k = 0; k < 8; k++) t[k] = (base + k < L) ? tiles[base + k] : 0;
+    }
+    uint32_t prev = (base == 0) ? 0xffffffffu : (uint32_t)tiles[base - 1];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int idx = base + k;
+        if (idx < L) {
+            const uint32_t cur = t[k];
+            if (idx == 0) {
+                ranges[cur].x = 0;
+            } else if (cur != prev) {
+                ranges[prev].y = idx;
+                ranges[cur].x = idx;
+            }
+            if (idx == L - 1) ranges[cur].y = L;
+            prev = cur;
         }
     }
-    if (idx == L - 1) ranges[cur].y = L;
+}
+
+// max |subpixel offset| -> *out (float bits, non-negative, so integer max orders correctly).
+// Needed by the exact tile culling: pixel centres are integer + offset.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ v, size_t n, uint32_t* out)
+{
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = fabsf(__ldg(v + i));
+        m = (a > m || a != a) ? a : m;     // NaN propagates
+    }
+    uint32_t b = __float_as_uint(m);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
 }
 
 // smallest b with (n >> b) == 0, computed like rasterizer_impl.cu:35-50
@@ -149,6 +215,14 @@ size_t binning_stage2_temp_bytes(int R)
     return a + 256;
 }
 
+cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    absmax_kernel<<<148 * 4, 256, 0, s>>>(subpixel_offset, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t binning_stage1(const GeometryState& g, int P, cudaStream_t s)
 {
     size_t tb = g.temp_bytes;
@@ -166,13 +240,15 @@ cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const 
     const int tiles = grid_x * grid_y;
     cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, s);
     if (e != cudaSuccess || R <= 0) return e;
-    duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.order, g.key_sorted, g.offsets, g.tiles_touched, g.rec,
-                                                     radii, grid_x, grid_y, flags, b.tile_unsorted, b.val_unsorted);
+    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
+        P, g.order, g.key_sorted, g.offsets, g.tiles_touched, g.rec, radii, grid_x, grid_y, flags,
+        reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted);
     size_t tb = b.temp_bytes;
     const int bit = (int)higher_msb((uint32_t)tiles);
     e = cub::DeviceRadixSort::SortPairs(b.temp, tb, b.tile_unsorted, b.tile_sorted, b.val_unsorted, b.point_list,
                                         R, 0, bit < 16 ? bit : 16, s);
     if (e != cudaSuccess) return e;
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges);
+    const int groups = (R + 7) / 8;
+    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges);
     return cudaGetLastError();
 }

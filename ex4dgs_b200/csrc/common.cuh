@@ -119,6 +119,7 @@ struct PreprocessParams {
     int grid_x, grid_y;
     int prefiltered;
     unsigned flags;
+    const float* pad_ptr;   // max |subpixel offset| (device scalar), read when EX4DGS_FLAG_TILE_CULL
     int* radii;
     uint32_t* key_in;
     uint32_t* val_in;
@@ -187,6 +188,7 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
 void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
 
+cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
 size_t binning_stage1_temp_bytes(int P);
 size_t binning_stage2_temp_bytes(int R);
 // sort Gaussians by depth bits, scan tiles_touched in that order; returns cudaError
@@ -226,6 +228,7 @@ __device__ __forceinline__ bool tile_cannot_contribute(float cx, float cy, float
     // agree exactly, so every operation is pinned (no compiler-chosen FMA contraction).
     // q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy  (= -power), minimised over the tile's pixel rectangle.
     // The quadratic is convex when A,C > 0 and AC > B^2; otherwise be conservative.
+    if (!(pad <= 4096.f)) return false;          // NaN / absurd subpixel offsets: never cull
     const float detc = fa(fm(A, C), -fm(B, B));
     if (!(A > 0.f) || !(C > 0.f) || !(detc > 0.f)) return false;
     const float dx0 = fa(fa((float)(tx * EX_TILE), -pad), -cx), dx1 = fa(fa((float)(tx * EX_TILE + EX_TILE - 1), pad), -cx);

@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
 
         uint32_t count = area;
         if (p.flags & 1u) {
+            const float pad = __ldg(p.pad_ptr);
             // conservative per-tile culling; identical test in the duplicate kernel
             count = 0;
             for (int ty = y0; ty < y1; ty++)
                 for (int tx = x0; tx < x1; tx++)
-                    count += tile_cannot_contribute(px, py, conA, conB, conC, thr, tx, ty, 0.5f) ? 0u : 1u;
+                    count += tile_cannot_contribute(px, py, conA, conB, conC, thr, tx, ty, pad) ? 0u : 1u;
         }
 
         SplatRec rc;
@@ -515,6 +516,215 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
         reinterpret_cast<float4*>(p.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same math, B200 memory layout: 128 Gaussians per CTA, every [P,3] / [P,16,3] tensor crosses
+// HBM with fully coalesced 128-bit accesses through a shared-memory staging area (rows padded to
+// 49 floats: conflict-free for the per-thread row accesses), the 192-byte SH row is read and its
+// gradient written in place in that staging area (no 48+48 register arrays -> 3x the occupancy).
+// Handles M == 16 (degree-3 layout) and M == 0 (precomputed colours); other M use the kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBT = 128;        // threads = Gaussians per CTA
+constexpr int kRow = 49;        // padded SH row (floats)
+
+__device__ __forceinline__ void sh_basis_and_grad(int D, float x, float y, float z, int k,
+                                                  float& b, float& bx, float& by, float& bz)
+{
+    // value and d/d(x,y,z) of real SH basis k (forward.cu:30-59, backward.cu:47-123), k < (D+1)^2
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    bx = by = bz = 0.f;
+    switch (k) {
+    case 0: b = kC0; break;
+    case 1: b = -kC1 * y; by = -kC1; break;
+    case 2: b = kC1 * z; bz = kC1; break;
+    case 3: b = -kC1 * x; bx = -kC1; break;
+    case 4: b = kC2[0] * xy; bx = kC2[0] * y; by = kC2[0] * x; break;
+    case 5: b = kC2[1] * yz; by = kC2[1] * z; bz = kC2[1] * y; break;
+    case 6: b = kC2[2] * (2.f * zz - xx - yy); bx = kC2[2] * 2.f * -x; by = kC2[2] * 2.f * -y; bz = kC2[2] * 2.f * 2.f * z; break;
+    case 7: b = kC2[3] * xz; bx = kC2[3] * z; bz = kC2[3] * x; break;
+    case 8: b = kC2[4] * (xx - yy); bx = kC2[4] * 2.f * x; by = kC2[4] * 2.f * -y; break;
+    case 9: b = kC3[0] * y * (3.f * xx - yy); bx = kC3[0] * 3.f * 2.f * xy; by = kC3[0] * 3.f * (xx - yy); break;
+    case 10: b = kC3[1] * xy * z; bx = kC3[1] * yz; by = kC3[1] * xz; bz = kC3[1] * xy; break;
+    case 11: b = kC3[2] * y * (4.f * zz - xx - yy); bx = kC3[2] * -2.f * xy; by = kC3[2] * (-3.f * yy + 4.f * zz - xx); bz = kC3[2] * 4.f * 2.f * yz; break;
+    case 12: b = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = kC3[3] * -3.f * 2.f * xz; by = kC3[3] * -3.f * 2.f * yz; bz = kC3[3] * 3.f * (2.f * zz - xx - yy); break;
+    case 13: b = kC3[4] * x * (4.f * zz - xx - yy); bx = kC3[4] * (-3.f * xx + 4.f * zz - yy); by = kC3[4] * -2.f * xy; bz = kC3[4] * 4.f * 2.f * xz; break;
+    case 14: b = kC3[5] * z * (xx - yy); bx = kC3[5] * 2.f * xz; by = kC3[5] * -2.f * yz; bz = kC3[5] * (xx - yy); break;
+    default: b = kC3[6] * x * (xx - 3.f * yy); bx = kC3[6] * 3.f * (xx - yy); by = kC3[6] * -3.f * 2.f * xy; break;
+    }
+}
+
+__global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __grid_constant__ PreprocessBwdParams p)
+{
+    extern __shared__ float smem[];
+    float* s_cam = smem;                       // 36 (+4 pad)
+    float* s_o3 = smem + 40;                   // 5 x [kBT*3]: mean2D, color, dir, mean3D, scale
+    float* s_sh = s_o3 + 5 * kBT * 3;          // [kBT][kRow]   (only when M == 16)
+    const int tid = threadIdx.x;
+    if (tid < 16) s_cam[tid] = __ldg(p.view + tid);
+    else if (tid < 32) s_cam[tid] = __ldg(p.proj + tid - 16);
+    else if (tid < 35) s_cam[tid] = __ldg(p.cam + tid - 32);
+    const int base = blockIdx.x * kBT;
+    const int idx = base + tid;
+    const int nvalid = min(kBT, p.P - base);
+    const bool has_sh = (p.shs != nullptr);    // implies M == 16 here
+
+    // cooperative, coalesced load of the block's SH rows
+    if (has_sh) {
+        const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)base * 48);
+        const int n4 = nvalid * 12;
+        for (int f = tid; f < n4; f += kBT) {
+            const float4 v = __ldg(src + f);
+            const int row = f / 12, col = (f % 12) * 4;
+            float* d = s_sh + row * kRow + col;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    __syncthreads();
+    const float* view = s_cam;
+    const float* pr = s_cam + 16;
+    const float* cam = s_cam + 32;
+
+    if (idx < p.P) {
+        const GradAcc g = p.gacc[idx];
+        s_o3[0 * kBT * 3 + 3 * tid + 0] = g.g0.x; s_o3[0 * kBT * 3 + 3 * tid + 1] = g.g0.y; s_o3[0 * kBT * 3 + 3 * tid + 2] = g.g0.z;
+        s_o3[1 * kBT * 3 + 3 * tid + 0] = g.g2.x; s_o3[1 * kBT * 3 + 3 * tid + 1] = g.g2.y; s_o3[1 * kBT * 3 + 3 * tid + 2] = g.g2.z;
+        s_o3[2 * kBT * 3 + 3 * tid + 0] = g.g3.x; s_o3[2 * kBT * 3 + 3 * tid + 1] = g.g3.y; s_o3[2 * kBT * 3 + 3 * tid + 2] = g.g3.z;
+        p.dL_dopacity[idx] = g.g0.w;
+
+        float dmean[3] = {0.f, 0.f, 0.f};
+        float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float dscale[3] = {0.f, 0.f, 0.f};
+        float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* row = s_sh + tid * kRow;
+        if (p.radii[idx] > 0) {
+            const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
+            float cov3D[6];
+            float sx = 0, sy = 0, sz = 0;
+            float4 q = make_float4(0, 0, 0, 0);
+            if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) cov3D[i] = __ldg(p.cov3D_precomp + 6 * idx + i);
+            } else {
+                q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+                sx = __ldg(p.scales + 3 * idx); sy = __ldg(p.scales + 3 * idx + 1); sz = __ldg(p.scales + 3 * idx + 2);
+                cov3d_from_scale_rot(sx, sy, sz, p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+            }
+            {   // conic -> cov2D -> cov3D (backward.cu:144-257)
+                const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
+                const float a = cv.a + p.kernel_size, b = cv.b, c = cv.c + p.kernel_size;
+                const float dcx = g.g1.x, dcy = g.g1.y, dcz = g.g1.z;
+                const float denom = a * c - b * b;
+                const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+                if (denom2inv != 0) {
+                    const float dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
+                    const float dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
+                    const float dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+                    const float* T0 = cv.T0; const float* T1 = cv.T1;
+                    dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
+                    dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
+                    dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
+                    dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
+                    dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
+                    dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
+                }
+            }
+            {   // mean2D -> mean3D (backward.cu:396-414)
+                const float hw = pr[3] * mx + pr[7] * my + pr[11] * mz + pr[15];
+                const float m_w = 1.0f / (hw + 0.0000001f);
+                const float mul1 = (pr[0] * mx + pr[4] * my + pr[8] * mz + pr[12]) * m_w * m_w;
+                const float mul2 = (pr[1] * mx + pr[5] * my + pr[9] * mz + pr[13]) * m_w * m_w;
+                const float mul3 = (pr[2] * mx + pr[6] * my + pr[10] * mz + pr[14]) * m_w * m_w;
+                const float gx = g.g0.x, gy = g.g0.y, gz = g.g0.z;
+                dmean[0] = (pr[0] * m_w - pr[3] * mul1) * gx + (pr[1] * m_w - pr[3] * mul2) * gy + (pr[2] * m_w - pr[3] * mul3) * gz;
+                dmean[1] = (pr[4] * m_w - pr[7] * mul1) * gx + (pr[5] * m_w - pr[7] * mul2) * gy + (pr[6] * m_w - pr[7] * mul3) * gz;
+                dmean[2] = (pr[8] * m_w - pr[11] * mul1) * gx + (pr[9] * m_w - pr[11] * mul2) * gy + (pr[10] * m_w - pr[11] * mul3) * gz;
+            }
+            if (has_sh) {   // SH backward in place on the staged row (backward.cu:20-139)
+                const float ox = mx - cam[0], oy = my - cam[1], oz = mz - cam[2];
+                const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+                const float x = ox / len, y = oy / len, z = oz / len;
+                const uint8_t cl = p.clamped[idx];
+                const float d0 = (cl & 1) ? 0.f : g.g2.x, d1 = (cl & 2) ? 0.f : g.g2.y, d2 = (cl & 4) ? 0.f : g.g2.z;
+                const int nb = (p.D + 1) * (p.D + 1);
+                float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k < nb) {
+                        float b, bx, by, bz;
+                        sh_basis_and_grad(p.D, x, y, z, k, b, bx, by, bz);
+                        const float s = row[3 * k] * d0 + row[3 * k + 1] * d1 + row[3 * k + 2] * d2;
+                        ddx += bx * s; ddy += by * s; ddz += bz * s;
+                        row[3 * k] = b * d0; row[3 * k + 1] = b * d1; row[3 * k + 2] = b * d2;
+                    } else {
+                        row[3 * k] = 0.f; row[3 * k + 1] = 0.f; row[3 * k + 2] = 0.f;
+                    }
+                }
+                const float sum2 = ox * ox + oy * oy + oz * oz;
+                const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+                dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+                dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+                dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+            }
+            if (p.scales != nullptr) {   // cov3D -> scale / rotation (backward.cu:304-367)
+                const float r = q.x, x = q.y, y = q.z, z = q.w;
+                const float R[3][3] = {
+                    {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+                const float s[3] = {p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
+                const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                        {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                        {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+                float dM[3][3];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int rr = 0; rr < 3; rr++)
+                        dM[c][rr] = 2.0f * (s[rr] * R[0][rr] * dS[c][0] + s[rr] * R[1][rr] * dS[c][1] + s[rr] * R[2][rr] * dS[c][2]);
+#pragma unroll
+                for (int a = 0; a < 3; a++) dscale[a] = R[0][a] * dM[0][a] + R[1][a] * dM[1][a] + R[2][a] * dM[2][a];
+                float Mt[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int b2 = 0; b2 < 3; b2++) Mt[a][b2] = dM[b2][a] * s[a];
+                drot.x = 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
+                drot.y = 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r * (Mt[1][2] - Mt[2][1]) - 4 * x * (Mt[2][2] + Mt[1][1]);
+                drot.z = 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) - 4 * y * (Mt[2][2] + Mt[0][0]);
+                drot.w = 2 * r * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) - 4 * z * (Mt[1][1] + Mt[0][0]);
+            }
+        } else if (has_sh) {
+#pragma unroll
+            for (int k = 0; k < 48; k++) row[k] = 0.f;
+        }
+        s_o3[3 * kBT * 3 + 3 * tid + 0] = dmean[0]; s_o3[3 * kBT * 3 + 3 * tid + 1] = dmean[1]; s_o3[3 * kBT * 3 + 3 * tid + 2] = dmean[2];
+        s_o3[4 * kBT * 3 + 3 * tid + 0] = dscale[0]; s_o3[4 * kBT * 3 + 3 * tid + 1] = dscale[1]; s_o3[4 * kBT * 3 + 3 * tid + 2] = dscale[2];
+        if (p.dL_dcov3D != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) p.dL_dcov3D[6 * idx + i] = dcov[i];
+        }
+        if (p.dL_drot != nullptr) reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
+    }
+    __syncthreads();
+
+    // coalesced write-out
+    float* outs[5] = {p.dL_dmean2D, p.dL_dcolor, p.dL_ddir, p.dL_dmean3D, p.dL_dscale};
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        if (outs[a] == nullptr) continue;
+        float* dst = outs[a] + (size_t)base * 3;
+        for (int f = tid; f < nvalid * 3; f += kBT) dst[f] = s_o3[a * kBT * 3 + f];
+    }
+    if (has_sh) {
+        float4* dst = reinterpret_cast<float4*>(p.dL_dsh + (size_t)base * 48);
+        const int n4 = nvalid * 12;
+        for (int f = tid; f < n4; f += kBT) {
+            const int row = f / 12, col = (f % 12) * 4;
+            const float* s = s_sh + row * kRow + col;
+            dst[f] = make_float4(s[0], s[1], s[2], s[3]);
+        }
+    }
+}
+
 }  // namespace
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
@@ -526,7 +736,12 @@ void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s)
 {
     if (p.P <= 0) return;
-    preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+    if (p.shs == nullptr || p.M == 16) {
+        const size_t smem = sizeof(float) * (40 + 5 * kBT * 3 + (p.shs != nullptr ? kBT * kRow : 0));
+        preprocess_bwd_staged_kernel<<<(p.P + kBT - 1) / kBT, kBT, smem, s>>>(p);
+    } else {
+        preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+    }
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,

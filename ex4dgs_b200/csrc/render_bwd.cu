@@ -73,7 +73,7 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(256, 2) render_bwd_kernel(const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constant__ RenderParams p)
 {
     __shared__ float4 s_rec[2][kSub * 3];
     __shared__ __align__(16) float s_part[8][kSub][16];
@@ -158,65 +158,65 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(const __grid_constan
         const float4* __restrict__ s = s_rec[r & 1];
         const int cnt = min(kSub, start - r * kSub);
         unsigned long long mask = 0ull;
+#pragma unroll 2
         for (int j = 0; j < cnt; j++) {
             const int q = start - 1 - (r * kSub + j);
+            const float4 a = s[j * 3 + 0];
+            const float4 b = s[j * 3 + 1];
+            const float dx = fa(a.x, -pxf), dy = fa(a.y, -pyf);
+            const float power = ff(ff(dx, fm(dx, b.x), fm(fm(b.z, dy), dy)), -0.5f, -fm(fm(b.y, dx), dy));
+            bool contributes = (q < last_contributor) && !(power > 0.0f) && !(power < a.w);
+            float G = 0.f, alpha = 0.f;
+            if (contributes) {
+                G = expf(power);
+                alpha = fminf(0.99f, fm(b.w, G));
+                contributes = !(alpha < 1.0f / 255.0f);
+            }
+            if (!__any_sync(0xffffffffu, contributes)) continue;
             float v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = 0.f;
-            bool contributes = false;
-            if (q < last_contributor) {
-                const float4 a = s[j * 3 + 0];
-                const float4 b = s[j * 3 + 1];
-                const float dx = fa(a.x, -pxf), dy = fa(a.y, -pyf);
-                const float power = ff(ff(dx, fm(dx, b.x), fm(fm(b.z, dy), dy)), -0.5f, -fm(fm(b.y, dx), dy));
-                if (!(power > 0.0f) && !(power < a.w)) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, fm(b.w, G));
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        contributes = true;
-                        const float4 c = s[j * 3 + 2];
-                        T = T / (1.f - alpha);
-                        const float w = alpha * T;               // dchannel_dcolor
-                        float dL_dalpha = 0.0f;
-                        const float dep = a.z;
-                        if ((dep > p.min_depth) & (w > 0.0f)) {
-                            v[2] = dL_ddepth * w;
-                            dL_dalpha += (final_depth - dep) * dL_ddepth * T;
-                        }
-                        accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
-                        accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
-                        accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
-                        last_c0 = c.x; last_c1 = c.y; last_c2 = c.z;
-                        dL_dalpha += (c.x - accum_rec0) * dpix0;
-                        dL_dalpha += (c.y - accum_rec1) * dpix1;
-                        dL_dalpha += (c.z - accum_rec2) * dpix2;
-                        v[8] = w * dpix0; v[9] = w * dpix1; v[10] = w * dpix2;
-                        v[12] = w * dflow0; v[13] = w * dflow1; v[14] = w * dflow2;
-                        dL_dalpha *= T;
-                        dL_dacc *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                        const float dL_dG = b.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * b.x - gdy * b.y;
-                        const float dG_ddely = -gdy * b.z - gdx * b.y;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[4] = -0.5f * gdx * dx * dL_dG;
-                        v[5] = -0.5f * gdx * dy * dL_dG;
-                        v[6] = -0.5f * gdy * dy * dL_dG;
-                        v[3] = G * dL_dalpha + G * dL_dacc;
-                    }
+            if (contributes) {
+                const float4 c = s[j * 3 + 2];
+                const float inv1ma = 1.f / (1.f - alpha);
+                T = T * inv1ma;
+                const float w = alpha * T;               // dchannel_dcolor
+                float dL_dalpha = 0.0f;
+                const float dep = a.z;
+                if ((dep > p.min_depth) & (w > 0.0f)) {
+                    v[2] = dL_ddepth * w;
+                    dL_dalpha += (final_depth - dep) * dL_ddepth * T;
                 }
+                accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
+                accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
+                accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
+                last_c0 = c.x; last_c1 = c.y; last_c2 = c.z;
+                dL_dalpha += (c.x - accum_rec0) * dpix0;
+                dL_dalpha += (c.y - accum_rec1) * dpix1;
+                dL_dalpha += (c.z - accum_rec2) * dpix2;
+                v[8] = w * dpix0; v[9] = w * dpix1; v[10] = w * dpix2;
+                v[12] = w * dflow0; v[13] = w * dflow1; v[14] = w * dflow2;
+                dL_dalpha *= T;
+                dL_dacc *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
+                const float dL_dG = b.w * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * b.x - gdy * b.y;
+                const float dG_ddely = -gdy * b.z - gdx * b.y;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[4] = -0.5f * gdx * dx * dL_dG;
+                v[5] = -0.5f * gdx * dy * dL_dG;
+                v[6] = -0.5f * gdy * dy * dL_dG;
+                v[3] = G * dL_dalpha + G * dL_dacc;
             }
-            if (__any_sync(0xffffffffu, contributes)) {
-                const float tot = butterfly16(v, lane);
-                if (!(lane & 1)) {
-                    const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    s_part[warp][j][k] = tot;
-                }
-                mask |= 1ull << j;
+            const float tot = butterfly16(v, lane);
+            if (!(lane & 1)) {
+                const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                s_part[warp][j][k] = tot;
             }
+            mask |= 1ull << j;
         }
         if (lane == 0) s_mask[warp] = mask;
         __syncthreads();                       // (B) partial sums of all warps complete

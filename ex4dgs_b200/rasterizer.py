@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import NamedTuple
 
 import torch
@@ -55,21 +56,22 @@ def _f32c(t: torch.Tensor, dev) -> torch.Tensor:
     return t.contiguous()
 
 
-class _Scratch:
-    """Allocator callbacks handing out torch byte tensors (the C form of
-    rasterize_points.cu:27-33 resizeFunctional)."""
+# Allocator callbacks handing out torch byte tensors (the C form of rasterize_points.cu:27-33
+# resizeFunctional).  One persistent ctypes trampoline for the whole process: the `user` cookie is
+# the buffer index (0 geometry, 1 binning, 2 image) and the tensors land in a per-thread list that
+# the calling forward() installs - no per-call CFUNCTYPE objects and no reference cycles that
+# would keep hundreds of MB of scratch alive until the cyclic GC runs.
+_tls = threading.local()
 
-    def __init__(self, device):
-        self.device = device
-        self.tensors = [None, None, None]
-        self.cbs = [_lib.ALLOC_FN(self._make(i)) for i in range(3)]
 
-    def _make(self, i):
-        def alloc(_user, nbytes):
-            t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
-            self.tensors[i] = t
-            return t.data_ptr()
-        return alloc
+def _alloc_trampoline(user, nbytes):
+    i = int(user or 0)
+    t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=_tls.device)
+    _tls.tensors[i] = t
+    return t.data_ptr()
+
+
+_ALLOC_CB = _lib.ALLOC_FN(_alloc_trampoline)
 
 
 def rasterize_gaussians(means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
@@ -143,12 +145,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         acc = torch.empty(1, H, W, **fopt)
         flow = torch.empty(3, H, W, **fopt)
         idxs = torch.empty(1, H, W, **iopt)
-        scratch = _Scratch(dev)
+        _tls.device = dev
+        _tls.tensors = [None, None, None]
         stream = torch.cuda.current_stream(dev).cuda_stream
         try:
             with torch.cuda.device(dev):
                 R = lib.ex4dgs_forward(
-                    scratch.cbs[0], None, scratch.cbs[1], None, scratch.cbs[2], None,
+                    _ALLOC_CB, C.c_void_p(0), _ALLOC_CB, C.c_void_p(1), _ALLOC_CB, C.c_void_p(2),
                     P, int(rs.sh_degree), int(M),
                     _ptr(bg), W, H,
                     _ptr(means3D_c), _ptr(dir3D_c), _ptr(sh_c), _ptr(colors_c),
@@ -165,7 +168,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             raise ex
 
-        geomBuffer, binningBuffer, imgBuffer = scratch.tensors
+        geomBuffer, binningBuffer, imgBuffer = _tls.tensors
+        _tls.tensors = None
         ctx.raster_settings = rs
         ctx.num_rendered = int(R)
         ctx.flags = flags
