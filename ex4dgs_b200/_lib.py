@@ -18,6 +18,7 @@ FLAG_TILE_CULL = 1
 _F = C.c_float
 _P = C.c_void_p
 _I = C.c_int
+_D = C.c_double
 
 
 class ArrayDesc(C.Structure):
@@ -61,11 +62,11 @@ SIGNATURES = {
     "ex4dgs_frontend_forward": (_I, [_I, _I, _I,
                                      _P, _P, _P, _P, _P,
                                      _P, _P, _P, _P, _P, _P,
-                                     _F, _F, _F, _F, _F,
+                                     _D, _D, _D, _D, _D,
                                      _P, _P, _P, _P, _P]),
     "ex4dgs_frontend_backward": (_I, [_I, _I, _I,
-                                      _P, _P, _P, _P, _P, _P,
-                                      _F, _F, _F, _F, _F,
+                                      _P, _P, _P, _P, _P, _P, _P,
+                                      _D, _D, _D, _D, _D,
                                       _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _P,

@@ -20,119 +20,83 @@ struct TilesInOrder {
     __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles_touched[id]; }
 };
 
-constexpr int kDupThreads = 128;
-constexpr int kDupCap = 1024;   // staged (tile, id) pairs per warp
+constexpr int kDupThreads = 256;
 
-// One warp handles 32 consecutive entries of `order`.  The serial per-thread rectangle loop of
-// rasterizer_impl.cu:100-111 writes 2- and 4-byte items at 32 unrelated addresses per instruction;
-// here every lane deposits its run in a per-warp shared-memory window and the warp then streams
-// the window to global memory with fully coalesced stores.  Warps whose 32 Gaussians emit more
-// than the window holds (huge splats) fall back to direct writes, large rectangles spread over
-// the whole warp.
+// One warp handles 32 consecutive entries of `order`.  The (Gaussian, tile) items of the 32
+// rectangles are flattened in emission order (depth-sorted Gaussian, then row-major tile) and dealt
+// 32 at a time to the lanes: every store instruction writes 32 consecutive list entries, and one
+// huge rectangle no longer serialises its warp (rasterizer_impl.cu:100-111 loops per thread and
+// writes 2- and 4-byte items at 32 unrelated addresses per instruction).  With exact-output
+// culling the surviving items are compacted with a ballot; their order, and therefore the
+// offsets of the scan, are preserved.
 __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ key_sorted,
                                                                 const uint32_t* __restrict__ offsets,
-                                                                const uint32_t* __restrict__ tiles_touched,
                                                                 const SplatRec* __restrict__ rec, const int* __restrict__ radii,
                                                                 int grid_x, int grid_y, unsigned flags, const float* __restrict__ pad_ptr,
                                                                 uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out)
 {
-    __shared__ uint16_t s_tile[kDupThreads / 32][kDupCap];
-    __shared__ uint32_t s_val[kDupThreads / 32][kDupCap];
+    __shared__ CullCtx s_ctx[kDupThreads / 32][32];
+    __shared__ int s_prefix[kDupThreads / 32][32];
     const unsigned full = 0xffffffffu;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool cull = (flags & 1u) != 0;
     const float pad = cull ? __ldg(pad_ptr) : 0.f;
-    uint32_t id = 0, cnt = 0, off = 0;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    float px = 0, py = 0, A = 0, B = 0, C = 0, thr = 0;
+    const int jw = (j & ~31);
+    if (jw >= P) return;
+    // the warp's output window starts at wbase: offsets are an inclusive scan in this order
+    const uint32_t wbase = (jw == 0) ? 0u : offsets[jw - 1];
+    if (offsets[min(jw + 31, P - 1)] == wbase) return;       // nothing to emit
+
+    CullCtx c;
+    c.ok = 0; c.w = 0; c.x0 = c.y0 = 0; c.id = 0;
+    int area = 0;
     if (j < P && key_sorted[j] != EX_INVISIBLE_KEY) {
-        id = order[j];
-        cnt = tiles_touched[id];
-        off = (j == 0) ? 0u : offsets[j - 1];
+        const uint32_t id = order[j];
         const float4 a = rec[id].a;
-        px = a.x; py = a.y; thr = a.w;
-        tile_rect(px, py, radii[id], grid_x, grid_y, x0, y0, x1, y1);
+        int x0, y0, x1, y1;
+        tile_rect(a.x, a.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
+        area = (x1 - x0) * (y1 - y0);
         if (cull) {
             const float4 b = rec[id].b;
-            A = b.x; B = b.y; C = b.z;
-        }
-    }
-    // the warp's output window [wbase, wbase + wtotal): offsets are an inclusive scan in this order
-    const int jw = (j & ~31);
-    const uint32_t wbase = (jw == 0) ? 0u : ((jw < P) ? offsets[jw - 1] : 0u);
-    const int jl = min(jw + 31, P - 1);
-    const uint32_t wtotal = (jw < P) ? (offsets[jl] - wbase) : 0u;
-    if (wtotal == 0) return;
-
-    if (wtotal <= (uint32_t)kDupCap) {
-        uint32_t o = off - wbase;
-        if (cnt) {
-            for (int ty = y0; ty < y1; ty++)
-                for (int tx = x0; tx < x1; tx++) {
-                    if (cull && tile_cannot_contribute(px, py, A, B, C, thr, tx, ty, pad)) continue;
-                    s_tile[warp][o] = (uint16_t)(ty * grid_x + tx);
-                    s_val[warp][o] = id;
-                    o++;
-                }
-        }
-        __syncwarp();
-        for (uint32_t t = lane; t < wtotal; t += 32) {
-            tile_out[wbase + t] = s_tile[warp][t];
-            val_out[wbase + t] = s_val[warp][t];
-        }
-        return;
-    }
-
-    // ---- fallback: direct writes
-    const bool big = cnt > 32;
-    if (cnt && !big) {
-        for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) {
-                if (cull && tile_cannot_contribute(px, py, A, B, C, thr, tx, ty, pad)) continue;
-                tile_out[off] = (uint16_t)(ty * grid_x + tx);
-                val_out[off] = id;
-                off++;
-            }
-    }
-    unsigned todo = __ballot_sync(full, big);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t bid = __shfl_sync(full, id, src);
-        const uint32_t boff = __shfl_sync(full, off, src);
-        const int bx0 = __shfl_sync(full, x0, src), by0 = __shfl_sync(full, y0, src);
-        const int bx1 = __shfl_sync(full, x1, src), by1 = __shfl_sync(full, y1, src);
-        const int w = bx1 - bx0, n = w * (by1 - by0);
-        if (!cull) {
-            for (int t = lane; t < n; t += 32) {
-                const int ty = by0 + t / w, tx = bx0 + t % w;
-                tile_out[boff + t] = (uint16_t)(ty * grid_x + tx);
-                val_out[boff + t] = bid;
-            }
+            c = cull_prepare(a.x, a.y, b.x, b.y, b.z, a.w, x0, y0, x1 - x0, id, pad);
         } else {
-            const float bpx = __shfl_sync(full, px, src), bpy = __shfl_sync(full, py, src);
-            const float bA = __shfl_sync(full, A, src), bB = __shfl_sync(full, B, src);
-            const float bC = __shfl_sync(full, C, src), bthr = __shfl_sync(full, thr, src);
-            uint32_t base = boff;
-            for (int t0 = 0; t0 < n; t0 += 32) {
-                const int t = t0 + lane;
-                bool keep = false;
-                int ty = 0, tx = 0;
-                if (t < n) {
-                    ty = by0 + t / w; tx = bx0 + t % w;
-                    keep = !tile_cannot_contribute(bpx, bpy, bA, bB, bC, bthr, tx, ty, pad);
-                }
-                const unsigned m = __ballot_sync(full, keep);
-                if (keep) {
-                    const uint32_t o = base + __popc(m & ((1u << lane) - 1u));
-                    tile_out[o] = (uint16_t)(ty * grid_x + tx);
-                    val_out[o] = bid;
-                }
-                base += __popc(m);
-            }
+            c.x0 = x0; c.y0 = y0; c.w = x1 - x0; c.id = id;
         }
+    }
+    int incl = area;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(full, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(full, incl, 31);
+    s_prefix[warp][lane] = incl - area;
+    s_ctx[warp][lane] = c;
+    __syncwarp();
+    uint32_t out = wbase;
+    for (int base = 0; base < total; base += 32) {
+        const int item = base + lane;
+        bool keep = false;
+        uint16_t tile = 0;
+        uint32_t id = 0;
+        if (item < total) {
+            const int src = expand_owner(s_prefix[warp], item);
+            const int local = item - s_prefix[warp][src];
+            const int w = s_ctx[warp][src].w;
+            const int ty = s_ctx[warp][src].y0 + local / w, tx = s_ctx[warp][src].x0 + local % w;
+            id = s_ctx[warp][src].id;
+            tile = (uint16_t)(ty * grid_x + tx);
+            keep = !(cull && cull_test(s_ctx[warp][src], tx, ty, pad));
+        }
+        const unsigned m = __ballot_sync(full, keep);
+        if (keep) {
+            const uint32_t o = out + __popc(m & ((1u << lane) - 1u));
+            tile_out[o] = tile;
+            val_out[o] = id;
+        }
+        out += __popc(m);
     }
 }
 
@@ -241,7 +205,7 @@ cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const 
     cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, s);
     if (e != cudaSuccess || R <= 0) return e;
     duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
-        P, g.order, g.key_sorted, g.offsets, g.tiles_touched, g.rec, radii, grid_x, grid_y, flags,
+        P, g.order, g.key_sorted, g.offsets, g.rec, radii, grid_x, grid_y, flags,
         reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted);
     size_t tb = b.temp_bytes;
     const int bit = (int)higher_msb((uint32_t)tiles);

@@ -215,49 +215,81 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gr
     y1 = min(grid_y, max(0, ay1));
 }
 
-// Exact-output tile culling (EX4DGS_FLAG_TILE_CULL): true when NO pixel of tile (tx,ty) can pass
-// the `alpha >= 1/255` test of the compositing loop for this splat, i.e. when the maximum of
-// `power` over the tile's pixel rectangle is below the splat's skip threshold.  Pixel centres
-// are integers + subpixel offset; callers pass a rectangle already widened by the maximal
-// |subpixel offset| they allow (offsets are in [-0.5,0.5] in the application; the flag is ignored
-// by the host wrapper when it cannot guarantee that).
-__device__ __forceinline__ bool tile_cannot_contribute(float cx, float cy, float A, float B, float C,
-                                                       float thr, int tx, int ty, float pad)
+// ---- exact-output tile culling (EX4DGS_FLAG_TILE_CULL) ---------------------------------------------
+// A (Gaussian, tile) instance can be dropped when NO pixel of the tile can pass the `alpha >= 1/255`
+// test of the compositing loop, i.e. when the maximum of `power` over the tile's pixel rectangle
+// (pixel centres are integers + subpixel offset, so the rectangle is widened by the frame's maximal
+// |offset| = pad) is below the splat's skip threshold.  q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy = -power
+// is convex, so its minimum over a rectangle that does not contain the centre lies on one of the
+// four edges and has a closed form.  Two kernels evaluate this (count in preprocess, emit in
+// duplicate) and must agree exactly: every operation is pinned, per-splat invariants are hoisted.
+struct CullCtx {
+    float cx, cy, A, B, C;
+    float nBoC, nBoA;     // -B/C, -B/A
+    float shrink;         // rounding guard, see cull_prepare
+    float tq;             // cull iff qmin*shrink > tq
+    int x0, y0, w;        // tile rectangle origin and width
+    uint32_t id;
+    int ok;               // 0: never cull (non-convex / ill-conditioned / bad pad)
+    int pad0, pad1;
+};
+
+__device__ __forceinline__ CullCtx cull_prepare(float cx, float cy, float A, float B, float C, float thr,
+                                                int x0, int y0, int w, uint32_t id, float pad)
 {
-    // NOTE: evaluated by two different kernels (count in preprocess, emit in duplicate) that must
-    // agree exactly, so every operation is pinned (no compiler-chosen FMA contraction).
-    // q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy  (= -power), minimised over the tile's pixel rectangle.
-    // The quadratic is convex when A,C > 0 and AC > B^2; otherwise be conservative.
-    if (!(pad <= 4096.f)) return false;          // NaN / absurd subpixel offsets: never cull
+    CullCtx c;
+    c.cx = cx; c.cy = cy; c.A = A; c.B = B; c.C = C; c.x0 = x0; c.y0 = y0; c.w = w; c.id = id;
+    c.pad0 = c.pad1 = 0;
     const float detc = fa(fm(A, C), -fm(B, B));
-    if (!(A > 0.f) || !(C > 0.f) || !(detc > 0.f)) return false;
-    const float dx0 = fa(fa((float)(tx * EX_TILE), -pad), -cx), dx1 = fa(fa((float)(tx * EX_TILE + EX_TILE - 1), pad), -cx);
-    const float dy0 = fa(fa((float)(ty * EX_TILE), -pad), -cy), dy1 = fa(fa((float)(ty * EX_TILE + EX_TILE - 1), pad), -cy);
+    c.ok = (A > 0.f) && (C > 0.f) && (detc > 0.f) && (pad <= 4096.f);
+    c.nBoC = __fdiv_rn(-B, C);
+    c.nBoA = __fdiv_rn(-B, A);
+    // The compositing loop evaluates `power` in float with a handful of roundings on terms that may
+    // cancel; the evaluated value is <= -q*(1 - eps*kappa) where kappa = (sqrt(AC)+|B|)^2/(AC-B^2)
+    // bounds (sum of |terms|)/q.  eps = 2e-5 is ~50x the real worst case (and also covers the
+    // rounding of this bound itself); very ill-conditioned conics are simply not culled.
+    const float sAC = fa(__fsqrt_rn(fm(A, C)), fabsf(B));
+    const float kappa = __fdiv_rn(fm(sAC, sAC), detc);
+    c.shrink = fa(1.0f, -fm(2e-5f, kappa));
+    if (!(c.shrink > 0.5f)) c.ok = 0;
+    c.tq = fa(1e-3f, -thr);          // -qmin*shrink + 1e-3 < thr  <=>  qmin*shrink > 1e-3 - thr
+    return c;
+}
+
+// true when tile (tx,ty) cannot contribute
+__device__ __forceinline__ bool cull_test(const CullCtx& c, int tx, int ty, float pad)
+{
+    if (!c.ok) return false;
+    const float dx0 = fa(fa((float)(tx * EX_TILE), -pad), -c.cx), dx1 = fa(fa((float)(tx * EX_TILE + EX_TILE - 1), pad), -c.cx);
+    const float dy0 = fa(fa((float)(ty * EX_TILE), -pad), -c.cy), dy1 = fa(fa((float)(ty * EX_TILE + EX_TILE - 1), pad), -c.cy);
     if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return false;   // centre inside
-    // centre outside => the minimum lies on the boundary: minimise over the 4 edges
     float qmin = 3.4e38f;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         const float dx = e ? dx1 : dx0;
-        const float dy = fminf(dy1, fmaxf(dy0, __fdiv_rn(-fm(B, dx), C)));
-        const float q = fa(fm(0.5f, fa(fm(fm(A, dx), dx), fm(fm(C, dy), dy))), fm(fm(B, dx), dy));
+        const float dy = fminf(dy1, fmaxf(dy0, fm(c.nBoC, dx)));
+        const float q = fa(fm(0.5f, fa(fm(fm(c.A, dx), dx), fm(fm(c.C, dy), dy))), fm(fm(c.B, dx), dy));
         qmin = fminf(qmin, q);
     }
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         const float dy = e ? dy1 : dy0;
-        const float dx = fminf(dx1, fmaxf(dx0, __fdiv_rn(-fm(B, dy), A)));
-        const float q = fa(fm(0.5f, fa(fm(fm(A, dx), dx), fm(fm(C, dy), dy))), fm(fm(B, dx), dy));
+        const float dx = fminf(dx1, fmaxf(dx0, fm(c.nBoA, dy)));
+        const float q = fa(fm(0.5f, fa(fm(fm(c.A, dx), dx), fm(fm(c.C, dy), dy))), fm(fm(c.B, dx), dy));
         qmin = fminf(qmin, q);
     }
-    // power_max = -qmin.  The compositing loop evaluates `power` in float with a handful of
-    // roundings on terms that may cancel; the evaluated value is <= -q*(1 - eps*kappa) where
-    // kappa = (sqrt(AC)+|B|)^2/(AC-B^2) bounds (sum of |terms|)/q.  eps = 2e-5 is ~50x the real
-    // worst case (and also covers the rounding of this bound itself); very ill-conditioned conics
-    // are simply not culled.
-    const float sAC = fa(__fsqrt_rn(fm(A, C)), fabsf(B));
-    const float kappa = __fdiv_rn(fm(sAC, sAC), detc);
-    const float shrink = fa(1.0f, -fm(2e-5f, kappa));
-    if (!(shrink > 0.5f)) return false;
-    return fa(fm(-qmin, shrink), 1e-3f) < thr;
+    return fm(qmin, c.shrink) > c.tq;
+}
+
+// Warp-cooperative enumeration of the (lane, tile) items of 32 rectangles: `area` items per lane,
+// flattened in (lane, row-major tile) order and dealt 32 at a time to the lanes, so that one huge
+// rectangle does not serialise the warp (the per-thread loops of rasterizer_impl.cu:100-111 do).
+// s_prefix: 32 ints of the warp (exclusive prefix of area).  Returns the owner lane of `item`.
+__device__ __forceinline__ int expand_owner(const int* s_prefix, int item)
+{
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1)
+        if (s_prefix[lo + step] <= item) lo += step;      // last lane with prefix <= item
+    return lo;
 }

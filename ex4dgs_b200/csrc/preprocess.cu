@@ -116,13 +116,20 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     const float* proj = s_cam + 16;
     const float* cam = s_cam + 32;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+    const bool valid = idx < p.P;
+    const bool cull = (p.flags & 1u) != 0;
+    const float pad = cull ? __ldg(p.pad_ptr) : 0.f;
 
     int radius_out = 0;
     uint32_t tiles = 0, key = EX_INVISIBLE_KEY;
-    const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (valid) { mx = __ldg(p.means3D + 3 * idx); my = __ldg(p.means3D + 3 * idx + 1); mz = __ldg(p.means3D + 3 * idx + 2); }
+    CullCtx cc;
+    cc.ok = 0; cc.w = 0;
+    int cull_area = 0;
 
     do {
+        if (!valid) break;
         // ---- frustum test (auxiliary.h:267-294)
         const float hx = xform_row(proj, 0, mx, my, mz);
         const float hy = xform_row(proj, 1, mx, my, mz);
@@ -246,13 +253,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
 
         uint32_t count = area;
-        if (p.flags & 1u) {
-            const float pad = __ldg(p.pad_ptr);
-            // conservative per-tile culling; identical test in the duplicate kernel
-            count = 0;
-            for (int ty = y0; ty < y1; ty++)
-                for (int tx = x0; tx < x1; tx++)
-                    count += tile_cannot_contribute(px, py, conA, conB, conC, thr, tx, ty, pad) ? 0u : 1u;
+        if (cull) {   // counted cooperatively below; identical test in the duplicate kernel
+            cc = cull_prepare(px, py, conA, conB, conC, thr, x0, y0, x1 - x0, (uint32_t)idx, pad);
+            cull_area = (int)area;
         }
 
         SplatRec rc;
@@ -267,10 +270,44 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         key = __float_as_uint(depth);
     } while (false);
 
-    p.radii[idx] = radius_out;
-    p.tiles_touched[idx] = tiles;
-    p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
-    p.val_in[idx] = (uint32_t)idx;
+    if (cull) {
+        // warp-cooperative count of the tiles that survive the exact-output culling
+        __shared__ CullCtx s_ctx[8][32];
+        __shared__ int s_prefix[8][32];
+        __shared__ int s_cnt[8][32];
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int incl = cull_area;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(full, incl, 31);
+        s_prefix[warp][lane] = incl - cull_area;
+        s_ctx[warp][lane] = cc;
+        s_cnt[warp][lane] = 0;
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int item = base + lane;
+            if (item < total) {
+                const int src = expand_owner(s_prefix[warp], item);
+                const CullCtx c = s_ctx[warp][src];
+                const int local = item - s_prefix[warp][src];
+                const int ty = c.y0 + local / c.w, tx = c.x0 + local % c.w;
+                if (!cull_test(c, tx, ty, pad)) atomicAdd(&s_cnt[warp][src], 1);
+            }
+        }
+        __syncwarp();
+        if (cull_area) tiles = (uint32_t)s_cnt[warp][lane];
+    }
+
+    if (valid) {
+        p.radii[idx] = radius_out;
+        p.tiles_touched[idx] = tiles;
+        p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
+        p.val_in[idx] = (uint32_t)idx;
+    }
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,

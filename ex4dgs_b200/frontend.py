@@ -1,0 +1,84 @@
+"""Fused model front-end: CGaussianModel's per-frame getters in one kernel.
+
+`interpolate_gaussians(...)` returns the flat `[P,.]` tensors that gaussian_renderer/__init__.py:62-81
+obtains from `pc.get_xyz_at_t(t)`, `pc.get_rotation_at_t(t)`, `pc.get_scaling()`, `pc.get_opacity_at_t(t)`
+(scene/c_gaussian_model.py:170-215,330-375), static Gaussians first, differentiable w.r.t. the
+model's native tensors.  interp_type "cube" and rot_interp_type "slerp" (the defaults of every
+reference config) are implemented; anything else must keep using the PyTorch getters.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _p(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+class _FusedFrontEnd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion,
+                opacity_motion, opacity_center, opacity_var, t, duration, interval, time_shift, var_min):
+        if not xyz.is_cuda:
+            raise RuntimeError("ex4dgs_b200: the fused front-end is CUDA-only")
+        lib = _lib.load()
+        dev = xyz.device
+        Ns, Nd = xyz.shape[0], xyz_motion.shape[0]
+        K = xyz_motion.shape[1] if Nd else 0
+        ten = [_c(x) for x in (xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion,
+                               opacity_motion, opacity_center, opacity_var)]
+        P = Ns + Nd
+        means = torch.empty(P, 3, device=dev)
+        rots = torch.empty(P, 4, device=dev)
+        scales = torch.empty(P, 3, device=dev)
+        opac = torch.empty(P, 1, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.ex4dgs_frontend_forward(Ns, Nd, K, *[_p(x) for x in ten], float(t), float(duration), float(interval),
+                                             float(time_shift), float(var_min), _p(means), _p(rots), _p(scales), _p(opac),
+                                             C.c_void_p(stream))
+        if rc < 0:
+            raise RuntimeError("ex4dgs_frontend_forward failed (%d): timestamp outside the keyframe range?" % rc)
+        ctx.save_for_backward(*ten)
+        ctx.scalars = (float(t), float(duration), float(interval), float(time_shift), float(var_min))
+        ctx.shapes = [x.shape for x in (xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion,
+                                        scaling_motion, opacity_motion, opacity_center, opacity_var)]
+        return means, rots, scales, opac
+
+    @staticmethod
+    def backward(ctx, g_means, g_rots, g_scales, g_opac):
+        lib = _lib.load()
+        (xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion, opacity_motion,
+         opacity_center, opacity_var) = ctx.saved_tensors
+        dev = xyz.device
+        Ns, Nd = xyz.shape[0], xyz_motion.shape[0]
+        K = xyz_motion.shape[1] if Nd else 0
+        outs = [torch.empty_like(x) for x in (xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion,
+                                              scaling_motion, opacity_motion, opacity_center, opacity_var)]
+        g = [_c(x) for x in (g_means, g_rots, g_scales, g_opac)]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        t, duration, interval, time_shift, var_min = ctx.scalars
+        with torch.cuda.device(dev):
+            rc = lib.ex4dgs_frontend_backward(Ns, Nd, K, _p(rotation_motion), _p(scaling), _p(opacity), _p(scaling_motion),
+                                              _p(opacity_motion), _p(opacity_center), _p(opacity_var),
+                                              t, duration, interval, time_shift, var_min,
+                                              *[_p(x) for x in g], *[_p(x) for x in outs], C.c_void_p(stream))
+        if rc < 0:
+            raise RuntimeError("ex4dgs_frontend_backward failed (%d)" % rc)
+        outs = [o.reshape(s) for o, s in zip(outs, ctx.shapes)]
+        return (*outs, None, None, None, None, None)
+
+
+def interpolate_gaussians(xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion,
+                          opacity_motion, opacity_center, opacity_var, *, t, duration, interval, time_shift, var_min):
+    """-> (means3D [P,3], rotations [P,4], scales [P,3], opacities [P,1]); static Gaussians first."""
+    return _FusedFrontEnd.apply(xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion,
+                                opacity_motion, opacity_center, opacity_var, t, duration, interval, time_shift, var_min)

@@ -173,7 +173,8 @@ int ex4dgs_mark_visible(
  *   static : xyz [Ns,3], xyz_disp [Ns,3], rotation [Ns,4] (raw), scaling [Ns,3] (log), opacity [Ns] (logit)
  *   dynamic: xyz_motion [Nd,K,3], rotation_motion [Nd,K,4], scaling_motion [Nd,3] (log),
  *            opacity_motion [Nd] (logit), opacity_center [Nd,2], opacity_var [Nd,2]
- *   t timestamp; duration, interval, time_shift, var_min (= var_pad/interval) as in the model.
+ *   t timestamp; duration, interval, time_shift, var_min (= var_pad/interval) as in the model (doubles:
+ *   Python floats).
  *   outputs: means3D [P,3], rotations [P,4], scales [P,3], opacities [P]   (P = Ns + Nd)
  */
 int ex4dgs_frontend_forward(
@@ -182,20 +183,20 @@ int ex4dgs_frontend_forward(
     const float* scaling, const float* opacity,
     const float* xyz_motion, const float* rotation_motion, const float* scaling_motion,
     const float* opacity_motion, const float* opacity_center, const float* opacity_var,
-    float t, float duration, float interval, float time_shift, float var_min,
+    double t, double duration, double interval, double time_shift, double var_min,
     float* means3D, float* rotations, float* scales, float* opacities,
     void* stream);
 
 /* Backward of ex4dgs_frontend_forward.  Gradient outputs for the keyframe tensors
  * (dL_dxyz_motion [Nd,K,3], dL_drotation_motion [Nd,K,4]) are fully written (zeros outside the
- * 4 / 2 keyframes that the frame touches). */
+ * 4 / 2 keyframes that the frame touches).  The timing scalars are doubles so that the host
+ * reproduces the Python arithmetic of c_gaussian_model.py:184-187 exactly. */
 int ex4dgs_frontend_backward(
     int Ns, int Nd, int K,
-    const float* xyz_disp_unused, const float* rotation_motion,
-    const float* scaling, const float* opacity,
+    const float* rotation_motion, const float* scaling, const float* opacity,
     const float* scaling_motion, const float* opacity_motion,
     const float* opacity_center, const float* opacity_var,
-    float t, float duration, float interval, float time_shift, float var_min,
+    double t, double duration, double interval, double time_shift, double var_min,
     const float* dL_dmeans3D, const float* dL_drotations, const float* dL_dscales, const float* dL_dopacities,
     float* dL_dxyz, float* dL_dxyz_disp, float* dL_drotation, float* dL_dscaling, float* dL_dopacity,
     float* dL_dxyz_motion, float* dL_drotation_motion, float* dL_dscaling_motion,
