@@ -232,8 +232,8 @@ int ex4dgs_forward(
             return fail(EX4DGS_ERR_INVALID, "SH degree %d needs %d coefficients, got M=%d", D, (D + 1) * (D + 1), M);
     }
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
-    if ((long long)grid_x * grid_y > 65536)
-        return fail(EX4DGS_ERR_UNSUPPORTED, "more than 65536 tiles (%dx%d) is not supported (16-bit tile keys)", grid_x, grid_y);
+    if ((long long)grid_x * grid_y > 65535)
+        return fail(EX4DGS_ERR_UNSUPPORTED, "more than 65535 tiles (%dx%d) is not supported (16-bit tile keys)", grid_x, grid_y);
 
     // image-sized scratch
     const size_t img_bytes = carve_image(nullptr, width, height).total;

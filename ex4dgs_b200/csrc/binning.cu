@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
     s_prefix[warp][lane] = incl - area;
     s_ctx[warp][lane] = c;
     __syncwarp();
-    uint32_t out = wbase;
     for (int base = 0; base < total; base += 32) {
         const int item = base + lane;
         bool keep = false;
@@ -90,19 +89,18 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
             tile = (uint16_t)(ty * grid_x + tx);
             keep = !(cull && cull_test(s_ctx[warp][src], tx, ty, pad));
         }
-        const unsigned m = __ballot_sync(full, keep);
-        if (keep) {
-            const uint32_t o = out + __popc(m & ((1u << lane) - 1u));
-            tile_out[o] = tile;
-            val_out[o] = id;
+        // culled instances keep their slot (the scan counted the full rectangle) but are keyed to
+        // the dump tile 0xFFFF, which the stable tile sort moves behind every real tile
+        if (item < total) {
+            tile_out[wbase + item] = keep ? tile : (uint16_t)0xFFFF;
+            val_out[wbase + item] = id;
         }
-        out += __popc(m);
     }
 }
 
 // ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
 // eight 16-bit keys per thread from one 128-bit load.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges, uint32_t dump)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = g * 8;
@@ -122,12 +120,12 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t*
         if (idx < L) {
             const uint32_t cur = t[k];
             if (idx == 0) {
-                ranges[cur].x = 0;
+                if (cur != dump) ranges[cur].x = 0;
             } else if (cur != prev) {
-                ranges[prev].y = idx;
-                ranges[cur].x = idx;
+                ranges[prev].y = idx;                 // prev is never the dump tile (it sorts last)
+                if (cur != dump) ranges[cur].x = idx;
             }
-            if (idx == L - 1) ranges[cur].y = L;
+            if (idx == L - 1 && cur != dump) ranges[cur].y = L;
             prev = cur;
         }
     }
@@ -209,10 +207,11 @@ cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const 
         reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted);
     size_t tb = b.temp_bytes;
     const int bit = (int)higher_msb((uint32_t)tiles);
+    const bool cull = (flags & 1u) != 0;
     e = cub::DeviceRadixSort::SortPairs(b.temp, tb, b.tile_unsorted, b.tile_sorted, b.val_unsorted, b.point_list,
-                                        R, 0, bit < 16 ? bit : 16, s);
+                                        R, 0, (cull || bit > 16) ? 16 : bit, s);
     if (e != cudaSuccess) return e;
     const int groups = (R + 7) / 8;
-    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges);
+    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu);
     return cudaGetLastError();
 }

@@ -293,3 +293,45 @@ __device__ __forceinline__ int expand_owner(const int* s_prefix, int item)
         if (s_prefix[lo + step] <= item) lo += step;      // last lane with prefix <= item
     return lo;
 }
+
+// ---- warp-level culling inside the compositing kernels ------------------------------------------
+// Bounding box of the pixel centres a warp works on (8x4 block incl. subpixel offsets).
+struct BlockBox {
+    float x0, x1, y0, y1;
+};
+
+__device__ __forceinline__ BlockBox block_box(float pxf, float pyf, bool use)
+{
+    BlockBox b;
+    b.x0 = use ? pxf : 3.0e38f;  b.x1 = use ? pxf : -3.0e38f;
+    b.y0 = use ? pyf : 3.0e38f;  b.y1 = use ? pyf : -3.0e38f;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        b.x0 = fminf(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, d));
+        b.x1 = fmaxf(b.x1, __shfl_xor_sync(0xffffffffu, b.x1, d));
+        b.y0 = fminf(b.y0, __shfl_xor_sync(0xffffffffu, b.y0, d));
+        b.y1 = fmaxf(b.y1, __shfl_xor_sync(0xffffffffu, b.y1, d));
+    }
+    return b;
+}
+
+// true when the splat (record words a = (x, y, depth, thr), b = (A, B, C, opacity)) cannot reach
+// alpha >= 1/255 at any pixel centre inside `box`.  q = -power >= 0.5*(det/C)*dx^2 and
+// >= 0.5*(det/A)*dy^2 (completing the square), so the alpha >= 1/255 region lies inside the
+// axis-aligned box |dx| <= sqrt(2 t C/det), |dy| <= sqrt(2 t A/det) with t = -thr.  Conservative by
+// construction; the guard `shrink` covers the float rounding of the per-pixel power exactly like
+// cull_prepare (kappa is bounded above by 4AC/det), ill-conditioned or non-convex conics are kept.
+__device__ __forceinline__ bool block_reject(const float4& a, const float4& b, const BlockBox& box)
+{
+    const float A = b.x, B = b.y, C = b.z;
+    const float det = A * C - B * B;
+    if (!(A > 0.f) || !(C > 0.f) || !(det > 0.f)) return false;
+    const float inv = 1.0f / det;
+    const float shrink = 1.0f - 8e-5f * (A * C * inv);
+    if (!(shrink > 0.5f)) return false;
+    const float tq = 1e-3f - a.w;                       // NaN thr -> comparisons below are false -> keep
+    const float lim = 2.0f * tq * inv / shrink * 1.0001f;
+    const float dx = fmaxf(fmaxf(box.x0 - a.x, a.x - box.x1), 0.f);
+    const float dy = fmaxf(fmaxf(box.y0 - a.y, a.y - box.y1), 0.f);
+    return (dx * dx > lim * C) || (dy * dy > lim * A);
+}

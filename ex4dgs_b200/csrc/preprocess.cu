@@ -116,20 +116,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     const float* proj = s_cam + 16;
     const float* cam = s_cam + 32;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = idx < p.P;
-    const bool cull = (p.flags & 1u) != 0;
-    const float pad = cull ? __ldg(p.pad_ptr) : 0.f;
+    if (idx >= p.P) return;
 
     int radius_out = 0;
     uint32_t tiles = 0, key = EX_INVISIBLE_KEY;
-    float mx = 0.f, my = 0.f, mz = 0.f;
-    if (valid) { mx = __ldg(p.means3D + 3 * idx); my = __ldg(p.means3D + 3 * idx + 1); mz = __ldg(p.means3D + 3 * idx + 2); }
-    CullCtx cc;
-    cc.ok = 0; cc.w = 0;
-    int cull_area = 0;
+    const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
 
     do {
-        if (!valid) break;
         // ---- frustum test (auxiliary.h:267-294)
         const float hx = xform_row(proj, 0, mx, my, mz);
         const float hy = xform_row(proj, 1, mx, my, mz);
@@ -252,11 +245,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
         const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
 
-        uint32_t count = area;
-        if (cull) {   // counted cooperatively below; identical test in the duplicate kernel
-            cc = cull_prepare(px, py, conA, conB, conC, thr, x0, y0, x1 - x0, (uint32_t)idx, pad);
-            cull_area = (int)area;
-        }
+        // with EX4DGS_FLAG_TILE_CULL the duplicate kernel keys culled instances to the dump tile;
+        // the count stays the full rectangle so that no second pass is needed before the scan
+        const uint32_t count = area;
 
         SplatRec rc;
         rc.a = make_float4(px, py, depth, thr);
@@ -270,44 +261,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         key = __float_as_uint(depth);
     } while (false);
 
-    if (cull) {
-        // warp-cooperative count of the tiles that survive the exact-output culling
-        __shared__ CullCtx s_ctx[8][32];
-        __shared__ int s_prefix[8][32];
-        __shared__ int s_cnt[8][32];
-        const unsigned full = 0xffffffffu;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        int incl = cull_area;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(full, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int total = __shfl_sync(full, incl, 31);
-        s_prefix[warp][lane] = incl - cull_area;
-        s_ctx[warp][lane] = cc;
-        s_cnt[warp][lane] = 0;
-        __syncwarp();
-        for (int base = 0; base < total; base += 32) {
-            const int item = base + lane;
-            if (item < total) {
-                const int src = expand_owner(s_prefix[warp], item);
-                const CullCtx c = s_ctx[warp][src];
-                const int local = item - s_prefix[warp][src];
-                const int ty = c.y0 + local / c.w, tx = c.x0 + local % c.w;
-                if (!cull_test(c, tx, ty, pad)) atomicAdd(&s_cnt[warp][src], 1);
-            }
-        }
-        __syncwarp();
-        if (cull_area) tiles = (uint32_t)s_cnt[warp][lane];
-    }
-
-    if (valid) {
-        p.radii[idx] = radius_out;
-        p.tiles_touched[idx] = tiles;
-        p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
-        p.val_in[idx] = (uint32_t)idx;
-    }
+    p.radii[idx] = radius_out;
+    p.tiles_touched[idx] = tiles;
+    p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
+    p.val_in[idx] = (uint32_t)idx;
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,

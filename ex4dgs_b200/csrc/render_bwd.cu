@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     __shared__ float4 s_rec[2][kSub * 3];
     __shared__ __align__(16) float s_part[8][kSub][16];
     __shared__ unsigned long long s_mask[8];
+    __shared__ uint8_t s_list[8][kSub];
     __shared__ int s_start;
 
     const int tid = threadIdx.x;
@@ -128,6 +129,9 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     if (start == 0) return;
     const int rounds = (start + kSub - 1) / kSub;
 
+    // pixels that received nothing in the forward never contribute: keep them out of the warp's box
+    const BlockBox box = block_box(pxf, pyf, last_contributor > 0);
+    const bool warp_idle = __all_sync(0xffffffffu, last_contributor == 0);
     const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
     const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     float T = T_final;
@@ -158,8 +162,22 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
         const float4* __restrict__ s = s_rec[r & 1];
         const int cnt = min(kSub, start - r * kSub);
         unsigned long long mask = 0ull;
+        // which splats of the sub-batch can touch this warp's pixel block at all (exact, see block_reject)
+        int nw = 0;
+        if (!warp_idle) {
+            for (int g = 0; g < cnt; g += 32) {
+                const int jj = g + lane;
+                bool keep = false;
+                if (jj < cnt) keep = !block_reject(s[jj * 3], s[jj * 3 + 1], box);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
+                nw += __popc(m);
+            }
+            __syncwarp();
+        }
 #pragma unroll 2
-        for (int j = 0; j < cnt; j++) {
+        for (int e = 0; e < nw; e++) {
+            const int j = s_list[warp][e];
             const int q = start - 1 - (r * kSub + j);
             const float4 a = s[j * 3 + 0];
             const float4 b = s[j * 3 + 1];
