@@ -133,6 +133,7 @@ class Frame:
         self.d_gt = torch.empty(3, cam.H, cam.W, device=dev)
         self.d_cam = torch.empty(35, device=dev)
         self.h_loss = torch.zeros(1).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=dev)
         self.R = -1
         self.last = None
 
@@ -164,11 +165,17 @@ class Frame:
         self._zero()
 
     def step_e2e(self, group=None):
+        # camera first (the forward needs it); the ground-truth image is only needed by the loss, so
+        # its H2D copy runs on a side stream and overlaps the forward - still inside the timed step
+        main = torch.cuda.current_stream(self.dev)
         self.d_cam.copy_(self.h_cam, non_blocking=True)
-        self.d_gt.copy_(self.h_gt, non_blocking=True)
+        self.copy_stream.wait_stream(main)           # previous step's loss has consumed d_gt
+        with torch.cuda.stream(self.copy_stream):
+            self.d_gt.copy_(self.h_gt, non_blocking=True)
         c = self.d_cam
         rs = self.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
         color, radii, depth, flow, acc, idxs = self._raster(rs)
+        main.wait_stream(self.copy_stream)
         loss = (color - self.d_gt).abs().mean()
         torch.autograd.backward([loss, flow], [None, self.go["grad_flow"]])
         l = loss.detach().reshape(1)
@@ -234,7 +241,7 @@ def main():
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--profile-in-timed", type=int, default=1,
                     help="record per-stage CUDA events inside the timed region (1) or in a separate pass (0)")
-    ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "0")))
+    ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
     args = ap.parse_args()
     rank, local_rank, ws = dist_env()
     K, W = args.steps, max(args.warmup, 3)

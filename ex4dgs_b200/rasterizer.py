@@ -20,8 +20,8 @@ from . import _lib
 
 # Process-wide default for the exact-output tile culling (include/ex4dgs_raster.h,
 # EX4DGS_FLAG_TILE_CULL).  Outputs and gradients are identical either way; with 0 the internal
-# tile lists are bit-identical to the reference's.  Override with EX4DGS_TILE_CULL=0/1.
-_DEFAULT_FLAGS = int(os.environ.get("EX4DGS_TILE_CULL", "0")) & 1
+# tile lists are bit-identical to the reference's.  Default on; override with EX4DGS_TILE_CULL=0/1.
+_DEFAULT_FLAGS = int(os.environ.get("EX4DGS_TILE_CULL", "1")) & 1
 
 
 def set_default_flags(tile_cull: bool) -> None:

@@ -25,8 +25,23 @@ GRAD_RTOL = 2e-3      # 1e-3 of the north star + the reference's own atomic-orde
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _check_ints(a, b):
+@pytest.fixture(params=[0, 1], ids=["exact-lists", "tile-cull"])
+def cull(request):
+    """Run the parity cases in both modes of EX4DGS_FLAG_TILE_CULL: with the flag clear the tile
+    lists must equal the reference's bit for bit; with it set only the user-visible outputs and the
+    gradients are compared (the internal lists are shorter by construction)."""
+    mod = U.ours_module()
+    old = mod.get_default_flags()
+    mod.set_default_flags(bool(request.param))
+    yield request.param
+    mod.set_default_flags(bool(old))
+
+
+def _check_ints(a, b, cull=0):
     assert np.array_equal(a["radii"], b["radii"])
+    assert np.array_equal(a["idxs"], b["idxs"])
+    if cull:
+        return
     ia, ib = a["inter"], b["inter"]
     assert ia["R"] == ib["R"]
     assert np.array_equal(ia["tiles_touched"], ib["tiles_touched"])
@@ -50,16 +65,16 @@ def _check_floats(a, b, grads=True):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_against_cpu_oracle(built, name):
+def test_against_cpu_oracle(built, name, cull):
     sc, kw = make_case(name)
     ours = U.run_impl(U.ours_module(), sc, kind="ours", **kw)
     orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", **kw)
-    _check_ints(ours, orc)
+    _check_ints(ours, orc, cull)
     _check_floats(ours, orc)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_against_reference_golden(built, name):
+def test_against_reference_golden(built, name, cull):
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     if not os.path.exists(path):
         pytest.skip("golden not generated yet")
@@ -70,8 +85,10 @@ def test_against_reference_golden(built, name):
     ref["inter"] = {k[6:]: g[k] for k in g.files if k.startswith("inter_")}
     ref["inter"]["R"] = int(ref["inter"]["R"])
     ref["grads"] = {k[5:]: g[k] for k in g.files if k.startswith("grad_")}
-    _check_ints(ours, ref)
+    _check_ints(ours, ref, cull)
     _check_floats(ours, ref)
+    if cull:
+        return
     # the reference's 64-bit keys are (tile << 32 | depth bits) of our lists
     keys = (ours["inter"]["tile_sorted"].astype(np.uint64) << np.uint64(32)) | \
         ours["inter"]["depths"][ours["inter"]["point_list"]].view(np.uint32).astype(np.uint64)
@@ -79,16 +96,16 @@ def test_against_reference_golden(built, name):
 
 
 @pytest.mark.parametrize("cfg,kw", [("C1", {}), ("C1d", dict(pose="tilted", dir_nonzero=True))])
-def test_config1_against_oracle(built, cfg, kw):
+def test_config1_against_oracle(built, cfg, kw, cull):
     sc = synth.make_config(cfg, **kw)
     ours = U.run_impl(U.ours_module(), sc, kind="ours", grad_kind="all")
     orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", grad_kind="all")
-    _check_ints(ours, orc)
+    _check_ints(ours, orc, cull)
     _check_floats(ours, orc)
 
 
 @pytest.mark.parametrize("cfg", ["C1d", "C2"])
-def test_live_against_compiled_reference(built, cfg):
+def test_live_against_compiled_reference(built, cfg, cull):
     ref = U.reference_module()
     if ref is None:
         pytest.skip("oracle/_ref not built")
@@ -96,7 +113,7 @@ def test_live_against_compiled_reference(built, cfg):
     grads = cfg != "C2"                       # config 2 is forward-only (BASELINE.json)
     ours = U.run_impl(U.ours_module(), sc, kind="ours", grads=True, grad_kind="all")
     r = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind="all")
-    _check_ints(ours, r)
+    _check_ints(ours, r, cull)
     assert np.array_equal(ours["color"].view(np.uint32), r["color"].view(np.uint32)), "image not bit-identical"
     _check_floats(ours, r, grads=grads)
 
@@ -105,6 +122,7 @@ def test_full_size_properties(built):
     """Config 3 (2.0M Gaussians, 1352x1014): properties that need no second implementation."""
     sc = synth.make_config("C3")
     mod = U.ours_module()
+    old_flags = mod.get_default_flags()
     mod.set_default_flags(False)
     a = U.run_impl(mod, sc, kind="ours")
     ia = a["inter"]
@@ -141,17 +159,18 @@ def test_full_size_properties(built):
     try:
         c = U.run_impl(mod, sc, kind="ours")
     finally:
-        mod.set_default_flags(False)
+        mod.set_default_flags(bool(old_flags))
     for k in ("color", "depth", "acc", "flow", "idxs", "radii"):
         assert np.array_equal(a[k], c[k]), k
-    assert c["inter"]["R"] <= R
+    kept = int((c["inter"]["ranges"][:, 1].astype(np.int64) - c["inter"]["ranges"][:, 0]).sum())
+    assert kept < R and c["inter"]["R"] == R          # culled instances sit in the dump tile behind every range
     for k, g in a["grads"].items():
         assert U.rel_err(c["grads"][k], g, U.grad_floor(g)) <= 1e-3, k
     # linearity of the backward in the upstream gradient (checksum-of-checksums style property)
     assert np.isfinite(a["grads"]["means3D"]).all()
 
 
-def test_edge_cases(built):
+def test_edge_cases(built, cull):
     mod = U.ours_module()
     dev = "cuda"
     # P == 0: outputs keep the reference's fill values (rasterize_points.cu:73-90)
@@ -176,7 +195,7 @@ def test_edge_cases(built):
     sc3 = synth.make_scene(3, 0, 200, 120, sigma_px=120.0, seed=7)
     a = U.run_impl(mod, sc3, kind="ours")
     b = U.run_impl(U.oracle_module(), sc3, dev="cpu", kind="oracle")
-    _check_ints(a, b)
+    _check_ints(a, b, cull)
     _check_floats(a, b)
 
 
@@ -193,7 +212,7 @@ def test_mark_visible(built):
     assert 0 < vis.sum() < vis.size
 
 
-def test_non_default_stream_and_reentrancy(built):
+def test_non_default_stream_and_reentrancy(built, cull):
     """The library launches on torch's current stream (the reference uses the legacy default stream)."""
     mod = U.ours_module()
     sc, kw = make_case("gold_base")
