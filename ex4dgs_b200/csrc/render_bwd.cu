@@ -16,21 +16,13 @@
 //    reductions per (tile, splat) instead of 14 per (pixel, splat);
 //  * traversal starts at the tile's largest `n_contrib` instead of the end of the range
 //    (backward.cu:552-577 re-loads the whole range and skips entries one by one);
-//  * splat records are gathered with 16-byte asynchronous copies one sub-batch ahead.
+//  * splat records are gathered with TMA bulk copies (48 bytes per splat, mbarrier-tracked) one
+//    sub-batch ahead.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace {
 
 constexpr int kSub = 64;   // splats per sub-batch
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v)
 {
@@ -81,6 +73,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     __shared__ unsigned long long s_mask[8];
     __shared__ uint8_t s_list[8][kSub];
     __shared__ int s_start;
+    __shared__ __align__(8) unsigned long long s_bar[2];     // one mbarrier per ring buffer
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -92,7 +85,12 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     const size_t HW = (size_t)p.H * p.W;
 
     const uint2 range = p.ranges[tile];
-    if (tid == 0) s_start = 0;
+    if (tid == 0) {
+        s_start = 0;
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
 
     float pxf = (float)pix_x, pyf = (float)pix_y;
@@ -139,25 +137,25 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
     float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
 
-    // staging: thread -> (splat jj, 16-byte part v)
-    const int st_j = tid >> 2, st_v = tid & 3;
+    // TMA staging: thread t < kSub owns slot t and issues one 48-byte bulk copy of its splat's record
+    // (the dir3D word is not needed here); thread 0 announces the byte count to the buffer's mbarrier
     auto list_id = [&](int r) -> int {
-        const int q = start - 1 - (r * kSub + st_j);
-        return (q >= 0 && st_v < 3) ? (int)__ldg(p.point_list + range.x + q) : -1;
+        const int q = start - 1 - (r * kSub + tid);
+        return (tid < kSub && q >= 0) ? (int)__ldg(p.point_list + range.x + q) : -1;
     };
-    auto stage = [&](int buf, int id) {
-        if (id >= 0) cp_async16(&s_rec[buf][st_j * 3 + st_v], reinterpret_cast<const float4*>(p.rec + id) + st_v);
+    auto stage = [&](int buf, int r, int id) {
+        const int cnt_b = min(kSub, start - r * kSub);
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[buf], (unsigned)(cnt_b * 48));
+        if (id >= 0) tma_bulk_g2s(&s_rec[buf][tid * 3], p.rec + id, 48, &s_bar[buf]);
     };
-    stage(0, list_id(0));
-    cp_async_commit();
+    stage(0, 0, list_id(0));
     int id_next = (rounds > 1) ? list_id(1) : -1;
 
     for (int r = 0; r < rounds; r++) {
-        cp_async_wait_all();
-        __syncthreads();                       // (A) batch r landed; s_part / buffer (r+1)&1 free
+        mbar_wait(&s_bar[r & 1], (unsigned)((r >> 1) & 1));      // sub-batch r has landed
+        __syncthreads();                       // (A) s_part / buffer (r+1)&1 free
         if (r + 1 < rounds) {
-            stage((r + 1) & 1, id_next);
-            cp_async_commit();
+            stage((r + 1) & 1, r + 1, id_next);
             id_next = (r + 2 < rounds) ? list_id(r + 2) : -1;
         }
         const float4* __restrict__ s = s_rec[r & 1];
@@ -262,273 +260,10 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Deferred-gradient variant (default).  Profiling the kernel above shows two thirds of its issued
-// instructions in the per-splat "heavy" block (gradient math + 16-value butterfly), executed by a
-// whole warp although on average only ~8 of its 32 pixels contribute to a given splat.  Here the
-// warp-divergent part per (pixel, splat) pair is cut down to the strictly sequential state update
-// (T, the colour recursion folded into one scalar, the cumulative dL_dacc), and the contributing
-// pairs are pushed as 8-word records into a per-warp shared-memory queue.  Whenever 32 records are
-// queued, all 32 lanes process one record each: the 13 gradient values are computed at full lane
-// utilisation and reduced per splat with a segmented scan (records arrive sorted by splat), then
-// added to the warp's private partial-sum slice.  The CTA-level fold and the 16-byte vector
-// reductions into the per-Gaussian accumulator are unchanged.
-// ---------------------------------------------------------------------------------------------
-constexpr int kQ = 64;                      // queue capacity per warp (records)
-
-struct BwdSmem {
-    float4 rec[2][kSub * 3];                // staged splat records
-    float part[8][kSub][16];                // per-warp partial sums
-    float pc[8][32][8];                     // per-pixel constants: dpix[3], dflow[3], -, -
-    float q[8][8][kQ];                      // queue, SoA: 0 meta 1 w 2 v2 3 da 4 dacc 5 G 6 dx 7 dy
-    unsigned long long mask[8];
-    uint8_t list[8][kSub];
-    int start;
-};
-
-__global__ void __launch_bounds__(256, 3) render_bwd_deferred_kernel(const __grid_constant__ RenderParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
-    const unsigned full = 0xffffffffu;
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.y * p.grid_x + blockIdx.x;
-    const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = pix_x < p.W && pix_y < p.H;
-    const int pix_id = p.W * pix_y + pix_x;
-    const size_t HW = (size_t)p.H * p.W;
-
-    const uint2 range = p.ranges[tile];
-    if (tid == 0) S.start = 0;
-    __syncthreads();
-
-    float pxf = (float)pix_x, pyf = (float)pix_y;
-    float T_final = 0.f, final_depth = 0.f;
-    int last_contributor = 0;
-    float dL_ddepth = 0.f, dL_dacc = 0.f;
-    float dflow0 = 0.f, dflow1 = 0.f, dflow2 = 0.f;
-    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f;
-    if (inside) {
-        const float2 so = __ldg(p.subpixel_offset + pix_id);
-        pxf = fa(pxf, so.x);
-        pyf = fa(pyf, so.y);
-        T_final = p.final_T[pix_id];
-        last_contributor = (int)p.n_contrib[pix_id];
-        const float final_acc = __ldg(p.out_acc + pix_id);
-        final_depth = __ldg(p.out_depth + pix_id);
-        dL_ddepth = __ldg(p.dL_ddepth + pix_id);
-        if (final_acc > 0.0f) {
-            dL_ddepth = dL_ddepth / final_acc;
-            dflow0 = __ldg(p.dL_dflow + pix_id) / final_acc;
-            dflow1 = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
-            dflow2 = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
-            dL_dacc = __ldg(p.dL_dacc + pix_id);
-        }
-        dpix0 = __ldg(p.dL_dpix + pix_id);
-        dpix1 = __ldg(p.dL_dpix + HW + pix_id);
-        dpix2 = __ldg(p.dL_dpix + 2 * HW + pix_id);
-    }
-    {
-        float* pc = S.pc[warp][lane];
-        *reinterpret_cast<float4*>(pc) = make_float4(dpix0, dpix1, dpix2, dflow0);
-        *reinterpret_cast<float4*>(pc + 4) = make_float4(dflow1, dflow2, 0.f, 0.f);
-        const int wmax = __reduce_max_sync(full, last_contributor);
-        if (lane == 0 && wmax > 0) atomicMax(&S.start, wmax);
-    }
-    __syncthreads();
-    const int start = S.start;            // positions >= start contribute to no pixel of the tile
-    if (start == 0) return;
-    const int rounds = (start + kSub - 1) / kSub;
-
-    const BlockBox box = block_box(pxf, pyf, last_contributor > 0);
-    const bool warp_idle = __all_sync(full, last_contributor == 0);
-    const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
-    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
-    float T = T_final;
-    float Srec = 0.f, last_alpha = 0.f, last_cdot = 0.f;      // colour recursion folded with dL_dpixel
-
-    float (*Q)[kQ] = S.q[warp];
-    int q_head = 0, q_tail = 0;                               // warp-uniform
-
-    // phase 2: lanes < n take one queued record each
-    auto flush = [&](int n, const float4* __restrict__ s) {
-        __syncwarp();
-        int j = 255;
-        float v[13];
-#pragma unroll
-        for (int k = 0; k < 13; k++) v[k] = 0.f;
-        if (lane < n) {
-            const int e = (q_head + lane) & (kQ - 1);
-            const int meta = __float_as_int(Q[0][e]);
-            j = meta & 0xff;
-            const int src = meta >> 8;
-            const float w = Q[1][e], v2 = Q[2][e], da = Q[3][e], dacc = Q[4][e], G = Q[5][e], dx = Q[6][e], dy = Q[7][e];
-            const float4 c0 = *reinterpret_cast<const float4*>(S.pc[warp][src]);
-            const float4 c1 = *reinterpret_cast<const float4*>(S.pc[warp][src] + 4);
-            const float4 b = s[j * 3 + 1];
-            const float dL_dG = b.w * da;
-            const float gdx = G * dx, gdy = G * dy;
-            v[0] = dL_dG * (-gdx * b.x - gdy * b.y) * ddelx_dx;
-            v[1] = dL_dG * (-gdy * b.z - gdx * b.y) * ddely_dy;
-            v[2] = v2;
-            v[3] = G * da + G * dacc;
-            v[4] = -0.5f * gdx * dx * dL_dG;
-            v[5] = -0.5f * gdx * dy * dL_dG;
-            v[6] = -0.5f * gdy * dy * dL_dG;
-            v[7] = w * c0.x; v[8] = w * c0.y; v[9] = w * c0.z;
-            v[10] = w * c0.w; v[11] = w * c1.x; v[12] = w * c1.y;
-        }
-        // segmented inclusive scan over lanes (records are sorted by splat)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int ju = __shfl_up_sync(full, j, d);
-            const bool take = (lane >= d) && (ju == j);
-#pragma unroll
-            for (int k = 0; k < 13; k++) {
-                const float t = __shfl_up_sync(full, v[k], d);
-                if (take) v[k] += t;
-            }
-        }
-        const int jn = __shfl_down_sync(full, j, 1);
-        if (lane < n && (lane == 31 || jn != j)) {
-            float* dst = S.part[warp][j];
-            // slot order of the accumulator: 0..3 = mean2D.xyz + opacity, 4..6 conic, 8..10 colour, 12..14 dir
-            dst[0] += v[0]; dst[1] += v[1]; dst[2] += v[2]; dst[3] += v[3];
-            dst[4] += v[4]; dst[5] += v[5]; dst[6] += v[6];
-            dst[8] += v[7]; dst[9] += v[8]; dst[10] += v[9];
-            dst[12] += v[10]; dst[13] += v[11]; dst[14] += v[12];
-        }
-        q_head += n;
-        __syncwarp();
-    };
-
-    // staging: thread -> (splat jj, 16-byte part v)
-    const int st_j = tid >> 2, st_v = tid & 3;
-    auto list_id = [&](int r) -> int {
-        const int q = start - 1 - (r * kSub + st_j);
-        return (q >= 0 && st_v < 3) ? (int)__ldg(p.point_list + range.x + q) : -1;
-    };
-    auto stage = [&](int buf, int id) {
-        if (id >= 0) cp_async16(&S.rec[buf][st_j * 3 + st_v], reinterpret_cast<const float4*>(p.rec + id) + st_v);
-    };
-    stage(0, list_id(0));
-    cp_async_commit();
-    int id_next = (rounds > 1) ? list_id(1) : -1;
-
-    for (int r = 0; r < rounds; r++) {
-        cp_async_wait_all();
-        __syncthreads();                       // (A) batch r landed; part / buffer (r+1)&1 free
-        if (r + 1 < rounds) {
-            stage((r + 1) & 1, id_next);
-            cp_async_commit();
-            id_next = (r + 2 < rounds) ? list_id(r + 2) : -1;
-        }
-        const float4* __restrict__ s = S.rec[r & 1];
-        const int cnt = min(kSub, start - r * kSub);
-        unsigned long long mask = 0ull;
-        int nw = 0;
-        if (!warp_idle) {
-            for (int g = 0; g < cnt; g += 32) {
-                const int jj = g + lane;
-                bool keep = false;
-                if (jj < cnt) keep = !block_reject(s[jj * 3], s[jj * 3 + 1], box);
-                const unsigned m = __ballot_sync(full, keep);
-                if (keep) S.list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
-                nw += __popc(m);
-            }
-            __syncwarp();
-        }
-        // phase 1: sequential per-pixel state, contributing pairs are queued
-        for (int e = 0; e < nw; e++) {
-            const int j = S.list[warp][e];
-            const int q = start - 1 - (r * kSub + j);
-            const float4 a = s[j * 3 + 0];
-            const float4 b = s[j * 3 + 1];
-            const float dx = fa(a.x, -pxf), dy = fa(a.y, -pyf);
-            const float power = ff(ff(dx, fm(dx, b.x), fm(fm(b.z, dy), dy)), -0.5f, -fm(fm(b.y, dx), dy));
-            bool contributes = (q < last_contributor) && !(power > 0.0f) && !(power < a.w);
-            float G = 0.f, alpha = 0.f;
-            if (contributes) {
-                G = expf(power);
-                alpha = fminf(0.99f, fm(b.w, G));
-                contributes = !(alpha < 1.0f / 255.0f);
-            }
-            const unsigned m = __ballot_sync(full, contributes);
-            if (m == 0) continue;
-            if (!((mask >> j) & 1ull)) {       // first contribution to this splat in the sub-batch
-                if (lane < 16) S.part[warp][j][lane] = 0.f;
-                mask |= 1ull << j;
-            }
-            if (contributes) {
-                const float4 c = s[j * 3 + 2];
-                const float inv1ma = 1.f / (1.f - alpha);
-                T = T * inv1ma;
-                const float w = alpha * T;               // dchannel_dcolor
-                float dL_dalpha = 0.0f, v2 = 0.f;
-                const float dep = a.z;
-                if ((dep > p.min_depth) & (w > 0.0f)) {
-                    v2 = dL_ddepth * w;
-                    dL_dalpha += (final_depth - dep) * dL_ddepth * T;
-                }
-                // sum_ch (c_ch - accum_rec_ch) * dpix_ch with accum_rec folded into one scalar
-                const float cdot = c.x * dpix0 + c.y * dpix1 + c.z * dpix2;
-                Srec = last_alpha * last_cdot + (1.f - last_alpha) * Srec;
-                last_cdot = cdot;
-                dL_dalpha += cdot - Srec;
-                dL_dalpha *= T;
-                dL_dacc *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                const int pos = (q_tail + __popc(m & ((1u << lane) - 1u))) & (kQ - 1);
-                Q[0][pos] = __int_as_float(j | (lane << 8));
-                Q[1][pos] = w; Q[2][pos] = v2; Q[3][pos] = dL_dalpha; Q[4][pos] = dL_dacc;
-                Q[5][pos] = G; Q[6][pos] = dx; Q[7][pos] = dy;
-            }
-            q_tail += __popc(m);
-            if (q_tail - q_head >= 32) flush(32, s);
-        }
-        if (q_tail > q_head) flush(q_tail - q_head, s);
-        if (lane == 0) S.mask[warp] = mask;
-        __syncthreads();                       // (B) partial sums of all warps complete
-        {
-            const int jj = tid >> 2, qd = tid & 3;
-            if (jj < cnt) {
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool any = false;
-#pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    if ((S.mask[w] >> jj) & 1ull) {
-                        const float4 t = *reinterpret_cast<const float4*>(&S.part[w][jj][4 * qd]);
-                        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-                        any = true;
-                    }
-                }
-                if (any) {
-                    const int id = __float_as_int(s[jj * 3 + 2].w);
-                    red_add_v4(reinterpret_cast<float*>(p.gacc + id) + 4 * qd, sum);
-                }
-            }
-        }
-    }
-}
-
 }  // namespace
 
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
     dim3 grid(grid_x, grid_y, 1);
-    static const bool legacy = (getenv("EX4DGS_BWD_LEGACY") != nullptr);
-    if (legacy) {
-        render_bwd_kernel<<<grid, 256, 0, s>>>(p);
-        return;
-    }
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(render_bwd_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
-        configured = true;
-    }
-    render_bwd_deferred_kernel<<<grid, 256, sizeof(BwdSmem), s>>>(p);
+    render_bwd_kernel<<<grid, 256, 0, s>>>(p);
 }

@@ -223,7 +223,8 @@ size_t ex4dgs_binning_bytes(int R);
 size_t ex4dgs_image_bytes(int width, int height);
 
 /* ---- measurement hooks (bench.py; not part of the reference interface) -------------------------
- * While profiling is on, every ex4dgs_forward / ex4dgs_backward of the calling thread records
+ * While profiling is on (process-wide: autograd runs the backward on its own thread), every
+ * ex4dgs_forward / ex4dgs_backward records
  * CUDA events at its stage boundaries on the launching stream.  ex4dgs_profile_read synchronises
  * those events, ADDS the elapsed milliseconds per stage into ms[0..EX4DGS_NUM_STAGES) and the
  * number of frames into *frames, and clears the recorded set.  Stages:
@@ -232,7 +233,7 @@ size_t ex4dgs_image_bytes(int width, int height);
 #define EX4DGS_NUM_STAGES 6
 void ex4dgs_profile_enable(int on);
 int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd);
-/* number of kernels of this library (not CUB's) launched by the calling thread so far */
+/* number of kernels of this library (not CUB's) launched by this process so far */
 unsigned long long ex4dgs_launch_count(void);
 
 int ex4dgs_abi_version(void);
