@@ -15,6 +15,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local int g_last_R = 0;     // sizing hint only (previous frame of this thread)
 // Measurement state is process-wide: autograd runs the backward on its own thread.
 std::atomic<bool> g_prof{false};
 std::atomic<unsigned long long> g_launches{0};
@@ -249,7 +250,8 @@ int ex4dgs_forward(
     rp.final_T = img.final_T; rp.n_contrib = img.n_contrib; rp.tile_batches = img.tile_batches; rp.ranges = img.ranges;
     rp.out_color = out_color; rp.out_depth = out_depth; rp.out_acc = out_acc; rp.out_flow = out_flow; rp.out_idx = out_idx;
 
-    int R = 0;
+    int R = 0, spec_R = 0;
+    void* spec_base = nullptr;
     GeometryState geom;
     memset(&geom, 0, sizeof(geom));
     BinningState bin;
@@ -297,15 +299,31 @@ int ex4dgs_forward(
         prof.mark();
         uint32_t r32 = 0;
         CK(cudaMemcpyAsync(&r32, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning
+        // buffer sized from the previous frame of this thread (+25 %): the allocator callback (a trip
+        // into Python) then overlaps the device work instead of extending the idle gap after the sync.
+        if (g_last_R > 0) {
+            const long long guess = (long long)g_last_R + g_last_R / 4 + 65536;
+            if (guess < 0x7fffffffLL) {
+                spec_R = (int)guess;
+                const size_t spec_bytes = carve_binning(nullptr, spec_R, binning_stage2_temp_bytes(spec_R)).total;
+                spec_base = binningBuffer(binning_user, spec_bytes);
+                if (!spec_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", spec_bytes);
+            }
+        }
         CK(cudaStreamSynchronize(s));
         R = (int)r32;
+        g_last_R = R;
     }
 
     const size_t temp2 = binning_stage2_temp_bytes(R);
-    const size_t bin_bytes = carve_binning(nullptr, R, temp2).total;
-    void* bin_base = binningBuffer(binning_user, bin_bytes);
-    if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
-    bin = carve_binning(align256(bin_base), R, temp2);
+    void* bin_base = spec_base;
+    if (bin_base == nullptr || R > spec_R) {
+        const size_t bin_bytes = carve_binning(nullptr, R, temp2).total;
+        bin_base = binningBuffer(binning_user, bin_bytes);
+        if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
+    }
+    bin = carve_binning(align256(bin_base), R, temp2);     // arrays are laid out from R alone (temp is last)
 
     if (P > 0) {
         CK(binning_stage2(geom, bin, img, radii, P, R, grid_x, grid_y, flags, s));

@@ -49,7 +49,9 @@ typedef enum ex4dgs_status {
 #define EX4DGS_FLAG_TILE_CULL 1u
 
 /* Resizable scratch buffers, the C form of `std::function<char*(size_t)>` in
- * rasterizer.h:38-40 / rasterize_points.cu:27-33: called at most once per buffer per forward;
+ * rasterizer.h:38-40 / rasterize_points.cu:27-33: called once per buffer per forward (the binning
+ * allocator may be called a second time when a size estimate proved too small - the last
+ * returned pointer is the one in use);
  * must return a device pointer to at least `nbytes` bytes, 256-byte aligned, that stays valid
  * until the matching ex4dgs_backward (the Python layer keeps the torch byte tensors alive
  * through autograd exactly like ctx.save_for_backward in __init__.py:106). */

@@ -223,3 +223,63 @@ def test_non_default_stream_and_reentrancy(built, cull):
     s.synchronize()
     assert np.array_equal(base["color"], other["color"])
     assert np.array_equal(base["inter"]["point_list"], other["inter"]["point_list"])
+
+
+@pytest.mark.parametrize("variant", ["deg0", "deg2", "scale_mod", "kernel_size", "tight_planes", "odd_size"])
+def test_setting_variants_against_oracle(built, variant, cull):
+    """Less common GaussianRasterizationSettings values, each against the CPU oracle."""
+    kw = dict(P_static=900, P_dynamic=300, W=112, H=80, sigma_px=3.0, seed=synth.SEED + 40, pose="tilted")
+    scale_modifier = 1.0
+    if variant == "odd_size":
+        kw.update(W=97, H=53)
+    if variant == "tight_planes":
+        kw.update(min_depth=3.0, max_depth=25.0)
+    if variant == "kernel_size":
+        kw.update(kernel_size=0.35)
+    sc = synth.make_scene(**kw)
+    if variant == "deg0":
+        sc.sh_degree = 0
+    if variant == "deg2":
+        sc.sh_degree = 2
+    if variant == "scale_mod":
+        scale_modifier = 1.7
+
+    def run(mod, dev, kind):
+        if scale_modifier == 1.0:
+            return U.run_impl(mod, sc, dev=dev, kind=kind, grad_kind="all")
+        orig = U.settings_for
+
+        def patched(m, s_, d, subpixel=None, debug=False):
+            rs = orig(m, s_, d, subpixel, debug)
+            return rs._replace(scale_modifier=scale_modifier)
+        U.settings_for = patched
+        try:
+            return U.run_impl(mod, sc, dev=dev, kind=kind, grad_kind="all")
+        finally:
+            U.settings_for = orig
+    ours = run(U.ours_module(), "cuda", "ours")
+    orc = run(U.oracle_module(), "cpu", "oracle")
+    _check_ints(ours, orc, cull)
+    _check_floats(ours, orc)
+
+
+def test_debug_flag_and_error_paths(built):
+    """debug=True synchronises after every stage (auxiliary.h:296-303) and must give the same result;
+    bad SH layouts are rejected by the C ABI with a message."""
+    mod = U.ours_module()
+    sc, kw = make_case("gold_base")
+    base = U.run_impl(mod, sc, kind="ours", **kw)
+    orig = U.settings_for
+    U.settings_for = lambda m, s_, d, subpixel=None, debug=False: orig(m, s_, d, subpixel, True)
+    try:
+        dbg = U.run_impl(mod, sc, kind="ours", **kw)
+    finally:
+        U.settings_for = orig
+    assert np.array_equal(base["color"], dbg["color"])
+    inp = synth.flat_inputs(sc)
+    rs = U.settings_for(mod, sc, "cuda")
+    P = inp["means3D"].shape[0]
+    with pytest.raises(RuntimeError, match="needs 16 coefficients"):
+        mod.GaussianRasterizer(rs)(means3D=inp["means3D"].cuda(), means2D=torch.zeros(P, 3).cuda(), dir3D=inp["dir3D"].cuda(),
+                                   opacities=inp["opacities"].cuda(), shs=inp["shs"][:, :9].contiguous().cuda(),
+                                   scales=inp["scales"].cuda(), rotations=inp["rotations"].cuda())
