@@ -105,132 +105,6 @@ __device__ __forceinline__ Cov2D cov2d_project(float mx, float my, float mz, con
     return o;
 }
 
-// ---- forward preprocess, shared pieces -----------------------------------------------------------
-struct Geom {
-    int radius;
-    uint32_t area;
-    float px, py, depth, conA, conB, conC, opac, thr;
-};
-
-// frustum cull, covariance, EWA projection, mip filter, extent, tile rectangle (forward.cu:201-250).
-// Returns false when the Gaussian is dropped.
-__device__ __forceinline__ bool preprocess_geom(const PreprocessParams& p, const float* view, const float* proj,
-                                                int idx, float mx, float my, float mz, Geom& g)
-{
-    // ---- frustum test (auxiliary.h:267-294)
-    const float hx = xform_row(proj, 0, mx, my, mz);
-    const float hy = xform_row(proj, 1, mx, my, mz);
-    const float hw = xform_row(proj, 3, mx, my, mz);
-    const float pw = __fdiv_rn(1.0f, fa(hw, 0.0000001f));
-    const float ndc_x = fm(hx, pw), ndc_y = fm(hy, pw);
-    const float depth = xform_row(view, 2, mx, my, mz);
-    if ((depth <= p.min_depth) || (depth > p.max_depth) ||
-        ((double)ndc_x < -1.3 || (double)ndc_x > 1.3 || (double)ndc_y < -1.3 || (double)ndc_y > 1.3)) {
-        if (p.prefiltered) {
-            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-            __trap();
-        }
-        return false;
-    }
-    // ---- 3D covariance
-    float cov3D[6];
-    if (p.cov3D_precomp != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) cov3D[i] = __ldg(p.cov3D_precomp + 6 * idx + i);
-    } else {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
-        cov3d_from_scale_rot(__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2),
-                             p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
-    }
-    // ---- EWA projection + mip filter (forward.cu:74-124)
-    const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
-    const float bb = fm(cv.b, cv.b);
-    const float det0f = ff(cv.a, cv.c, -bb);
-    const float ak = fa(cv.a, p.kernel_size), ck = fa(cv.c, p.kernel_size);
-    const float det = ff(ak, ck, -bb);             // == det_1 before clamping == det of filtered cov
-    const float det_0 = (float)fmax(1e-6, (double)det0f);
-    const float det_1 = (float)fmax(1e-6, (double)det);
-    float coef = (float)sqrt((double)det_0 / ((double)det_1 + 1e-6) + 1e-6);
-    if ((double)det_0 <= 1e-6 || (double)det_1 <= 1e-6) coef = 0.0f;
-    if (det == 0.0f) return false;
-    const float det_inv = __fdiv_rn(1.f, det);
-    g.conA = fm(ck, det_inv); g.conB = fm(-cv.b, det_inv); g.conC = fm(ak, det_inv);
-    // ---- extent (forward.cu:242-250)
-    const float mid = fm(0.5f, fa(ak, ck));
-    const float disc = __fsqrt_rn(fmaxf(0.1f, ff(mid, mid, -det)));
-    const float lam = fmaxf(fa(mid, disc), fa(mid, -disc));
-    const float radf = ceilf(fm(3.f, __fsqrt_rn(lam)));
-    g.radius = (int)radf;
-    // ndc2Pix in double: ((v + 1.0) * S - 1.0) * 0.5   (auxiliary.h:41-44)
-    g.px = (float)((((double)ndc_x + 1.0) * (double)p.W - 1.0) * 0.5);
-    g.py = (float)((((double)ndc_y + 1.0) * (double)p.H - 1.0) * 0.5);
-    int x0, y0, x1, y1;
-    tile_rect(g.px, g.py, g.radius, p.grid_x, p.grid_y, x0, y0, x1, y1);
-    g.area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
-    if (g.area == 0) return false;
-    g.depth = depth;
-    g.opac = fm(__ldg(p.opacities + idx), coef);
-    // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
-    g.thr = logf(1.0f / (255.0f * g.opac)) - 1e-3f;
-    return true;
-}
-
-// SH -> RGB (forward.cu:20-71) from a row of 3*M floats readable through `sh` (global or shared)
-__device__ __forceinline__ uint8_t sh_to_rgb(int D, int M, const float* sh, bool vec16, float mx, float my, float mz,
-                                             const float* cam, float* rgb)
-{
-    float dx = fa(mx, -cam[0]), dy = fa(my, -cam[1]), dz = fa(mz, -cam[2]);
-    const float len = __fsqrt_rn(sum3(dx, dx, dy, dy, dz, dz));
-    dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
-    float b[16];
-    int nb = 1;
-    b[0] = kC0;
-    if (D > 0) {
-        b[1] = -kC1 * dy; b[2] = kC1 * dz; b[3] = -kC1 * dx; nb = 4;
-        if (D > 1) {
-            const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-            b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy);
-            b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy); nb = 9;
-            if (D > 2) {
-                b[9] = kC3[0] * dy * (3.0f * xx - yy);
-                b[10] = kC3[1] * xy * dz;
-                b[11] = kC3[2] * dy * (4.0f * zz - xx - yy);
-                b[12] = kC3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                b[13] = kC3[4] * dx * (4.0f * zz - xx - yy);
-                b[14] = kC3[5] * dz * (xx - yy);
-                b[15] = kC3[6] * dx * (xx - 3.0f * yy);
-                nb = 16;
-            }
-        }
-    }
-    float acc[3] = {0.f, 0.f, 0.f};
-    if (vec16) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k < nb) {
-                acc[0] = fmaf(b[k], sh[3 * k], acc[0]);
-                acc[1] = fmaf(b[k], sh[3 * k + 1], acc[1]);
-                acc[2] = fmaf(b[k], sh[3 * k + 2], acc[2]);
-            }
-        }
-    } else {
-        for (int k = 0; k < nb; k++) {
-            acc[0] = fmaf(b[k], sh[3 * k], acc[0]);
-            acc[1] = fmaf(b[k], sh[3 * k + 1], acc[1]);
-            acc[2] = fmaf(b[k], sh[3 * k + 2], acc[2]);
-        }
-    }
-    uint8_t clamp_bits = 0;
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const float v = acc[ch] + 0.5f;
-        if (v < 0.f) clamp_bits |= (1u << ch);
-        rgb[ch] = fmaxf(v, 0.0f);
-    }
-    return clamp_bits;
-}
-
-// Generic path: one thread per Gaussian, SH row read straight from global memory.
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p)
 {
     __shared__ float s_cam[36];   // view[16] | proj[16] | campos[3]
@@ -238,97 +112,159 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(p.proj + threadIdx.x - 16);
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = __ldg(p.cam + threadIdx.x - 32);
     __syncthreads();
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
+
+    int radius_out = 0;
+    uint32_t tiles = 0, key = EX_INVISIBLE_KEY;
     const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
-    Geom g;
-    const bool vis = preprocess_geom(p, s_cam, s_cam + 16, idx, mx, my, mz, g);
-    if (vis) {
+
+    do {
+        // ---- frustum test (auxiliary.h:267-294)
+        const float hx = xform_row(proj, 0, mx, my, mz);
+        const float hy = xform_row(proj, 1, mx, my, mz);
+        const float hw = xform_row(proj, 3, mx, my, mz);
+        const float pw = __fdiv_rn(1.0f, fa(hw, 0.0000001f));
+        const float ndc_x = fm(hx, pw), ndc_y = fm(hy, pw);
+        const float depth = xform_row(view, 2, mx, my, mz);
+        if ((depth <= p.min_depth) || (depth > p.max_depth) ||
+            ((double)ndc_x < -1.3 || (double)ndc_x > 1.3 || (double)ndc_y < -1.3 || (double)ndc_y > 1.3)) {
+            if (p.prefiltered) {
+                printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                __trap();
+            }
+            break;
+        }
+        // ---- 3D covariance
+        float cov3D[6];
+        if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cov3D[i] = __ldg(p.cov3D_precomp + 6 * idx + i);
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+            cov3d_from_scale_rot(__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2),
+                                 p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+        }
+        // ---- EWA projection + mip filter (forward.cu:74-124)
+        const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
+        const float bb = fm(cv.b, cv.b);
+        const float det0f = ff(cv.a, cv.c, -bb);
+        const float ak = fa(cv.a, p.kernel_size), ck = fa(cv.c, p.kernel_size);
+        const float det = ff(ak, ck, -bb);             // == det_1 before clamping == det of filtered cov
+        const float det_0 = (float)fmax(1e-6, (double)det0f);
+        const float det_1 = (float)fmax(1e-6, (double)det);
+        float coef = (float)sqrt((double)det_0 / ((double)det_1 + 1e-6) + 1e-6);
+        if ((double)det_0 <= 1e-6 || (double)det_1 <= 1e-6) coef = 0.0f;
+        if (det == 0.0f) break;
+        const float det_inv = __fdiv_rn(1.f, det);
+        const float conA = fm(ck, det_inv), conB = fm(-cv.b, det_inv), conC = fm(ak, det_inv);
+        // ---- extent (forward.cu:242-250)
+        const float mid = fm(0.5f, fa(ak, ck));
+        const float disc = __fsqrt_rn(fmaxf(0.1f, ff(mid, mid, -det)));
+        const float lam = fmaxf(fa(mid, disc), fa(mid, -disc));
+        const float radf = ceilf(fm(3.f, __fsqrt_rn(lam)));
+        const int radius = (int)radf;
+        // ndc2Pix in double: ((v + 1.0) * S - 1.0) * 0.5   (auxiliary.h:41-44)
+        const float px = (float)((((double)ndc_x + 1.0) * (double)p.W - 1.0) * 0.5);
+        const float py = (float)((((double)ndc_y + 1.0) * (double)p.H - 1.0) * 0.5);
+        int x0, y0, x1, y1;
+        tile_rect(px, py, radius, p.grid_x, p.grid_y, x0, y0, x1, y1);
+        const uint32_t area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        if (area == 0) break;
+
+        // ---- colour
         float rgb[3];
         uint8_t clamp_bits = 0;
         if (p.colors_precomp == nullptr) {
-            clamp_bits = sh_to_rgb(p.D, p.M, p.shs + (size_t)idx * p.M * 3, false, mx, my, mz, s_cam + 32, rgb);
+            float dx = fa(mx, -cam[0]), dy = fa(my, -cam[1]), dz = fa(mz, -cam[2]);
+            const float len = __fsqrt_rn(sum3(dx, dx, dy, dy, dz, dz));
+            dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            float b[16];
+            int nb = 1;
+            b[0] = kC0;
+            if (p.D > 0) {
+                b[1] = -kC1 * dy; b[2] = kC1 * dz; b[3] = -kC1 * dx; nb = 4;
+                if (p.D > 1) {
+                    const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+                    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy);
+                    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy); nb = 9;
+                    if (p.D > 2) {
+                        b[9] = kC3[0] * dy * (3.0f * xx - yy);
+                        b[10] = kC3[1] * xy * dz;
+                        b[11] = kC3[2] * dy * (4.0f * zz - xx - yy);
+                        b[12] = kC3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                        b[13] = kC3[4] * dx * (4.0f * zz - xx - yy);
+                        b[14] = kC3[5] * dz * (xx - yy);
+                        b[15] = kC3[6] * dx * (xx - 3.0f * yy);
+                        nb = 16;
+                    }
+                }
+            }
+            float acc[3] = {0.f, 0.f, 0.f};
+            if (p.M == 16) {
+                // 192-byte row, 16-byte aligned: twelve 128-bit loads
+                const float4* s4 = reinterpret_cast<const float4*>(sh);
+                float v[48];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const float4 t = __ldg(s4 + i);
+                    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k < nb) {
+                        acc[0] = fmaf(b[k], v[3 * k], acc[0]);
+                        acc[1] = fmaf(b[k], v[3 * k + 1], acc[1]);
+                        acc[2] = fmaf(b[k], v[3 * k + 2], acc[2]);
+                    }
+                }
+            } else {
+                for (int k = 0; k < nb; k++) {
+                    acc[0] = fmaf(b[k], __ldg(sh + 3 * k), acc[0]);
+                    acc[1] = fmaf(b[k], __ldg(sh + 3 * k + 1), acc[1]);
+                    acc[2] = fmaf(b[k], __ldg(sh + 3 * k + 2), acc[2]);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float v = acc[ch] + 0.5f;
+                if (v < 0.f) clamp_bits |= (1u << ch);
+                rgb[ch] = fmaxf(v, 0.0f);
+            }
         } else {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) rgb[ch] = __ldg(p.colors_precomp + 3 * idx + ch);
         }
         p.clamped[idx] = clamp_bits;
+
+        const float opac = fm(__ldg(p.opacities + idx), coef);
+        // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
+        const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
+
+        // with EX4DGS_FLAG_TILE_CULL the duplicate kernel keys culled instances to the dump tile;
+        // the count stays the full rectangle so that no second pass is needed before the scan
+        const uint32_t count = area;
+
         SplatRec rc;
-        rc.a = make_float4(g.px, g.py, g.depth, g.thr);
-        rc.b = make_float4(g.conA, g.conB, g.conC, g.opac);
+        rc.a = make_float4(px, py, depth, thr);
+        rc.b = make_float4(conA, conB, conC, opac);
         rc.c = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(idx));
         rc.d = make_float4(__ldg(p.dir3D + 3 * idx), __ldg(p.dir3D + 3 * idx + 1), __ldg(p.dir3D + 3 * idx + 2), 0.f);
         p.rec[idx] = rc;
-    }
-    // with EX4DGS_FLAG_TILE_CULL the duplicate kernel keys culled instances to the dump tile; the
-    // count stays the full rectangle so that no second pass is needed before the scan
-    p.radii[idx] = vis ? g.radius : 0;
-    p.tiles_touched[idx] = vis ? g.area : 0u;
-    p.key_in[idx] = vis ? __float_as_uint(g.depth) : EX_INVISIBLE_KEY;
-    p.val_in[idx] = (uint32_t)idx;
-}
 
-// Degree-3 layout (M == 16), the common case: 128 Gaussians per CTA; the SH rows of the VISIBLE
-// Gaussians are brought in with coalesced 128-bit loads through a padded shared-memory area (the
-// per-thread 192-byte strided reads of the generic path touch every sector twice), and the 64-byte
-// records leave through shared memory as coalesced 128-bit stores.
-constexpr int kFT = 128;
-__global__ void __launch_bounds__(kFT) preprocess_fwd_staged_kernel(const __grid_constant__ PreprocessParams p)
-{
-    __shared__ float s_cam[36];
-    __shared__ int s_vis[kFT];
-    __shared__ float s_sh[kFT * 49];
-    __shared__ float4 s_rec[kFT * 4];
-    const int tid = threadIdx.x;
-    if (tid < 16) s_cam[tid] = __ldg(p.view + tid);
-    else if (tid < 32) s_cam[tid] = __ldg(p.proj + tid - 16);
-    else if (tid < 35) s_cam[tid] = __ldg(p.cam + tid - 32);
-    __syncthreads();
-    const int base = blockIdx.x * kFT;
-    const int idx = base + tid;
-    const int nvalid = min(kFT, p.P - base);
-    float mx = 0.f, my = 0.f, mz = 0.f;
-    Geom g;
-    bool vis = false;
-    if (idx < p.P) {
-        mx = __ldg(p.means3D + 3 * idx); my = __ldg(p.means3D + 3 * idx + 1); mz = __ldg(p.means3D + 3 * idx + 2);
-        vis = preprocess_geom(p, s_cam, s_cam + 16, idx, mx, my, mz, g);
-    }
-    s_vis[tid] = vis;
-    __syncthreads();
-    {
-        const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)base * 48);
-        const int n4 = nvalid * 12;
-        for (int f = tid; f < n4; f += kFT) {
-            const int row = f / 12, col = (f % 12) * 4;
-            if (s_vis[row]) {
-                const float4 v = __ldg(src + f);
-                float* d = s_sh + row * 49 + col;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-        }
-    }
-    __syncthreads();
-    if (vis) {
-        float rgb[3];
-        p.clamped[idx] = sh_to_rgb(p.D, 16, s_sh + tid * 49, true, mx, my, mz, s_cam + 32, rgb);
-        s_rec[tid * 4 + 0] = make_float4(g.px, g.py, g.depth, g.thr);
-        s_rec[tid * 4 + 1] = make_float4(g.conA, g.conB, g.conC, g.opac);
-        s_rec[tid * 4 + 2] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(idx));
-        s_rec[tid * 4 + 3] = make_float4(__ldg(p.dir3D + 3 * idx), __ldg(p.dir3D + 3 * idx + 1), __ldg(p.dir3D + 3 * idx + 2), 0.f);
-    }
-    if (idx < p.P) {
-        p.radii[idx] = vis ? g.radius : 0;
-        p.tiles_touched[idx] = vis ? g.area : 0u;
-        p.key_in[idx] = vis ? __float_as_uint(g.depth) : EX_INVISIBLE_KEY;
-        p.val_in[idx] = (uint32_t)idx;
-    }
-    __syncthreads();
-    {
-        float4* dst = reinterpret_cast<float4*>(p.rec + base);
-        for (int f = tid; f < nvalid * 4; f += kFT)
-            if (s_vis[f >> 2]) dst[f] = s_rec[f];
-    }
+        radius_out = radius;
+        tiles = count;
+        key = __float_as_uint(depth);
+    } while (false);
+
+    p.radii[idx] = radius_out;
+    p.tiles_touched[idx] = tiles;
+    p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
+    p.val_in[idx] = (uint32_t)idx;
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
@@ -625,21 +561,15 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
     const int nvalid = min(kBT, p.P - base);
     const bool has_sh = (p.shs != nullptr);    // implies M == 16 here
 
-    __shared__ int s_vis[kBT];
-    const bool vis = (idx < p.P) && (p.radii[idx] > 0);
-    s_vis[tid] = vis;
-    __syncthreads();
-    // cooperative, coalesced load of the SH rows of the block's VISIBLE Gaussians only
+    // cooperative, coalesced load of the block's SH rows
     if (has_sh) {
         const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)base * 48);
         const int n4 = nvalid * 12;
         for (int f = tid; f < n4; f += kBT) {
+            const float4 v = __ldg(src + f);
             const int row = f / 12, col = (f % 12) * 4;
-            if (s_vis[row]) {
-                const float4 v = __ldg(src + f);
-                float* d = s_sh + row * kRow + col;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
+            float* d = s_sh + row * kRow + col;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     }
     __syncthreads();
@@ -648,9 +578,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
     const float* cam = s_cam + 32;
 
     if (idx < p.P) {
-        GradAcc g;      // never touched by the compositing loop when invisible: all zero
-        if (vis) g = p.gacc[idx];
-        else g.g0 = g.g1 = g.g2 = g.g3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const GradAcc g = p.gacc[idx];
         s_o3[0 * kBT * 3 + 3 * tid + 0] = g.g0.x; s_o3[0 * kBT * 3 + 3 * tid + 1] = g.g0.y; s_o3[0 * kBT * 3 + 3 * tid + 2] = g.g0.z;
         s_o3[1 * kBT * 3 + 3 * tid + 0] = g.g2.x; s_o3[1 * kBT * 3 + 3 * tid + 1] = g.g2.y; s_o3[1 * kBT * 3 + 3 * tid + 2] = g.g2.z;
         s_o3[2 * kBT * 3 + 3 * tid + 0] = g.g3.x; s_o3[2 * kBT * 3 + 3 * tid + 1] = g.g3.y; s_o3[2 * kBT * 3 + 3 * tid + 2] = g.g3.z;
@@ -661,7 +589,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         float dscale[3] = {0.f, 0.f, 0.f};
         float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
         float* row = s_sh + tid * kRow;
-        if (vis) {
+        if (p.radii[idx] > 0) {
             const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
             float cov3D[6];
             float sx = 0, sy = 0, sz = 0;
@@ -796,10 +724,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
 {
     if (p.P <= 0) return;
-    if (p.shs != nullptr && p.M == 16 && p.colors_precomp == nullptr)
-        preprocess_fwd_staged_kernel<<<(p.P + kFT - 1) / kFT, kFT, 0, s>>>(p);
-    else
-        preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+    preprocess_fwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
 }
 
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s)

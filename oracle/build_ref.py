@@ -48,6 +48,7 @@ def build(force=False):
     if os.path.exists(so) and not force:
         newest = max(os.path.getmtime(s) for s in srcs + [os.path.abspath(__file__)])
         if os.path.getmtime(so) >= newest:
+            install_callers()
             return True
     import torch
     from torch.utils import cpp_extension as ce
@@ -76,7 +77,21 @@ def build(force=False):
     # "install" the binding next to the extension, as pip --target would (git-ignored dir).
     shutil.copyfile(os.path.join(REF, "diff_gaussian_rasterization_df", "__init__.py"),
                     os.path.join(OUT, "__init__.py"))
+    install_callers()
     return True
+
+
+def install_callers():
+    """Install (git-ignored, like the extension) the reference's ONLY caller of the rasterizer,
+    gaussian_renderer/__init__.py, and its one pure-PyTorch import (utils/sh_utils.py), so that the
+    GPU box can run the unmodified render() against this repository's drop-in package
+    (tests/test_gpu_dropin.py).  Nothing else of the reference is needed by render()."""
+    root = "/root/reference"
+    dst = os.path.join(HERE, "_ref", "callers")
+    for rel in ("gaussian_renderer/__init__.py", "utils/sh_utils.py"):
+        os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
+        shutil.copyfile(os.path.join(root, rel), os.path.join(dst, rel))
+    open(os.path.join(dst, "utils", "__init__.py"), "a").close()
 
 
 if __name__ == "__main__":
