@@ -155,6 +155,10 @@ class Frame:
         for v in list(self.t.values()) + [self.means2D]:
             v.grad = None
 
+    def step_forward(self):
+        with torch.no_grad():
+            self.last = self._raster(self.settings(self.view, self.proj, self.campos))[0]
+
     def step_device(self):
         color, radii, depth, flow, acc, idxs = self._raster(self.settings(self.view, self.proj, self.campos))
         go = self.go
@@ -203,11 +207,13 @@ def frame_stats(frame: Frame):
         return img[a + off:a + off + es * cnt].cpu().numpy().view(dtype)
 
     ranges = view("ranges", np.uint32).reshape(-1, 2).astype(np.int64)
-    batches = view("tile_batches", np.uint32).astype(np.int64)
+    word = view("tile_batches", np.uint32).astype(np.int64)
+    batches, kept = word & 0xFF, word >> 8
     rl = ranges[:, 1] - ranges[:, 0]
     r_eff = int(np.minimum(rl, 256 * batches).sum())
     n_contrib = view("n_contrib", np.uint32)
     return dict(R=R, P_vis=int((radii > 0).sum().item()), R_eff=r_eff, tiles=int(ranges.shape[0]),
+                R_listed=int(rl.sum()), block_keep=float(kept.sum()) / max(1.0, 8.0 * r_eff),
                 mean_n_contrib=float(n_contrib.mean()))
 
 
@@ -239,6 +245,8 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true",
+                    help="forward-only render under no_grad (BASELINE.json config 2); changes the metric name")
     ap.add_argument("--profile-in-timed", type=int, default=1,
                     help="record per-stage CUDA events inside the timed region (1) or in a separate pass (0)")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
@@ -287,6 +295,9 @@ def main():
         mod, lib = ref_mod, None
 
     frame = Frame(mod, sc, dev, seed_off=rank)
+    if args.fwd_only:
+        frame.step_device = frame.step_forward
+        frame.step_e2e = lambda group=None: frame.step_forward()
 
     def barrier():
         torch.cuda.synchronize()
@@ -355,7 +366,7 @@ def main():
         return
 
     h2d = frame.h_gt.numel() * 4 + frame.h_cam.numel() * 4
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+    line = {"metric": METRIC if not args.fwd_only else "fwd-only frames/sec (config 2 style)", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -376,6 +387,7 @@ def main():
         achieved = alg_bytes / t_render / 1e9
         line["gpu_launches"] = int(launches)
         line["config"].update({"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"],
+                               "R_listed": st["R_listed"], "block_keep": st["block_keep"],
                                "tile_cull": int(args.tile_cull), "mean_n_contrib": st["mean_n_contrib"]})
         line["roofline"] = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": None,

@@ -370,8 +370,9 @@ int ex4dgs_backward(
     if (scales && (!dL_dscale || !dL_drot)) return fail(EX4DGS_ERR_INVALID, "dL_dscale/dL_drot are required when scales are given");
 
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
-    const GeometryState geom = carve_geometry(align256(geom_buffer), P, binning_stage1_temp_bytes(P));
-    const BinningState bin = carve_binning(align256(binning_buffer), R, binning_stage2_temp_bytes(R));
+    // the CUB temp areas are the last sub-arrays and are not used by the backward
+    const GeometryState geom = carve_geometry(align256(geom_buffer), P, 0);
+    const BinningState bin = carve_binning(align256(binning_buffer), R, 0);
     const ImageState img = carve_image(align256(image_buffer), width, height);
 
     PreprocessBwdParams bp;

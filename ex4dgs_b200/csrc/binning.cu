@@ -136,9 +136,22 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t*
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ v, size_t n, uint32_t* out)
 {
     float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float a = fabsf(__ldg(v + i));
+    auto upd = [&](float x) {
+        const float a = fabsf(x);
         m = (a > m || a != a) ? a : m;     // NaN propagates
+    };
+    const size_t n4 = n >> 2;               // subpixel_offset is [H,W,2] floats, 16-byte aligned in practice
+    const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (aligned) {
+        const float4* v4 = reinterpret_cast<const float4*>(v);
+        for (size_t i = t0; i < n4; i += stride) {
+            const float4 x = __ldg(v4 + i);
+            upd(x.x); upd(x.y); upd(x.z); upd(x.w);
+        }
+        for (size_t i = (n4 << 2) + t0; i < n; i += stride) upd(__ldg(v + i));
+    } else {
+        for (size_t i = t0; i < n; i += stride) upd(__ldg(v + i));
     }
     uint32_t b = __float_as_uint(m);
     b = __reduce_max_sync(0xffffffffu, b);
@@ -159,29 +172,44 @@ uint32_t higher_msb(uint32_t n)
 
 }  // namespace
 
+// The CUB size queries touch the driver (device attributes, function attributes): memoised, because
+// they sit on the critical path right after the forward's host synchronisation.
 size_t binning_stage1_temp_bytes(int P)
 {
+    static thread_local int last_p = -1;
+    static thread_local size_t last_bytes = 0;
+    if (P == last_p) return last_bytes;
     size_t a = 0, b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
     cub::TransformInputIterator<uint32_t, TilesInOrder, const uint32_t*> it(nullptr, TilesInOrder{nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
-    return (a > b ? a : b) + 256;
+    last_p = P;
+    last_bytes = (a > b ? a : b) + 256;
+    return last_bytes;
 }
 
 size_t binning_stage2_temp_bytes(int R)
 {
+    // temp size grows monotonically with the item count: query once per 1M-item bucket
+    static thread_local long long last_bucket = -1;
+    static thread_local size_t last_bytes = 0;
+    const long long bucket = ((long long)(R > 0 ? R : 1) + 0xFFFFF) >> 20;
+    if (bucket == last_bucket) return last_bytes;
+    const long long n = bucket << 20;
     size_t a = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint16_t*)nullptr, (uint16_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, R > 0 ? R : 1);
-    return a + 256;
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n < 0x7fffffffLL ? n : 0x7fffffffLL));
+    last_bucket = bucket;
+    last_bytes = a + 256;
+    return last_bytes;
 }
 
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    absmax_kernel<<<148 * 4, 256, 0, s>>>(subpixel_offset, n, out);
+    absmax_kernel<<<148 * 8, 256, 0, s>>>(subpixel_offset, n, out);
     return cudaGetLastError();
 }
 

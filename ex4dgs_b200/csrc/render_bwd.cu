@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
     // pixels that received nothing in the forward never contribute: keep them out of the warp's box
     const BlockBox box = block_box(pxf, pyf, last_contributor > 0);
     const bool warp_idle = __all_sync(0xffffffffu, last_contributor == 0);
+    const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);   // list positions >= this are dead for the warp
     const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
     const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     float T = T_final;
@@ -163,11 +164,12 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
         unsigned long long mask = 0ull;
         // which splats of the sub-batch can touch this warp's pixel block at all (exact, see block_reject)
         int nw = 0;
-        if (!warp_idle) {
+        if (!warp_idle && (start - r * kSub - cnt) < warp_last) {      // some entry of the sub-batch is still live for this warp
             for (int g = 0; g < cnt; g += 32) {
                 const int jj = g + lane;
                 bool keep = false;
-                if (jj < cnt) keep = !block_reject(s[jj * 3], s[jj * 3 + 1], box);
+                // entry jj sits at list position q = start-1-(r*kSub+jj); only q < warp_last can matter
+                if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !block_reject(s[jj * 3], s[jj * 3 + 1], box);
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 if (keep) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
                 nw += __popc(m);

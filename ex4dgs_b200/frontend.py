@@ -82,3 +82,54 @@ def interpolate_gaussians(xyz, xyz_disp, rotation, scaling, opacity, xyz_motion,
     """-> (means3D [P,3], rotations [P,4], scales [P,3], opacities [P,1]); static Gaussians first."""
     return _FusedFrontEnd.apply(xyz, xyz_disp, rotation, scaling, opacity, xyz_motion, rotation_motion, scaling_motion,
                                 opacity_motion, opacity_center, opacity_var, t, duration, interval, time_shift, var_min)
+
+
+class FusedGetters:
+    """Duck-typed stand-in for the per-frame getters of CGaussianModel: wrap the model and hand the
+    wrapper to the reference's unmodified render() (gaussian_renderer/__init__.py:28,62-95).  The four
+    getters that render() calls for one timestamp (get_xyz_at_t twice, get_opacity_at_t,
+    get_scaling, get_rotation_at_t) are served from ONE fused kernel launch, cached per timestamp;
+    get_features still concatenates in PyTorch.  Every other attribute is forwarded to the model.
+
+    `model` needs the reference's attribute names: _xyz, _xyz_disp, _rotation, _scaling, _opacity,
+    _xyz_motion, _rotation_motion, _scaling_motion, _opacity_motion, _opacity_duration_center,
+    _opacity_duration_var, duration, interval, time_shift, var_pad (interp_type "cube", slerp)."""
+
+    def __init__(self, model):
+        object.__setattr__(self, "_m", model)
+        object.__setattr__(self, "_key", None)
+        object.__setattr__(self, "_val", None)
+
+    def __getattr__(self, name):
+        return getattr(object.__getattribute__(self, "_m"), name)
+
+    def _frame(self, t):
+        m = self._m
+        key = (float(t), tuple(int(getattr(m, n)._version) for n in ("_xyz", "_xyz_motion", "_rotation_motion", "_opacity_motion")))
+        if self._key != key:
+            val = interpolate_gaussians(m._xyz, m._xyz_disp, m._rotation, m._scaling, m._opacity, m._xyz_motion,
+                                        m._rotation_motion, m._scaling_motion, m._opacity_motion,
+                                        m._opacity_duration_center, m._opacity_duration_var, t=float(t),
+                                        duration=float(m.duration), interval=float(m.interval),
+                                        time_shift=float(m.time_shift), var_min=float(m.var_pad) / float(m.interval))
+            object.__setattr__(self, "_key", key)
+            object.__setattr__(self, "_val", val)
+        return self._val
+
+    def get_xyz_at_t(self, t, mode=0, training=True):
+        assert mode == 0, "fused getters implement mode 0 (static + dynamic)"
+        return self._frame(t)[0]
+
+    def get_rotation_at_t(self, t, mode=0):
+        assert mode == 0
+        return self._frame(t)[1]
+
+    def get_scaling(self, mode=0):
+        assert mode == 0
+        if self._val is None:
+            raise RuntimeError("get_scaling() before any get_*_at_t(t): the fused getters need the timestamp first")
+        return self._val[2]
+
+    def get_opacity_at_t(self, t, mode=0, training=False):
+        assert mode == 0
+        return self._frame(t)[3]

@@ -126,7 +126,7 @@ def _our_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
     out = dict(R=R, rec=rec, visible=vis, depth_key=key, tiles_touched=view("tiles_touched", np.uint32),
                order=view("order", np.uint32), clamped_bits=view("clamped", np.uint8),
                final_T=view("final_T", np.float32), n_contrib=view("n_contrib", np.uint32),
-               ranges=view("ranges", np.uint32).reshape(tiles, 2), tile_batches=view("tile_batches", np.uint32))
+               ranges=view("ranges", np.uint32).reshape(tiles, 2), tile_batches=view("tile_batches", np.uint32) & 0xFF)
     if R > 0:
         out["point_list"] = view("point_list", np.uint32)
         out["tile_sorted"] = view("tile_sorted", np.uint16)

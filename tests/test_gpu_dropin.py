@@ -99,3 +99,35 @@ def test_unmodified_render_runs_on_the_dropin(built):
         assert np.array_equal(a[k], b[k]), k
     for k in ("viewspace_grad", "l1points_grad", "xyz_grad", "sh_grad"):
         assert U.rel_err(a[k], b[k], U.grad_floor(b[k])) <= 2e-3, k
+
+
+def test_unmodified_render_with_fused_getters(built):
+    """render() + FusedGetters (one kernel for all per-frame getters) == render() + PyTorch getters."""
+    if not os.path.exists(os.path.join(CALLERS, "gaussian_renderer", "__init__.py")):
+        pytest.skip("reference caller not installed (python oracle/build_ref.py)")
+    import diff_gaussian_rasterization_df as ours_pkg
+    from ex4dgs_b200.frontend import FusedGetters
+    sc = synth.make_config("C1d", pose="tilted")
+    model = types.SimpleNamespace(
+        _xyz=sc.xyz.cuda(), _xyz_disp=sc.xyz_disp.cuda(), _rotation=sc.rotation.cuda(), _scaling=sc.scaling.cuda(),
+        _opacity=sc.opacity.cuda(), _xyz_motion=sc.xyz_motion.cuda(), _rotation_motion=sc.rotation_motion.cuda(),
+        _scaling_motion=sc.scaling_motion.cuda(), _opacity_motion=sc.opacity_motion.cuda(),
+        _opacity_duration_center=sc.opacity_center.cuda(), _opacity_duration_var=sc.opacity_var.cuda(),
+        duration=sc.duration, interval=sc.interval, time_shift=sc.time_shift, var_pad=sc.var_pad,
+        kernel_size=sc.cam.kernel_size, active_sh_degree=sc.sh_degree, max_sh_degree=3,
+        get_features=lambda mode=0: torch.cat([sc.features, sc.features_motion]).cuda())
+    sys.modules["diff_gaussian_rasterization_df"] = ours_pkg
+    sys.path.insert(0, CALLERS)
+    try:
+        for m in ("gaussian_renderer", "utils", "utils.sh_utils"):
+            sys.modules.pop(m, None)
+        gr = importlib.import_module("gaussian_renderer")
+    finally:
+        sys.path.remove(CALLERS)
+    pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+    out = gr.render(_camera(sc), FusedGetters(model), pipe, sc.bg.cuda(), near=sc.cam.min_depth, far=sc.cam.max_depth)
+    ref = U.run_impl(ours_pkg, sc, kind="ours", grads=False, intermediates=False)
+    assert float(np.abs(out["render"].detach().cpu().numpy() - ref["color"]).max()) <= 1e-4
+    assert np.array_equal(out["radii"].cpu().numpy(), ref["radii"])
+    for m in ("gaussian_renderer", "utils", "utils.sh_utils", "diff_gaussian_rasterization_df"):
+        sys.modules.pop(m, None)
