@@ -372,3 +372,44 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// Exact variant of block_reject: minimum of q = -power over the FOUR EDGES of the box (the box does
+// not contain the centre, q is convex), division-free: on the edge dx = const the parabola in dy
+// has its vertex at dy = -B dx / C, inside [dy0, dy1] iff C*dy0 <= -B*dx <= C*dy1, with value
+// 0.5*(det/C)*dx^2; otherwise the nearer end point is evaluated.  Same rounding guard.
+__device__ __forceinline__ bool block_reject_exact(const float4& a, const float4& b, const BlockBox& box)
+{
+    const float A = b.x, B = b.y, C = b.z;
+    const float det = A * C - B * B;
+    if (!(A > 0.f) || !(C > 0.f) || !(det > 0.f)) return false;
+    const float shrink = 1.0f - 8e-5f * (A * C / det);
+    if (!(shrink > 0.5f)) return false;
+    const float tq = 1e-3f - a.w;
+    if (!(tq == tq)) return false;                       // NaN threshold: keep
+    const float tqs = tq / shrink * (tq > 0.f ? 1.0001f : 0.9999f);
+    const float dx0 = box.x0 - a.x, dx1 = box.x1 - a.x, dy0 = box.y0 - a.y, dy1 = box.y1 - a.y;
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return false;   // centre inside the box
+    const float hd = 0.5f * det;
+    bool all_above = true;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const float dx = e ? dx1 : dx0;
+        const float t = -B * dx;
+        bool above;
+        if (t < C * dy0)      above = (0.5f * (A * dx * dx + C * dy0 * dy0) + B * dx * dy0) > tqs;
+        else if (t > C * dy1) above = (0.5f * (A * dx * dx + C * dy1 * dy1) + B * dx * dy1) > tqs;
+        else                  above = hd * dx * dx > tqs * C;
+        all_above = all_above && above;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const float dy = e ? dy1 : dy0;
+        const float t = -B * dy;
+        bool above;
+        if (t < A * dx0)      above = (0.5f * (A * dx0 * dx0 + C * dy * dy) + B * dx0 * dy) > tqs;
+        else if (t > A * dx1) above = (0.5f * (A * dx1 * dx1 + C * dy * dy) + B * dx1 * dy) > tqs;
+        else                  above = hd * dy * dy > tqs * A;
+        all_above = all_above && above;
+    }
+    return all_above;
+}
