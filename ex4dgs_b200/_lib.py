@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libex4dgs_raster.so")
+LIB_PATH = os.environ.get("EX4DGS_LIB") or os.path.join(HERE, "libex4dgs_raster.so")   # EX4DGS_LIB: tuning experiments only
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 

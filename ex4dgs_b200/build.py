@@ -48,6 +48,22 @@ def _compile(src: str, force: bool, verbose: bool) -> str:
     return o
 
 
+def build_variant(name: str, defines) -> str:
+    """Experiment helper: build libex4dgs_raster_<name>.so with extra -D flags (selected at run time
+    with EX4DGS_LIB=<path>); the product always loads libex4dgs_raster.so."""
+    objdir = os.path.join(HERE, "_obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        o = os.path.join(objdir, src + ".o")
+        subprocess.check_call(["nvcc", "-c", os.path.join(CSRC, src), "-o", o] + NVCC_FLAGS + ["-D" + d for d in defines],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        objs.append(o)
+    lib = os.path.join(HERE, "libex4dgs_raster_%s.so" % name)
+    subprocess.check_call(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.isdir(CSRC):
         raise RuntimeError("csrc missing")

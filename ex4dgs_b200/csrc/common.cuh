@@ -15,6 +15,15 @@
 #define EX_TILE_PIX 256
 #define EX_INVISIBLE_KEY 0xFFFFFFFFu
 
+// tuning knobs of the compositing kernels (defaults = measured best on B200, see profiles/)
+#ifndef EX_FWD_MINBLOCKS
+#define EX_FWD_MINBLOCKS 4      // 64 registers (44 B of spills) but 32 resident warps: 0.49 vs 0.53 ms at C3
+#endif
+#ifndef EX_BWD_MINBLOCKS
+#define EX_BWD_MINBLOCKS 3
+#endif
+#define EX_BLOCK_TEST block_reject   // an exact 4-edge variant was measured slower (more instructions than it saves)
+
 // ---- pinned float arithmetic -------------------------------------------------------------------
 __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
@@ -91,6 +100,7 @@ struct ImageState {
     uint32_t* n_contrib;      // [W*H]
     uint2* ranges;            // [tiles]
     uint32_t* tile_batches;   // [tiles] number of 256-splat batches the forward fetched (stats)
+    uint32_t* tile_order;     // [tiles] launch order of the compositing CTAs (longest lists first)
     size_t total;
 };
 
@@ -132,6 +142,7 @@ struct RenderParams {
     const uint2* ranges;
     const uint32_t* point_list;
     const SplatRec* rec;
+    const uint32_t* tile_order;   // CTA index -> tile id (NULL: identity)
     int W, H, grid_x;
     const float2* subpixel_offset;
     const float* bg;     // [3] device
@@ -373,43 +384,3 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Exact variant of block_reject: minimum of q = -power over the FOUR EDGES of the box (the box does
-// not contain the centre, q is convex), division-free: on the edge dx = const the parabola in dy
-// has its vertex at dy = -B dx / C, inside [dy0, dy1] iff C*dy0 <= -B*dx <= C*dy1, with value
-// 0.5*(det/C)*dx^2; otherwise the nearer end point is evaluated.  Same rounding guard.
-__device__ __forceinline__ bool block_reject_exact(const float4& a, const float4& b, const BlockBox& box)
-{
-    const float A = b.x, B = b.y, C = b.z;
-    const float det = A * C - B * B;
-    if (!(A > 0.f) || !(C > 0.f) || !(det > 0.f)) return false;
-    const float shrink = 1.0f - 8e-5f * (A * C / det);
-    if (!(shrink > 0.5f)) return false;
-    const float tq = 1e-3f - a.w;
-    if (!(tq == tq)) return false;                       // NaN threshold: keep
-    const float tqs = tq / shrink * (tq > 0.f ? 1.0001f : 0.9999f);
-    const float dx0 = box.x0 - a.x, dx1 = box.x1 - a.x, dy0 = box.y0 - a.y, dy1 = box.y1 - a.y;
-    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return false;   // centre inside the box
-    const float hd = 0.5f * det;
-    bool all_above = true;
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const float dx = e ? dx1 : dx0;
-        const float t = -B * dx;
-        bool above;
-        if (t < C * dy0)      above = (0.5f * (A * dx * dx + C * dy0 * dy0) + B * dx * dy0) > tqs;
-        else if (t > C * dy1) above = (0.5f * (A * dx * dx + C * dy1 * dy1) + B * dx * dy1) > tqs;
-        else                  above = hd * dx * dx > tqs * C;
-        all_above = all_above && above;
-    }
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const float dy = e ? dy1 : dy0;
-        const float t = -B * dy;
-        bool above;
-        if (t < A * dx0)      above = (0.5f * (A * dx0 * dx0 + C * dy * dy) + B * dx0 * dy) > tqs;
-        else if (t > A * dx1) above = (0.5f * (A * dx1 * dx1 + C * dy * dy) + B * dx1 * dy) > tqs;
-        else                  above = hd * dy * dy > tqs * A;
-        all_above = all_above && above;
-    }
-    return all_above;
-}

@@ -66,7 +66,7 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
 {
     __shared__ float4 s_rec[2][kSub * 3];
     __shared__ __align__(16) float s_part[8][kSub][16];
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.y * p.grid_x + blockIdx.x;
-    const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
+    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
+    const int pix_x = tile_x * EX_TILE + (warp & 1) * 8 + (lane & 7);
+    const int pix_y = tile_y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = pix_x < p.W && pix_y < p.H;
     const int pix_id = p.W * pix_y + pix_x;
     const size_t HW = (size_t)p.H * p.W;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
                 const int jj = g + lane;
                 bool keep = false;
                 // entry jj sits at list position q = start-1-(r*kSub+jj); only q < warp_last can matter
-                if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !block_reject(s[jj * 3], s[jj * 3 + 1], box);
+                if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !EX_BLOCK_TEST(s[jj * 3], s[jj * 3 + 1], box);
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 if (keep) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
                 nw += __popc(m);
@@ -266,6 +267,6 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(const __grid_constan
 
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
-    dim3 grid(grid_x, grid_y, 1);
+    dim3 grid(grid_x * grid_y, 1, 1);
     render_bwd_kernel<<<grid, 256, 0, s>>>(p);
 }
