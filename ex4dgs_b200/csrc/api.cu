@@ -128,7 +128,6 @@ ImageState carve_image(void* base, int width, int height)
     im.n_contrib = c.take<uint32_t>(n);
     im.ranges = c.take<uint2>(tiles);
     im.tile_batches = c.take<uint32_t>(tiles);
-    im.tile_order = c.take<uint32_t>(tiles);
     im.total = c.off + 256;
     return im;
 }
@@ -336,7 +335,6 @@ int ex4dgs_forward(
 
     rp.point_list = bin.point_list;
     rp.rec = geom.rec;
-    rp.tile_order = (P > 0 && R > 0) ? img.tile_order : nullptr;
     prof.mark();
     launch_render_fwd(rp, grid_x, grid_y, s);
     g_launches += 1;
@@ -386,7 +384,6 @@ int ex4dgs_backward(
     RenderParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.ranges = img.ranges; rp.point_list = bin.point_list; rp.rec = geom.rec;
-    rp.tile_order = (R > 0) ? img.tile_order : nullptr;
     rp.W = width; rp.H = height; rp.grid_x = grid_x;
     rp.subpixel_offset = reinterpret_cast<const float2*>(subpixel_offset);
     rp.bg = background;

@@ -131,40 +131,6 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t*
     }
 }
 
-// Longest-processing-time-first launch order for the compositing kernels: tiles are bucketed by
-// the length of their splat list (32 logarithmic classes, longest first) with one counting sort in
-// a single CTA, so that the last wave of CTAs is made of short tiles.  Order within a class is
-// arbitrary (outputs do not depend on scheduling order).
-__global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ order)
-{
-    __shared__ unsigned s_cnt[32], s_base[32];
-    const int tid = threadIdx.x;
-    if (tid < 32) s_cnt[tid] = 0;
-    __syncthreads();
-    auto cls = [](uint32_t len) -> int {
-        // half-octave size classes: k = 2*floor(log2 len) + next bit; longer lists -> smaller class
-        if (len == 0) return 31;
-        const int lg = 31 - __clz(len);
-        const int half = (len >> (lg > 0 ? lg - 1 : 0)) & 1;
-        const int k = 2 * lg + half;
-        return min(30, max(0, 40 - k));
-    };
-    for (int t = tid; t < tiles; t += blockDim.x) {
-        const uint2 r = ranges[t];
-        atomicAdd(&s_cnt[cls(r.y - r.x)], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned run = 0;
-        for (int c = 0; c < 32; c++) { s_base[c] = run; run += s_cnt[c]; }
-    }
-    __syncthreads();
-    for (int t = tid; t < tiles; t += blockDim.x) {
-        const uint2 r = ranges[t];
-        order[atomicAdd(&s_base[cls(r.y - r.x)], 1u)] = (uint32_t)t;
-    }
-}
-
 // max |subpixel offset| -> *out (float bits, non-negative, so integer max orders correctly).
 // Needed by the exact tile culling: pixel centres are integer + offset.
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ v, size_t n, uint32_t* out)
@@ -275,6 +241,5 @@ cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const 
     if (e != cudaSuccess) return e;
     const int groups = (R + 7) / 8;
     tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu);
-    tile_order_kernel<<<1, 1024, 0, s>>>(tiles, img.ranges, img.tile_order);
     return cudaGetLastError();
 }

@@ -100,7 +100,6 @@ struct ImageState {
     uint32_t* n_contrib;      // [W*H]
     uint2* ranges;            // [tiles]
     uint32_t* tile_batches;   // [tiles] number of 256-splat batches the forward fetched (stats)
-    uint32_t* tile_order;     // [tiles] launch order of the compositing CTAs (longest lists first)
     size_t total;
 };
 
@@ -142,7 +141,6 @@ struct RenderParams {
     const uint2* ranges;
     const uint32_t* point_list;
     const SplatRec* rec;
-    const uint32_t* tile_order;   // CTA index -> tile id (NULL: identity)
     int W, H, grid_x;
     const float2* subpixel_offset;
     const float* bg;     // [3] device

@@ -77,10 +77,9 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
-    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
-    const int pix_x = tile_x * EX_TILE + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = tile_y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int tile = blockIdx.y * p.grid_x + blockIdx.x;
+    const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
+    const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = pix_x < p.W && pix_y < p.H;
     const int pix_id = p.W * pix_y + pix_x;
     const size_t HW = (size_t)p.H * p.W;
@@ -267,6 +266,6 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
-    dim3 grid(grid_x * grid_y, 1, 1);
+    dim3 grid(grid_x, grid_y, 1);
     render_bwd_kernel<<<grid, 256, 0, s>>>(p);
 }
