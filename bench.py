@@ -111,6 +111,16 @@ def load_reference():
     return mod
 
 
+def load_reference_loss():
+    """utils/loss_utils.py of the reference, installed unmodified next to the extension (oracle/build_ref.py)."""
+    d = os.path.join(ROOT, "oracle", "_ref", "callers")
+    if not os.path.exists(os.path.join(d, "utils", "loss_utils.py")):
+        return None
+    sys.path.insert(0, d)
+    from utils import loss_utils
+    return loss_utils
+
+
 class Frame:
     """Resident inputs of one rank + the step functions."""
 
@@ -187,6 +197,43 @@ class Frame:
             torch.distributed.all_reduce(l)
         self.h_loss.copy_(l, non_blocking=True)
         self._zero()
+
+
+def make_train_step(frame: Frame, ref_loss, lambda_dssim=0.2):
+    """The training iteration of train.py:139-172 around the rasterizer: H2D camera + ground truth,
+    render, loss = 0.8 L1 + 0.2 (1 - SSIM), the l1_accum hook tensor as the flow gradient, backward,
+    loss D2H.  ref_loss = the reference's utils/loss_utils module (reference arm) or None (fused loss)."""
+    if ref_loss is None:
+        from ex4dgs_b200.loss import photometric_loss
+
+    def step(group=None):
+        main = torch.cuda.current_stream(frame.dev)
+        frame.d_cam.copy_(frame.h_cam, non_blocking=True)
+        frame.copy_stream.wait_stream(main)
+        with torch.cuda.stream(frame.copy_stream):
+            frame.d_gt.copy_(frame.h_gt, non_blocking=True)
+        c = frame.d_cam
+        image, radii, depth, flow, acc, idxs = frame._raster(frame.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35]))
+        main.wait_stream(frame.copy_stream)
+        gt_image = frame.d_gt
+        if ref_loss is None:
+            loss, Ll1, _, l1_errors, ssim_errors = photometric_loss(image, gt_image, lambda_dssim)
+        else:
+            Ll1 = ref_loss.l1_loss(image, gt_image)
+            loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ref_loss.ssim(image, gt_image))
+            l1_errors = (image - gt_image).abs().mean(dim=0)
+            ssim_errors = ref_loss.ssim(image, gt_image, reduce=False).mean(dim=0)
+        hook_tensor = torch.stack([acc[0], l1_errors, ssim_errors])
+        flow_h = flow.register_hook(lambda grad: hook_tensor)
+        loss = loss + flow.mean() * 0
+        loss.backward()
+        flow_h.remove()                                  # train.py:173
+        l = loss.detach().reshape(1)
+        if group is not None:
+            torch.distributed.all_reduce(l)
+        frame.h_loss.copy_(l, non_blocking=True)
+        frame._zero()
+    return step
 
 
 def frame_stats(frame: Frame):
@@ -358,6 +405,31 @@ def main():
         frame.step_e2e(group)
     ms_e2e, _, _ = timed(lambda: frame.step_e2e(group), K)
 
+    # training-iteration leg (row N2): the same step with the reference's loss block, train.py:144-151
+    train = None
+    if not args.fwd_only:
+        ref_loss = None
+        if args.impl != "ours":
+            ref_loss = load_reference_loss()
+            if ref_loss is None:                       # restated in float32 torch ops by the oracle
+                from oracle import loss_oracle
+                class _L:                              # noqa: E306
+                    l1_loss = staticmethod(lambda a, b: (a - b).abs().mean())
+                    @staticmethod
+                    def ssim(a, b, reduce=True):
+                        m = loss_oracle.ssim_map(a, b, torch.float32)
+                        return m.mean() if reduce else m
+                ref_loss = _L
+        train_step = make_train_step(frame, ref_loss)
+        for _ in range(W):
+            train_step(group)
+        ms_train, _, _ = timed(lambda: train_step(group), K)
+        train = {"value": ws * K / (ms_train / 1000.0), "unit": "frames/s", "ms_per_step": ms_train / K,
+                 "what": "training iteration around the rasterizer (train.py:139-172): H2D camera + ground truth, render, "
+                         "loss = 0.8 L1 + 0.2 (1 - SSIM) + l1_accum hook tensor, backward, loss D2H; "
+                         + ("fused loss kernels (ex4dgs_b200/loss.py)" if args.impl == "ours" else
+                            "the reference's utils/loss_utils.py (torch conv2d)")}
+
     value = ws * K / (ms_total / 1000.0)
     e2e_value = ws * K / (ms_e2e / 1000.0)
     if rank != 0:
@@ -374,6 +446,8 @@ def main():
                     "what": "per frame: H2D camera (35 floats) + ground-truth image from pinned memory, forward, L1 loss, "
                             "backward, loss (all-reduced over ranks) D2H; Gaussian parameters resident"},
             "clocks": clocks}
+    if train is not None:
+        line["train_step"] = train
     if args.impl == "ours":
         st = frame_stats(frame)
         peaks = {}

@@ -71,6 +71,9 @@ SIGNATURES = {
                                       _P, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _P,
                                       _P]),
+    "ex4dgs_loss_scratch_bytes": (C.c_size_t, [_I, _I]),
+    "ex4dgs_loss_forward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "ex4dgs_loss_backward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P]),
 }
 
 _lib = None

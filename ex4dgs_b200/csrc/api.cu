@@ -427,4 +427,35 @@ int ex4dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, co
     return EX4DGS_OK;
 }
 
+size_t ex4dgs_loss_scratch_bytes(int width, int height)
+{
+    return (width > 0 && height > 0) ? loss_scratch_bytes(width, height) : 0;
+}
+
+int ex4dgs_loss_forward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
+                        char* scratch, float* out_loss3, float* l1_errors, float* ssim_errors, void* stream)
+{
+    g_err[0] = 0;
+    if (width <= 0 || height <= 0 || !image || !gt_image || !scratch || !out_loss3 || !l1_errors || !ssim_errors)
+        return fail(EX4DGS_ERR_INVALID, "bad arguments");
+    cudaError_t e = launch_loss_forward(width, height, image, gt_image, lambda_dssim, scratch, out_loss3,
+                                        l1_errors, ssim_errors, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "loss_forward: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return EX4DGS_OK;
+}
+
+int ex4dgs_loss_backward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
+                         const char* scratch, const float* dL_dloss, float* dL_dimage, void* stream)
+{
+    g_err[0] = 0;
+    if (width <= 0 || height <= 0 || !image || !gt_image || !scratch || !dL_dloss || !dL_dimage)
+        return fail(EX4DGS_ERR_INVALID, "bad arguments");
+    cudaError_t e = launch_loss_backward(width, height, image, gt_image, lambda_dssim, scratch, dL_dloss,
+                                         dL_dimage, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "loss_backward: %s", cudaGetErrorString(e));
+    g_launches += 1;
+    return EX4DGS_OK;
+}
+
 }  // extern "C"

@@ -196,6 +196,12 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
                          float min_depth, float max_depth, uint8_t* present, cudaStream_t s);
 void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
+// photometric loss (loss.cu): scratch = per-block partial sums + the three SSIM derivative maps
+size_t loss_scratch_bytes(int W, int H);
+cudaError_t launch_loss_forward(int W, int H, const float* img, const float* gt, float lambda, char* scratch,
+                                float* out3, float* l1_err, float* ssim_err, cudaStream_t stream);
+cudaError_t launch_loss_backward(int W, int H, const float* img, const float* gt, float lambda, const char* scratch,
+                                 const float* dL_dloss, float* dL_dimg, cudaStream_t stream);
 
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
 size_t binning_stage1_temp_bytes(int P);

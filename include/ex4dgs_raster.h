@@ -205,6 +205,24 @@ int ex4dgs_frontend_backward(
     float* dL_dopacity_motion, float* dL_dopacity_center, float* dL_dopacity_var,
     void* stream);
 
+/* ---- photometric loss -------------------------------------------
+ * Replaces, for one rendered frame, the loss block of the reference's training step
+ * (train.py:144-151 with utils/loss_utils.py:22-25 l1_loss and :33-81 ssim/_ssim):
+ *     Ll1   = mean |image - gt_image|
+ *     ssim  = mean ssim_map(image, gt_image)      11x11 Gaussian window, sigma 1.5, zero padding 5
+ *     loss  = (1 - lambda_dssim) * Ll1 + lambda_dssim * (1 - ssim)
+ *     l1_errors   [H,W] = mean over channels of |image - gt_image|          (train.py:149)
+ *     ssim_errors [H,W] = mean over channels of ssim_map                    (train.py:150)
+ * image, gt_image: device float [3,H,W].  out_loss3: device float[3] = {loss, Ll1, ssim}.
+ * scratch: device bytes, ex4dgs_loss_scratch_bytes(width, height), kept by the caller between the
+ * forward and the backward of the same frame.  Sums are reduced in a fixed order (bit-reproducible). */
+size_t ex4dgs_loss_scratch_bytes(int width, int height);
+int ex4dgs_loss_forward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
+                        char* scratch, float* out_loss3, float* l1_errors, float* ssim_errors, void* stream);
+/* dL_dloss: device scalar (the gradient arriving at `loss`); dL_dimage: device float [3,H,W], overwritten. */
+int ex4dgs_loss_backward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
+                         const char* scratch, const float* dL_dloss, float* dL_dimage, void* stream);
+
 /* ---- introspection (used by the parity tests to look inside the opaque scratch buffers) ------- */
 typedef struct ex4dgs_array_desc {
     const char* name;    /* e.g. "point_list"                                  */

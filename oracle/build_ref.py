@@ -85,10 +85,12 @@ def install_callers():
     """Install (git-ignored, like the extension) the reference's ONLY caller of the rasterizer,
     gaussian_renderer/__init__.py, and its one pure-PyTorch import (utils/sh_utils.py), so that the
     GPU box can run the unmodified render() against this repository's drop-in package
-    (tests/test_gpu_dropin.py).  Nothing else of the reference is needed by render()."""
+    (tests/test_gpu_dropin.py); plus utils/loss_utils.py (and its import utils/graphics_utils.py),
+    the loss block of train.py:144-151, so that `bench.py --impl reference` can time the reference's
+    own training-step loss next to the fused one (row N2)."""
     root = "/root/reference"
     dst = os.path.join(HERE, "_ref", "callers")
-    for rel in ("gaussian_renderer/__init__.py", "utils/sh_utils.py"):
+    for rel in ("gaussian_renderer/__init__.py", "utils/sh_utils.py", "utils/loss_utils.py", "utils/graphics_utils.py"):
         os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
         shutil.copyfile(os.path.join(root, rel), os.path.join(dst, rel))
     open(os.path.join(dst, "utils", "__init__.py"), "a").close()
