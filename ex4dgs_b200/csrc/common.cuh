@@ -20,7 +20,7 @@
 #define EX_FWD_MINBLOCKS 4      // 64 registers (44 B of spills) but 32 resident warps: 0.49 vs 0.53 ms at C3
 #endif
 #ifndef EX_BWD_MINBLOCKS
-#define EX_BWD_MINBLOCKS 3
+#define EX_BWD_MINBLOCKS 4      // 64 registers; with the barrier-free loop 1.166 vs 1.198 ms at C3
 #endif
 #define EX_BLOCK_TEST block_reject   // an exact 4-edge variant was measured slower (more instructions than it saves)
 
@@ -366,6 +366,11 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)

@@ -23,6 +23,13 @@
 namespace {
 
 constexpr int kSub = 64;   // splats per sub-batch
+constexpr int kRing = 4;   // staging buffers
+constexpr int kAhead = 2;  // sub-batches in flight ahead of the one being consumed
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v)
 {
@@ -68,12 +75,11 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
 
 __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
 {
-    __shared__ float4 s_rec[2][kSub * 3];
-    __shared__ __align__(16) float s_part[8][kSub][16];
-    __shared__ unsigned long long s_mask[8];
+    __shared__ float4 s_rec[kRing][kSub * 3];
     __shared__ uint8_t s_list[8][kSub];
     __shared__ int s_start;
-    __shared__ __align__(8) unsigned long long s_bar[2];     // one mbarrier per ring buffer
+    __shared__ __align__(8) unsigned long long s_full[kRing];     // records of a sub-batch have landed (TMA byte count)
+    __shared__ __align__(8) unsigned long long s_empty[kRing];    // all 8 warps are done with the buffer
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -87,8 +93,11 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
     const uint2 range = p.ranges[tile];
     if (tid == 0) {
         s_start = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < kRing; i++) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 8);
+        }
         mbar_fence_init();
     }
     __syncthreads();
@@ -138,30 +147,38 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
     float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
     float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
 
-    // TMA staging: thread t < kSub owns slot t and issues one 48-byte bulk copy of its splat's record
-    // (the dir3D word is not needed here); thread 0 announces the byte count to the buffer's mbarrier
+    // TMA staging: every warp fetches 8 records of each sub-batch (lanes 0-7, one 48-byte bulk copy
+    // each; the dir3D word is not needed here), kAhead sub-batches ahead; thread 0 announces the byte
+    // count of the whole sub-batch to the buffer's `full` barrier.  No block-wide barrier in the loop:
+    // a warp only waits for the records (full) and, before refilling a buffer, for the slowest warp to
+    // have left it (empty) - with kRing buffers the warps of a tile may drift kRing - kAhead
+    // sub-batches apart, which absorbs the imbalance between the 8x4 pixel blocks.
+    const int slot = warp * 8 + lane;      // valid for lane < 8
     auto list_id = [&](int r) -> int {
-        const int q = start - 1 - (r * kSub + tid);
-        return (tid < kSub && q >= 0) ? (int)__ldg(p.point_list + range.x + q) : -1;
+        const int q = start - 1 - (r * kSub + slot);
+        return (lane < 8 && r < rounds && q >= 0) ? (int)__ldg(p.point_list + range.x + q) : -1;
     };
-    auto stage = [&](int buf, int r, int id) {
-        const int cnt_b = min(kSub, start - r * kSub);
-        if (tid == 0) mbar_arrive_expect_tx(&s_bar[buf], (unsigned)(cnt_b * 48));
-        if (id >= 0) tma_bulk_g2s(&s_rec[buf][tid * 3], p.rec + id, 48, &s_bar[buf]);
+    auto stage = [&](int r, int id) {
+        const int buf = r % kRing;
+        if (tid == 0) mbar_arrive_expect_tx(&s_full[buf], (unsigned)(min(kSub, start - r * kSub) * 48));
+        if (id >= 0) tma_bulk_g2s(&s_rec[buf][slot * 3], p.rec + id, 48, &s_full[buf]);
     };
-    stage(0, 0, list_id(0));
-    int id_next = (rounds > 1) ? list_id(1) : -1;
+#pragma unroll
+    for (int r = 0; r < kAhead; r++)
+        if (r < rounds) stage(r, list_id(r));
+    int id_next = list_id(kAhead);
 
     for (int r = 0; r < rounds; r++) {
-        mbar_wait(&s_bar[r & 1], (unsigned)((r >> 1) & 1));      // sub-batch r has landed
-        __syncthreads();                       // (A) s_part / buffer (r+1)&1 free
-        if (r + 1 < rounds) {
-            stage((r + 1) & 1, r + 1, id_next);
-            id_next = (r + 2 < rounds) ? list_id(r + 2) : -1;
+        const int buf = r % kRing;
+        if (r + kAhead < rounds) {
+            const int rn = r + kAhead;                 // refills the buffer sub-batch rn - kRing used
+            if (rn >= kRing) mbar_wait(&s_empty[rn % kRing], (unsigned)(((rn - kRing) / kRing) & 1));
+            stage(rn, id_next);
+            id_next = list_id(rn + 1);
         }
-        const float4* __restrict__ s = s_rec[r & 1];
+        mbar_wait(&s_full[buf], (unsigned)((r / kRing) & 1));      // sub-batch r has landed
+        const float4* __restrict__ s = s_rec[buf];
         const int cnt = min(kSub, start - r * kSub);
-        unsigned long long mask = 0ull;
         // which splats of the sub-batch can touch this warp's pixel block at all (exact, see block_reject)
         int nw = 0;
         if (!warp_idle && (start - r * kSub - cnt) < warp_last) {      // some entry of the sub-batch is still live for this warp
@@ -192,11 +209,11 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
                 contributes = !(alpha < 1.0f / 255.0f);
             }
             if (!__any_sync(0xffffffffu, contributes)) continue;
+            const float4 c = s[j * 3 + 2];
             float v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = 0.f;
             if (contributes) {
-                const float4 c = s[j * 3 + 2];
                 const float inv1ma = 1.f / (1.f - alpha);
                 T = T * inv1ma;
                 const float w = alpha * T;               // dchannel_dcolor
@@ -231,33 +248,14 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
                 v[3] = G * dL_dalpha + G * dL_dacc;
             }
             const float tot = butterfly16(v, lane);
-            if (!(lane & 1)) {
-                const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                s_part[warp][j][k] = tot;
-            }
-            mask |= 1ull << j;
+            // even lanes hold the 16 totals; 13 of them are real.  One warp-level reduction instruction:
+            // 13 lanes add into the 64-byte accumulator of the splat (2 sectors).
+            const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (!(lane & 1) && (k == 3 || (k & 3) != 3))
+                red_add_f32(reinterpret_cast<float*>(p.gacc + __float_as_int(c.w)) + k, tot);
         }
-        if (lane == 0) s_mask[warp] = mask;
-        __syncthreads();                       // (B) partial sums of all warps complete
-        {
-            const int jj = tid >> 2, qd = tid & 3;
-            if (jj < cnt) {
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool any = false;
-#pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    if ((s_mask[w] >> jj) & 1ull) {
-                        const float4 t = *reinterpret_cast<const float4*>(&s_part[w][jj][4 * qd]);
-                        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-                        any = true;
-                    }
-                }
-                if (any) {
-                    const int id = __float_as_int(s[jj * 3 + 2].w);
-                    red_add_v4(reinterpret_cast<float*>(p.gacc + id) + 4 * qd, sum);
-                }
-            }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);     // this warp no longer reads buffer `buf`
     }
 }
 
