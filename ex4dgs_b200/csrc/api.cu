@@ -405,6 +405,7 @@ int ex4dgs_backward(
     bp.focal_x = width / (2.0f * tan_fovx);
     bp.kernel_size = kernel_size;
     bp.radii = radii; bp.clamped = geom.clamped; bp.gacc = geom.gacc;
+    bp.W = (float)width; bp.H = (float)height;
     bp.dL_dmean2D = dL_dmean2D; bp.dL_dopacity = dL_dopacity; bp.dL_dcolor = dL_dcolor; bp.dL_dmean3D = dL_dmean3D;
     bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscale = dL_dscale; bp.dL_drot = dL_drot; bp.dL_ddir = dL_ddir;
     launch_preprocess_bwd(bp, s);

@@ -47,13 +47,26 @@ struct __align__(16) SplatRec {
     float4 a, b, c, d;
 };
 
-// Per-Gaussian gradient accumulator written by the backward compositing loop with 16-byte
-// vector reductions, consumed by the fused preprocess backward.
+// Per-Gaussian gradient accumulator written by the backward compositing loop with warp-level
+// reductions, consumed by the fused preprocess backward through gacc_load().
 //   g0 = (dL/dmean2D.x, .y, .z, dL/dopacity)   g1 = (dL/dconic.x, .y, .w, 0)
 //   g2 = (dL/dcolor r, g, b, 0)                g3 = (dL/ddir x, y, z, 0)
+// The compositing loop leaves the per-Gaussian constant factors out of its inner loop: it stores
+// g0.x / (-W/2), g0.y / (-H/2) and g1.xyz / (-1/2); gacc_load() applies them once per Gaussian.
 struct __align__(16) GradAcc {
     float4 g0, g1, g2, g3;
 };
+
+__device__ __forceinline__ GradAcc gacc_load(const GradAcc* gacc, int idx, float W, float H)
+{
+    GradAcc g = gacc[idx];
+    g.g0.x *= -0.5f * W;
+    g.g0.y *= -0.5f * H;
+    g.g1.x *= -0.5f;
+    g.g1.y *= -0.5f;
+    g.g1.z *= -0.5f;
+    return g;
+}
 
 struct Carver {
     char* base;
@@ -178,6 +191,7 @@ struct PreprocessBwdParams {
     const int* radii;
     const uint8_t* clamped;
     const GradAcc* gacc;
+    float W, H;          // image size (gacc_load)
     float* dL_dmean2D;
     float* dL_dopacity;
     float* dL_dcolor;

@@ -37,14 +37,20 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v)
                  : "memory");
 }
 
-// Reduce 16 per-lane values over the warp; afterwards lane L holds the total of value
+// Reduce 16 per-lane value slots over the warp; afterwards lane L holds the total of slot
 // k(L) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of L (both lanes of a pair hold the same total).
+// Slots 7, 11 and 15 are unused by the caller: their exchanges are dropped or left unselected, the
+// lanes that would hold their totals end up with don't-care values.
 __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
 {
     const unsigned full = 0xffffffffu;
     bool hi = lane & 16;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 7; i++) {
+        if (i == 3) {                       // slot 11 unused: the upper half-warp's result is don't-care
+            v[3] += __shfl_xor_sync(full, v[3], 16);
+            continue;
+        }
         const float mine = hi ? v[i + 8] : v[i];
         const float other = hi ? v[i] : v[i + 8];
         v[i] = mine + __shfl_xor_sync(full, other, 16);
@@ -52,6 +58,10 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
     hi = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
+        if (i == 3) {                       // slots 7 / 15 unused
+            v[3] += __shfl_xor_sync(full, v[3], 8);
+            continue;
+        }
         const float mine = hi ? v[i + 4] : v[i];
         const float other = hi ? v[i] : v[i + 4];
         v[i] = mine + __shfl_xor_sync(full, other, 8);
@@ -142,7 +152,6 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
     const bool warp_idle = __all_sync(0xffffffffu, last_contributor == 0);
     const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);   // list positions >= this are dead for the warp
     const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
-    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     float T = T_final;
     float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
     float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
@@ -236,15 +245,14 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
                 dL_dacc *= T;
                 last_alpha = alpha;
                 dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                const float dL_dG = b.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * b.x - gdy * b.y;
-                const float dG_ddely = -gdy * b.z - gdx * b.y;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[4] = -0.5f * gdx * dx * dL_dG;
-                v[5] = -0.5f * gdx * dy * dL_dG;
-                v[6] = -0.5f * gdy * dy * dL_dG;
+                // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
+                const float gG = G * (b.w * dL_dalpha);
+                const float X = gG * dx, Y = gG * dy;
+                v[0] = X * b.x + Y * b.y;
+                v[1] = Y * b.z + X * b.y;
+                v[4] = X * dx;
+                v[5] = X * dy;
+                v[6] = Y * dy;
                 v[3] = G * dL_dalpha + G * dL_dacc;
             }
             const float tot = butterfly16(v, lane);
