@@ -16,6 +16,27 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_last_R = 0;     // sizing hint only (previous frame of this thread)
+
+// Pinned landing pad of the forward's one read-back (R and the flow flag), one per host thread and
+// device: with pinned memory both 4-byte copies are truly asynchronous and cost a single sync.
+struct Readback {
+    uint32_t* host = nullptr;
+    int device = -1;
+    uint32_t* get()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+        if (host == nullptr || dev != device) {
+            if (host) cudaFreeHost(host);
+            host = nullptr;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&host), 64, cudaHostAllocDefault) != cudaSuccess) host = nullptr;
+            device = dev;
+        }
+        return host;
+    }
+    ~Readback() { if (host) cudaFreeHost(host); }
+};
+thread_local Readback g_readback;
 // Measurement state is process-wide: autograd runs the backward on its own thread.
 std::atomic<bool> g_prof{false};
 std::atomic<unsigned long long> g_launches{0};
@@ -251,6 +272,7 @@ int ex4dgs_forward(
     rp.out_color = out_color; rp.out_depth = out_depth; rp.out_acc = out_acc; rp.out_flow = out_flow; rp.out_idx = out_idx;
 
     int R = 0, spec_R = 0;
+    uint32_t flow32 = 0;      // read back with R: does any visible Gaussian carry a non-zero dir3D?
     void* spec_base = nullptr;
     GeometryState geom;
     memset(&geom, 0, sizeof(geom));
@@ -285,6 +307,8 @@ int ex4dgs_forward(
         pp.radii = radii; pp.key_in = geom.key_in; pp.val_in = geom.val_in; pp.tiles_touched = geom.tiles_touched;
         pp.rec = geom.rec; pp.clamped = geom.clamped;
         pp.pad_ptr = reinterpret_cast<const float*>(geom.meta);
+        pp.flow_flag = geom.meta + 1;
+        CK(cudaMemsetAsync(geom.meta, 0, 2 * sizeof(uint32_t), s));     // [0] max |subpixel offset| bits, [1] flow flag
         if (flags & EX4DGS_FLAG_TILE_CULL)
             CK(launch_subpixel_absmax(subpixel_offset, (size_t)width * height * 2, geom.meta, s));
         prof.mark();
@@ -297,8 +321,10 @@ int ex4dgs_forward(
         STAGE(debug, s, "depth sort + scan");
         // the one blocking read-back of the pipeline (rasterizer_impl.cu:299)
         prof.mark();
-        uint32_t r32 = 0;
-        CK(cudaMemcpyAsync(&r32, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        uint32_t* rb = g_readback.get();
+        if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
+        CK(cudaMemcpyAsync(rb, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rb + 1, geom.meta + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning
         // buffer sized from the previous frame of this thread (+25 %): the allocator callback (a trip
         // into Python) then overlaps the device work instead of extending the idle gap after the sync.
@@ -312,7 +338,8 @@ int ex4dgs_forward(
             }
         }
         CK(cudaStreamSynchronize(s));
-        R = (int)r32;
+        R = (int)rb[0];
+        flow32 = rb[1];
         g_last_R = R;
     }
 
@@ -336,7 +363,7 @@ int ex4dgs_forward(
     rp.point_list = bin.point_list;
     rp.rec = geom.rec;
     prof.mark();
-    launch_render_fwd(rp, grid_x, grid_y, s);
+    launch_render_fwd(rp, grid_x, grid_y, flow32 != 0, s);
     g_launches += 1;
     STAGE(debug, s, "render");
     prof.mark();

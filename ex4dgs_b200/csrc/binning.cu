@@ -205,10 +205,9 @@ size_t binning_stage2_temp_bytes(int R)
     return last_bytes;
 }
 
+// `out` must have been zeroed by the caller
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s)
 {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
     absmax_kernel<<<148 * 8, 256, 0, s>>>(subpixel_offset, n, out);
     return cudaGetLastError();
 }

@@ -20,7 +20,19 @@
 #define EX_FWD_MINBLOCKS 4      // 64 registers (44 B of spills) but 32 resident warps: 0.49 vs 0.53 ms at C3
 #endif
 #ifndef EX_BWD_MINBLOCKS
-#define EX_BWD_MINBLOCKS 4      // 64 registers; with the barrier-free loop 1.166 vs 1.198 ms at C3
+#define EX_BWD_MINBLOCKS 5      // CTAs of 128 threads (PPT = 2): 96 registers, 20 resident warps; 0.926 ms vs 1.011 (4) / 0.948 (6) at C3
+#endif
+#ifndef EX_FWD_STAGE_LDGSTS
+#define EX_FWD_STAGE_LDGSTS 1   // forward staging: 1 = per-thread 16-byte cp.async (LDGSTS), 0 = one TMA bulk copy per splat.
+                                // A bulk copy takes uniform registers, so 32 per-lane copies become a 32-trip loop of 9
+                                // instructions (7 % of the kernel's issue slots, ncu r1i); measured 0.422 vs 0.439 ms at C3.
+#endif
+#ifndef EX_BWD_FAST_RCP
+#define EX_BWD_FAST_RCP 1       // T /= (1 - alpha) with MUFU.RCP: 1.011 vs 1.075 ms at C3, gradients within the 1e-3 budget
+#endif
+#ifndef EX_BWD_PPT
+#define EX_BWD_PPT 2            // pixels per thread in the backward compositing kernel (1: 8 warps x 8x4, 2: 4 warps x 8x8);
+                                // PPT = 1 needs EX_BWD_MINBLOCKS <= 4 (256-thread CTAs); measured 0.982 (1) vs 0.926 ms (2)
 #endif
 #define EX_BLOCK_TEST block_reject   // an exact 4-edge variant was measured slower (more instructions than it saves)
 
@@ -148,6 +160,7 @@ struct PreprocessParams {
     uint32_t* tiles_touched;
     SplatRec* rec;
     uint8_t* clamped;
+    uint32_t* flow_flag;    // device word, set to 1 when a visible Gaussian has a non-zero dir3D component
 };
 
 struct RenderParams {
@@ -208,7 +221,7 @@ void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s);
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                          float min_depth, float max_depth, uint8_t* present, cudaStream_t s);
-void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
+void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, bool with_flow, cudaStream_t s);
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
 // photometric loss (loss.cu): scratch = per-block partial sums + the three SSIM derivative maps
 size_t loss_scratch_bytes(int W, int H);
@@ -329,6 +342,21 @@ struct BlockBox {
     float x0, x1, y0, y1;
 };
 
+// warp-wide union of per-lane boxes (an unused lane passes x0 = y0 = 3e38, x1 = y1 = -3e38)
+__device__ __forceinline__ BlockBox block_box_merge(float x0, float x1, float y0, float y1)
+{
+    BlockBox b;
+    b.x0 = x0; b.x1 = x1; b.y0 = y0; b.y1 = y1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        b.x0 = fminf(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, d));
+        b.x1 = fmaxf(b.x1, __shfl_xor_sync(0xffffffffu, b.x1, d));
+        b.y0 = fminf(b.y0, __shfl_xor_sync(0xffffffffu, b.y0, d));
+        b.y1 = fmaxf(b.y1, __shfl_xor_sync(0xffffffffu, b.y1, d));
+    }
+    return b;
+}
+
 __device__ __forceinline__ BlockBox block_box(float pxf, float pyf, bool use)
 {
     BlockBox b;
@@ -370,6 +398,23 @@ __device__ __forceinline__ bool block_reject(const float4& a, const float4& b, c
 // thread that owns the slot; completion is tracked by an mbarrier per ring buffer whose expected
 // transaction bytes are announced by thread 0 (the tx-count may run ahead of the expectation).
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// per-thread 16-byte asynchronous copy global -> shared (LDGSTS), tracked by cp.async groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// 16-byte shared-memory load from a 32-bit shared address (keeps the per-buffer base in one register:
+// through a generic pointer the compiler re-derives the shared window base in every loop iteration)
+__device__ __forceinline__ float4 lds128(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {

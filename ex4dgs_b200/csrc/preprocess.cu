@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         rc.b = make_float4(conA, conB, conC, opac);
         rc.c = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(idx));
         rc.d = make_float4(__ldg(p.dir3D + 3 * idx), __ldg(p.dir3D + 3 * idx + 1), __ldg(p.dir3D + 3 * idx + 2), 0.f);
+        // anything but +-0 (NaN/inf included) makes the compositing kernel carry the flow accumulators
+        if (((__float_as_uint(rc.d.x) | __float_as_uint(rc.d.y) | __float_as_uint(rc.d.z)) & 0x7fffffffu) != 0u) *p.flow_flag = 1u;
         p.rec[idx] = rc;
 
         radius_out = radius;

@@ -83,21 +83,31 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
+// first pixel of a lane assigns, further pixels add (keeps the PPT = 1 code free of `0 + x` adds)
+__device__ __forceinline__ void acc_to(float& dst, float x, int u)
 {
+    if (u == 0) dst = x; else dst += x;
+}
+
+// PPT = pixels per thread.  PPT = 1: 8 warps, each an 8x4 pixel block.  PPT = 2: 4 warps, each an
+// 8x8 block (a lane owns pixels (x, y) and (x, y + 4)): the per-lane gradient terms of the two
+// pixels are added before the warp butterfly, so one butterfly + one reduction instruction serves
+// 64 pixels instead of 32.
+template <int PPT>
+__global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
+{
+    constexpr int NW = 8 / PPT;            // warps per tile
+    constexpr int SLOTS = kSub / NW;       // records each warp fetches per sub-batch
     __shared__ float4 s_rec[kRing][kSub * 3];
-    __shared__ uint8_t s_list[8][kSub];
+    __shared__ uint8_t s_list[NW][kSub];
     __shared__ int s_start;
     __shared__ __align__(8) unsigned long long s_full[kRing];     // records of a sub-batch have landed (TMA byte count)
-    __shared__ __align__(8) unsigned long long s_empty[kRing];    // all 8 warps are done with the buffer
+    __shared__ __align__(8) unsigned long long s_empty[kRing];    // all warps are done with the buffer
 
+    const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
-    const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
-    const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = pix_x < p.W && pix_y < p.H;
-    const int pix_id = p.W * pix_y + pix_x;
     const size_t HW = (size_t)p.H * p.W;
 
     const uint2 range = p.ranges[tile];
@@ -106,66 +116,91 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 #pragma unroll
         for (int i = 0; i < kRing; i++) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 8);
+            mbar_init(&s_empty[i], NW);
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    float pxf = (float)pix_x, pyf = (float)pix_y;
-    float T_final = 0.f, final_acc = 0.f, final_depth = 0.f;
-    int last_contributor = 0;
-    float dL_ddepth = 0.f, dL_dacc = 0.f;
-    float dflow0 = 0.f, dflow1 = 0.f, dflow2 = 0.f;
-    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f;
-    if (inside) {
-        const float2 so = __ldg(p.subpixel_offset + pix_id);
-        pxf = fa(pxf, so.x);
-        pyf = fa(pyf, so.y);
-        T_final = p.final_T[pix_id];
-        last_contributor = (int)p.n_contrib[pix_id];
-        final_acc = __ldg(p.out_acc + pix_id);
-        final_depth = __ldg(p.out_depth + pix_id);
-        dL_ddepth = __ldg(p.dL_ddepth + pix_id);
-        if (final_acc > 0.0f) {
-            dL_ddepth = dL_ddepth / final_acc;
-            dflow0 = __ldg(p.dL_dflow + pix_id) / final_acc;
-            dflow1 = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
-            dflow2 = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
-            dL_dacc = __ldg(p.dL_dacc + pix_id);
+    float pxf[PPT], pyf[PPT], T_final[PPT], final_depth[PPT], dL_ddepth[PPT], dL_dacc[PPT];
+    float dflow0[PPT], dflow1[PPT], dflow2[PPT], dpix0[PPT], dpix1[PPT], dpix2[PPT];
+    int last_contributor[PPT];
+    int lane_last = 0;
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+        const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
+        const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * (4 * PPT) + (lane >> 3) + 4 * u;
+        const bool inside = pix_x < p.W && pix_y < p.H;
+        const int pix_id = p.W * pix_y + pix_x;
+        pxf[u] = (float)pix_x; pyf[u] = (float)pix_y;
+        T_final[u] = 0.f; final_depth[u] = 0.f; dL_ddepth[u] = 0.f; dL_dacc[u] = 0.f;
+        dflow0[u] = dflow1[u] = dflow2[u] = 0.f;
+        dpix0[u] = dpix1[u] = dpix2[u] = 0.f;
+        last_contributor[u] = 0;
+        if (inside) {
+            const float2 so = __ldg(p.subpixel_offset + pix_id);
+            pxf[u] = fa(pxf[u], so.x);
+            pyf[u] = fa(pyf[u], so.y);
+            T_final[u] = p.final_T[pix_id];
+            last_contributor[u] = (int)p.n_contrib[pix_id];
+            const float final_acc = __ldg(p.out_acc + pix_id);
+            final_depth[u] = __ldg(p.out_depth + pix_id);
+            dL_ddepth[u] = __ldg(p.dL_ddepth + pix_id);
+            if (final_acc > 0.0f) {
+                dL_ddepth[u] = dL_ddepth[u] / final_acc;
+                dflow0[u] = __ldg(p.dL_dflow + pix_id) / final_acc;
+                dflow1[u] = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
+                dflow2[u] = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
+                dL_dacc[u] = __ldg(p.dL_dacc + pix_id);
+            }
+            dpix0[u] = __ldg(p.dL_dpix + pix_id);
+            dpix1[u] = __ldg(p.dL_dpix + HW + pix_id);
+            dpix2[u] = __ldg(p.dL_dpix + 2 * HW + pix_id);
         }
-        dpix0 = __ldg(p.dL_dpix + pix_id);
-        dpix1 = __ldg(p.dL_dpix + HW + pix_id);
-        dpix2 = __ldg(p.dL_dpix + 2 * HW + pix_id);
+        lane_last = max(lane_last, last_contributor[u]);
     }
-    {
-        const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
-        if (lane == 0 && wmax > 0) atomicMax(&s_start, wmax);
-    }
+    const int warp_last = __reduce_max_sync(full, lane_last);   // list positions >= this are dead for the warp
+    if (lane == 0 && warp_last > 0) atomicMax(&s_start, warp_last);
     __syncthreads();
     const int start = s_start;            // positions >= start contribute to no pixel of the tile
     if (start == 0) return;
     const int rounds = (start + kSub - 1) / kSub;
 
     // pixels that received nothing in the forward never contribute: keep them out of the warp's box
-    const BlockBox box = block_box(pxf, pyf, last_contributor > 0);
-    const bool warp_idle = __all_sync(0xffffffffu, last_contributor == 0);
-    const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);   // list positions >= this are dead for the warp
-    const float bg_dot_dpixel = __ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1 + __ldg(p.bg + 2) * dpix2;
-    float T = T_final;
-    float accum_rec0 = 0.f, accum_rec1 = 0.f, accum_rec2 = 0.f;
-    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
+    BlockBox box;
+    {
+        float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+#pragma unroll
+        for (int u = 0; u < PPT; u++)
+            if (last_contributor[u] > 0) {
+                x0 = fminf(x0, pxf[u]); x1 = fmaxf(x1, pxf[u]);
+                y0 = fminf(y0, pyf[u]); y1 = fmaxf(y1, pyf[u]);
+            }
+        box = block_box_merge(x0, x1, y0, y1);
+    }
+    const bool warp_idle = warp_last == 0;
+    const float bg0 = __ldg(p.bg + 0), bg1 = __ldg(p.bg + 1), bg2 = __ldg(p.bg + 2);
+    float bg_dot_dpixel[PPT], T[PPT];
+    float accum_rec0[PPT], accum_rec1[PPT], accum_rec2[PPT];
+    float last_alpha[PPT], last_c0[PPT], last_c1[PPT], last_c2[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+        bg_dot_dpixel[u] = bg0 * dpix0[u] + bg1 * dpix1[u] + bg2 * dpix2[u];
+        T[u] = T_final[u];
+        accum_rec0[u] = accum_rec1[u] = accum_rec2[u] = 0.f;
+        last_alpha[u] = last_c0[u] = last_c1[u] = last_c2[u] = 0.f;
+    }
 
-    // TMA staging: every warp fetches 8 records of each sub-batch (lanes 0-7, one 48-byte bulk copy
-    // each; the dir3D word is not needed here), kAhead sub-batches ahead; thread 0 announces the byte
-    // count of the whole sub-batch to the buffer's `full` barrier.  No block-wide barrier in the loop:
-    // a warp only waits for the records (full) and, before refilling a buffer, for the slowest warp to
-    // have left it (empty) - with kRing buffers the warps of a tile may drift kRing - kAhead
-    // sub-batches apart, which absorbs the imbalance between the 8x4 pixel blocks.
-    const int slot = warp * 8 + lane;      // valid for lane < 8
+    // TMA staging: every warp fetches SLOTS records of each sub-batch (lanes 0..SLOTS-1, one 48-byte
+    // bulk copy each; the dir3D word is not needed here), kAhead sub-batches ahead; thread 0 announces
+    // the byte count of the whole sub-batch to the buffer's `full` barrier.  No block-wide barrier in
+    // the loop: a warp only waits for the records (full) and, before refilling a buffer, for the
+    // slowest warp to have left it (empty) - with kRing buffers the warps of a tile may drift
+    // kRing - kAhead sub-batches apart, which absorbs the imbalance between the pixel blocks.
+    const int slot = warp * SLOTS + lane;      // valid for lane < SLOTS
     auto list_id = [&](int r) -> int {
         const int q = start - 1 - (r * kSub + slot);
-        return (lane < 8 && r < rounds && q >= 0) ? (int)__ldg(p.point_list + range.x + q) : -1;
+        return (lane < SLOTS && r < rounds && q >= 0) ? (int)__ldg(p.point_list + range.x + q) : -1;
     };
     auto stage = [&](int r, int id) {
         const int buf = r % kRing;
@@ -196,64 +231,85 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
                 bool keep = false;
                 // entry jj sits at list position q = start-1-(r*kSub+jj); only q < warp_last can matter
                 if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !EX_BLOCK_TEST(s[jj * 3], s[jj * 3 + 1], box);
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const unsigned m = __ballot_sync(full, keep);
                 if (keep) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
                 nw += __popc(m);
             }
             __syncwarp();
         }
+        // entry j of the sub-batch sits at list position q = start-1-(r*kSub+j):  q < last_contributor  <=>  j >= jthr
+        int jthr[PPT];
+#pragma unroll
+        for (int u = 0; u < PPT; u++) jthr[u] = start - r * kSub - last_contributor[u];
+        const unsigned sb = smem_u32(s);
 #pragma unroll 2
         for (int e = 0; e < nw; e++) {
             const int j = s_list[warp][e];
-            const int q = start - 1 - (r * kSub + j);
-            const float4 a = s[j * 3 + 0];
-            const float4 b = s[j * 3 + 1];
-            const float dx = fa(a.x, -pxf), dy = fa(a.y, -pyf);
-            const float power = ff(ff(dx, fm(dx, b.x), fm(fm(b.z, dy), dy)), -0.5f, -fm(fm(b.y, dx), dy));
-            bool contributes = (q < last_contributor) && !(power > 0.0f) && !(power < a.w);
-            float G = 0.f, alpha = 0.f;
-            if (contributes) {
-                G = expf(power);
-                alpha = fminf(0.99f, fm(b.w, G));
-                contributes = !(alpha < 1.0f / 255.0f);
+            const float4 a = lds128(sb + j * 48);
+            const float4 b = lds128(sb + j * 48 + 16);
+            float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
+            bool contributes[PPT];
+            bool any_c = false;
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                dx[u] = fa(a.x, -pxf[u]);
+                dy[u] = fa(a.y, -pyf[u]);
+                const float power = ff(ff(dx[u], fm(dx[u], b.x), fm(fm(b.z, dy[u]), dy[u])), -0.5f, -fm(fm(b.y, dx[u]), dy[u]));
+                contributes[u] = (j >= jthr[u]) && !(power > 0.0f) && !(power < a.w);
+                G[u] = 0.f; alpha[u] = 0.f;
+                if (contributes[u]) {
+                    G[u] = expf(power);
+                    alpha[u] = fminf(0.99f, fm(b.w, G[u]));
+                    contributes[u] = !(alpha[u] < 1.0f / 255.0f);
+                }
+                any_c |= contributes[u];
             }
-            if (!__any_sync(0xffffffffu, contributes)) continue;
-            const float4 c = s[j * 3 + 2];
+            if (!__any_sync(full, any_c)) continue;
+            const float4 c = lds128(sb + j * 48 + 32);
             float v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = 0.f;
-            if (contributes) {
-                const float inv1ma = 1.f / (1.f - alpha);
-                T = T * inv1ma;
-                const float w = alpha * T;               // dchannel_dcolor
-                float dL_dalpha = 0.0f;
-                const float dep = a.z;
-                if ((dep > p.min_depth) & (w > 0.0f)) {
-                    v[2] = dL_ddepth * w;
-                    dL_dalpha += (final_depth - dep) * dL_ddepth * T;
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                if (contributes[u]) {
+#if EX_BWD_FAST_RCP
+                    // 1 - alpha is in [0.01, 1]: MUFU.RCP (1 ulp) instead of the 12-instruction IEEE division
+                    float inv1ma;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.f - alpha[u]));
+#else
+                    const float inv1ma = 1.f / (1.f - alpha[u]);
+#endif
+                    T[u] = T[u] * inv1ma;
+                    const float w = alpha[u] * T[u];               // dchannel_dcolor
+                    float dL_dalpha = 0.0f;
+                    const float dep = a.z;
+                    if ((dep > p.min_depth) & (w > 0.0f)) {
+                        acc_to(v[2], dL_ddepth[u] * w, u);
+                        dL_dalpha += (final_depth[u] - dep) * dL_ddepth[u] * T[u];
+                    }
+                    accum_rec0[u] = last_alpha[u] * last_c0[u] + (1.f - last_alpha[u]) * accum_rec0[u];
+                    accum_rec1[u] = last_alpha[u] * last_c1[u] + (1.f - last_alpha[u]) * accum_rec1[u];
+                    accum_rec2[u] = last_alpha[u] * last_c2[u] + (1.f - last_alpha[u]) * accum_rec2[u];
+                    last_c0[u] = c.x; last_c1[u] = c.y; last_c2[u] = c.z;
+                    dL_dalpha += (c.x - accum_rec0[u]) * dpix0[u];
+                    dL_dalpha += (c.y - accum_rec1[u]) * dpix1[u];
+                    dL_dalpha += (c.z - accum_rec2[u]) * dpix2[u];
+                    acc_to(v[8], w * dpix0[u], u); acc_to(v[9], w * dpix1[u], u); acc_to(v[10], w * dpix2[u], u);
+                    acc_to(v[12], w * dflow0[u], u); acc_to(v[13], w * dflow1[u], u); acc_to(v[14], w * dflow2[u], u);
+                    dL_dalpha *= T[u];
+                    dL_dacc[u] *= T[u];
+                    last_alpha[u] = alpha[u];
+                    dL_dalpha += (-T_final[u] * inv1ma) * bg_dot_dpixel[u];
+                    // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
+                    const float gG = G[u] * (b.w * dL_dalpha);
+                    const float X = gG * dx[u], Y = gG * dy[u];
+                    acc_to(v[0], X * b.x + Y * b.y, u);
+                    acc_to(v[1], Y * b.z + X * b.y, u);
+                    acc_to(v[4], X * dx[u], u);
+                    acc_to(v[5], X * dy[u], u);
+                    acc_to(v[6], Y * dy[u], u);
+                    acc_to(v[3], G[u] * dL_dalpha + G[u] * dL_dacc[u], u);
                 }
-                accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
-                accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
-                accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
-                last_c0 = c.x; last_c1 = c.y; last_c2 = c.z;
-                dL_dalpha += (c.x - accum_rec0) * dpix0;
-                dL_dalpha += (c.y - accum_rec1) * dpix1;
-                dL_dalpha += (c.z - accum_rec2) * dpix2;
-                v[8] = w * dpix0; v[9] = w * dpix1; v[10] = w * dpix2;
-                v[12] = w * dflow0; v[13] = w * dflow1; v[14] = w * dflow2;
-                dL_dalpha *= T;
-                dL_dacc *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * inv1ma) * bg_dot_dpixel;
-                // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
-                const float gG = G * (b.w * dL_dalpha);
-                const float X = gG * dx, Y = gG * dy;
-                v[0] = X * b.x + Y * b.y;
-                v[1] = Y * b.z + X * b.y;
-                v[4] = X * dx;
-                v[5] = X * dy;
-                v[6] = Y * dy;
-                v[3] = G * dL_dalpha + G * dL_dacc;
             }
             const float tot = butterfly16(v, lane);
             // even lanes hold the 16 totals; 13 of them are real.  One warp-level reduction instruction:
@@ -273,5 +329,5 @@ __global__ void __launch_bounds__(256, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
     dim3 grid(grid_x, grid_y, 1);
-    render_bwd_kernel<<<grid, 256, 0, s>>>(p);
+    render_bwd_kernel<EX_BWD_PPT><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
 }
