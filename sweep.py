@@ -6,6 +6,9 @@ interpolation of the dynamic Gaussians at that timestamp, one kernel) + the rast
 Gaussians are replicated, no collective on the render path; the per-rank times are max-reduced.
 
     python sweep.py [--frames 300] [--workload C3]
+    python sweep.py --model-path <trained model dir> [--iteration -1] --duration 300 --interval 10 --time-pad 2
+        (row N3: the reference's point_cloud.ply + dynamic_point_cloud.ply loaded by ex4dgs_b200/model_io.py;
+         the camera stays the synthetic one - dataset readers are out of scope)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 sweep.py
 """
 from __future__ import annotations
@@ -27,6 +30,11 @@ def main():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--fused", type=int, default=1, help="1: fused front-end kernel, 0: PyTorch getters (synth.flat_inputs)")
+    ap.add_argument("--model-path", default=None, help="trained reference model directory (point_cloud/iteration_*/...)")
+    ap.add_argument("--iteration", type=int, default=-1)
+    ap.add_argument("--duration", type=float, default=300.0)
+    ap.add_argument("--interval", type=float, default=10.0)
+    ap.add_argument("--time-pad", type=float, default=2.0)
     args = ap.parse_args()
     rank, local_rank, ws = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
@@ -36,8 +44,27 @@ def main():
     import ex4dgs_b200 as m
     from ex4dgs_b200.frontend import interpolate_gaussians
 
-    sc = synth.make_config(args.workload)
+    sc = synth.make_config(args.workload if args.model_path is None else "C1")
     cam = sc.cam
+    if args.model_path is not None:
+        # swap the synthetic Gaussians for a trained model in the reference's on-disk format
+        import copy
+        from ex4dgs_b200 import model_io
+        ga, it = model_io.load_iteration(args.model_path, args.iteration, duration=args.duration, interval=args.interval,
+                                         time_pad=args.time_pad)
+        sc = copy.copy(sc)
+        cam = copy.copy(cam)
+        cam.W, cam.H = 1352, 1014
+        cam.tanfovx, cam.tanfovy = cam.W / (2 * 1462.0), cam.H / (2 * 1462.0)
+        for dst, src in (("xyz", "_xyz"), ("xyz_disp", "_xyz_disp"), ("rotation", "_rotation"), ("scaling", "_scaling"),
+                         ("opacity", "_opacity"), ("xyz_motion", "_xyz_motion"), ("rotation_motion", "_rotation_motion"),
+                         ("scaling_motion", "_scaling_motion"), ("opacity_motion", "_opacity_motion"),
+                         ("opacity_center", "_opacity_duration_center"), ("opacity_var", "_opacity_duration_var")):
+            setattr(sc, dst, getattr(ga, src))
+        sc.features = torch.cat((ga._features_dc, ga._features_rest), dim=1)
+        sc.features_motion = torch.cat((ga._features_dc_motion, ga._features_rest_motion), dim=1)
+        sc.duration, sc.interval, sc.time_shift, sc.var_pad = ga.duration, ga.interval, ga.time_shift, ga.var_pad
+        sc.cam = cam
     names = ["xyz", "xyz_disp", "rotation", "scaling", "opacity", "xyz_motion", "rotation_motion", "scaling_motion",
              "opacity_motion", "opacity_center", "opacity_var"]
     T = {n: getattr(sc, n).to(dev) for n in names}
