@@ -235,6 +235,106 @@ def make_train_step(frame: Frame, ref_loss, lambda_dssim=0.2):
         frame._zero()
     return step
 
+# learning rates of arguments/__init__.py:93-110 (OptimizationParams defaults), in the group order of
+# scene/c_gaussian_model.py:430-449
+MODEL_GROUPS = [("xyz", 1.6e-4), ("f_dc", 2.5e-3), ("f_rest", 2.5e-3 / 20), ("opacity", 0.05), ("scaling", 0.005),
+                ("rotation", 1e-5), ("xyz_disp", 1e-4), ("motion_xyz", 1.6e-4), ("motion_f_dc", 2.5e-3),
+                ("motion_f_rest", 2.5e-3 / 20), ("motion_scaling", 0.005), ("motion_opacity", 0.05),
+                ("motion_opacity_center", 1e-3), ("motion_opacity_var", 5e-4), ("motion_rotation", 1e-3)]
+LR_SCALE = 1e-3     # keeps the synthetic scene stationary over the timed steps; RAdam's work is lr-independent
+
+
+def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_dssim=0.2):
+    """One full training iteration on the MODEL's native parameters (train.py:124-251 minus
+    densification): per-frame getters (fused front-end kernel, row N1 / the PyTorch getters of
+    scene/c_gaussian_model.py:170-215,330-375 restated in synth.py), get_features' torch.cat, render,
+    loss block (row N2 / utils/loss_utils.py), backward down to the 15 parameter tensors,
+    optimizer.step() (FusedRAdam, row N4 / torch.optim.RAdam) and zero_grad(set_to_none=True)."""
+    import copy
+    sc, dev = frame.sc, frame.dev
+    m = copy.copy(sc)
+
+    def par(t):
+        return torch.nn.Parameter(t.detach().to(dev).float().contiguous().clone())
+
+    raw = ["xyz", "xyz_disp", "rotation", "scaling", "opacity", "xyz_motion", "rotation_motion", "scaling_motion",
+           "opacity_motion", "opacity_center", "opacity_var"]
+    for n in raw:
+        setattr(m, n, par(getattr(sc, n)))
+    f_dc, f_rest = par(sc.features[:, :1]), par(sc.features[:, 1:])
+    f_dc_m, f_rest_m = par(sc.features_motion[:, :1]), par(sc.features_motion[:, 1:])
+    by_name = {"xyz": m.xyz, "f_dc": f_dc, "f_rest": f_rest, "opacity": m.opacity, "scaling": m.scaling,
+               "rotation": m.rotation, "xyz_disp": m.xyz_disp, "motion_xyz": m.xyz_motion, "motion_f_dc": f_dc_m,
+               "motion_f_rest": f_rest_m, "motion_scaling": m.scaling_motion, "motion_opacity": m.opacity_motion,
+               "motion_opacity_center": m.opacity_center, "motion_opacity_var": m.opacity_var,
+               "motion_rotation": m.rotation_motion}
+    groups = [{"params": [by_name[n]], "lr": lr * LR_SCALE, "name": n} for n, lr in MODEL_GROUPS]
+    params = [g["params"][0] for g in groups]
+    if impl == "ours":
+        from ex4dgs_b200.frontend import interpolate_gaussians
+        from ex4dgs_b200.loss import photometric_loss
+        from ex4dgs_b200.optim import FusedRAdam, allreduce_gradients
+        opt = FusedRAdam(groups, lr=0.001)
+    else:
+        opt = torch.optim.RAdam(groups, lr=0.001)
+    P = sc.xyz.shape[0] + sc.xyz_motion.shape[0]
+    n_param = sum(p.numel() for p in params)
+
+    def step(group=None):
+        main = torch.cuda.current_stream(dev)
+        frame.d_cam.copy_(frame.h_cam, non_blocking=True)
+        frame.copy_stream.wait_stream(main)
+        with torch.cuda.stream(frame.copy_stream):
+            frame.d_gt.copy_(frame.h_gt, non_blocking=True)
+        c = frame.d_cam
+        rs = frame.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
+        # get_features (c_gaussian_model.py:337-353): cat(dc, rest) per kind, then static + dynamic
+        shs = torch.cat([torch.cat([f_dc, f_rest], dim=1), torch.cat([f_dc_m, f_rest_m], dim=1)], dim=0)
+        if impl == "ours":
+            means, rots, scales, opac = interpolate_gaussians(
+                m.xyz, m.xyz_disp, m.rotation, m.scaling, m.opacity, m.xyz_motion, m.rotation_motion, m.scaling_motion,
+                m.opacity_motion, m.opacity_center, m.opacity_var, t=sc.timestamp, duration=sc.duration,
+                interval=sc.interval, time_shift=sc.time_shift, var_min=sc.var_pad / sc.interval)
+        else:
+            means, rots, scales, opac = synth.model_getters(m)
+        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)     # gaussian_renderer/__init__.py:28
+        flow_in = torch.zeros(P, 3, device=dev, requires_grad=True)      # :66
+        image, radii, depth, flow, acc, idxs = frame.mod.GaussianRasterizer(rs)(
+            means3D=means, means2D=means2D, dir3D=flow_in, opacities=opac, shs=shs, scales=scales, rotations=rots)
+        main.wait_stream(frame.copy_stream)
+        gt_image = frame.d_gt
+        if impl == "ours":
+            loss, Ll1, _, l1_errors, ssim_errors = photometric_loss(image, gt_image, lambda_dssim)
+        else:
+            Ll1 = ref_loss.l1_loss(image, gt_image)
+            loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ref_loss.ssim(image, gt_image))
+            l1_errors = (image - gt_image).abs().mean(dim=0)
+            ssim_errors = ref_loss.ssim(image, gt_image, reduce=False).mean(dim=0)
+        hook_tensor = torch.stack([acc[0], l1_errors, ssim_errors])
+        flow_h = flow.register_hook(lambda grad: hook_tensor)
+        loss = loss + flow.mean() * 0
+        loss.backward()
+        flow_h.remove()
+        scale = 1.0
+        if dp_grads and group is not None:
+            if impl == "ours":
+                scale = allreduce_gradients(params, group)
+            else:
+                ws = torch.distributed.get_world_size(group)
+                for p in params:
+                    torch.distributed.all_reduce(p.grad, group=group)
+                    p.grad /= ws
+        if impl == "ours":
+            opt.step(grad_scale=scale)
+        else:
+            opt.step()
+        opt.zero_grad(set_to_none=True)
+        l = loss.detach().reshape(1)
+        if group is not None:
+            torch.distributed.all_reduce(l)
+        frame.h_loss.copy_(l, non_blocking=True)
+    return step, n_param
+
 
 def frame_stats(frame: Frame):
     """R, P_vis and R_eff = sum_tiles min(range_len, 256*batches fetched) from the scratch buffers."""
@@ -296,6 +396,10 @@ def main():
                     help="forward-only render under no_grad (BASELINE.json config 2); changes the metric name")
     ap.add_argument("--profile-in-timed", type=int, default=1,
                     help="record per-stage CUDA events inside the timed region (1) or in a separate pass (0)")
+    ap.add_argument("--no-train-iter", action="store_true", help="skip the full-training-iteration leg")
+    ap.add_argument("--only-train-iter", action="store_true", help="profiling aid: run only the train_iter leg")
+    ap.add_argument("--dp-grads", action="store_true",
+                    help="train_iter leg under torchrun: SUM all-reduce of all gradients before the optimizer step")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
     args = ap.parse_args()
     rank, local_rank, ws = dist_env()
@@ -367,6 +471,21 @@ def main():
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
+    if args.only_train_iter:
+        # profiling aid (ncu launch lists): nothing but the full-training-iteration leg
+        rl = None
+        if args.impl != "ours":
+            rl = load_reference_loss()
+        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", rl, args.dp_grads)
+        for _ in range(W):
+            model_step(group)
+        ms_iter, _, _ = timed(lambda: model_step(group), K)
+        if rank == 0:
+            print(json.dumps({"train_iter_ms": ms_iter / K, "steps": K, "parameters": n_param, "impl": args.impl}), flush=True)
+        if ws > 1:
+            torch.distributed.destroy_process_group()
+        return
+
     # warm-up: W steps of each leg, then keep going until the clocks have ramped (~1 s of work)
     for _ in range(W):
         frame.step_device()
@@ -407,8 +526,8 @@ def main():
 
     # training-iteration leg (row N2): the same step with the reference's loss block, train.py:144-151
     train = None
+    ref_loss = None
     if not args.fwd_only:
-        ref_loss = None
         if args.impl != "ours":
             ref_loss = load_reference_loss()
             if ref_loss is None:                       # restated in float32 torch ops by the oracle
@@ -430,6 +549,21 @@ def main():
                          + ("fused loss kernels (ex4dgs_b200/loss.py)" if args.impl == "ours" else
                             "the reference's utils/loss_utils.py (torch conv2d)")}
 
+    # full training iteration on the model's native parameters (rows N1 + N2 + N4 around the path)
+    train_iter = None
+    if not args.fwd_only and not args.no_train_iter:
+        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", ref_loss, args.dp_grads)
+        for _ in range(W):
+            model_step(group)
+        Kt = max(20, K // 3)
+        ms_iter, _, _ = timed(lambda: model_step(group), Kt)
+        train_iter = {"value": ws * Kt / (ms_iter / 1000.0), "unit": "iterations/s", "ms_per_step": ms_iter / Kt, "steps": Kt,
+                      "parameters": n_param, "lr_scale": LR_SCALE, "gradient_allreduce": bool(args.dp_grads and ws > 1),
+                      "what": "train.py iteration without densification on the 15 native parameter tensors: per-frame getters, "
+                              "get_features cat, render, loss block, backward to the parameters, RAdam step, zero_grad; "
+                              + ("fused front-end + fused loss + FusedRAdam (one kernel each)" if args.impl == "ours" else
+                                 "PyTorch getters + utils/loss_utils.py + torch.optim.RAdam (foreach)")}
+
     value = ws * K / (ms_total / 1000.0)
     e2e_value = ws * K / (ms_e2e / 1000.0)
     if rank != 0:
@@ -448,6 +582,8 @@ def main():
             "clocks": clocks}
     if train is not None:
         line["train_step"] = train
+    if train_iter is not None:
+        line["train_iter"] = train_iter
     if args.impl == "ours":
         st = frame_stats(frame)
         peaks = {}
@@ -474,8 +610,18 @@ def main():
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[3],
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                             "note": "the kernel is instruction-issue-bound (ncu: ~84 % issue slots, ~4 % DRAM): see profiles/SUMMARY.md"}
-        line["stage_ms"] = dict(zip(["preprocess_fwd", "depth_sort_scan", "sync_duplicate_tilesort_ranges", "render_fwd",
-                                     "render_bwd", "preprocess_bwd"], stage_ms))
+        names = ["preprocess_fwd", "depth_sort_scan", "sync_duplicate_tilesort_ranges", "render_fwd", "render_bwd", "preprocess_bwd"]
+        line["stage_ms"] = dict(zip(names, stage_ms))
+        # algorithmic bytes per stage (with this design's record sizes) against the same HBM peak
+        Pn, Pv, Rn, Re, px = frame.P, st["P_vis"], st["R"], st["R_eff"], cam.W * cam.H
+        stage_bytes = [20 * Pn + 291 * Pv,                       # means + always-written words; visible: inputs + 64 B record
+                       (2 * 8 * 4 + 8) * Pn,                     # 4 radix passes over (u32 key, u32 value) + the scan
+                       8 * Pn + 12 * Pv + 6 * Rn + (2 * 6 * 2 + 2) * Rn + 2 * Rn + 8 * st["tiles"],   # duplicate, 2 passes of (u16, u32), ranges
+                       alg_bytes,
+                       44 * Re + 56 * px + 56 * Pv,              # staged records, per-pixel inputs, gradient read-modify-write
+                       579 * Pv + 156 * Pn]                      # inputs + accumulator of visible, dense zero-filled outputs
+        line["stage_roofline"] = {n: {"algorithmic_bytes": int(b), "GBps": b / (ms * 1e-3) / 1e9, "frac": b / (ms * 1e-3) / 1e9 / peak}
+                                  for n, b, ms in zip(names, stage_bytes, stage_ms) if ms > 0}
         if not args.no_cpu_baseline and ws == 1:
             line["cpu_baseline"] = cpu_oracle_baseline(sc)
     else:

@@ -21,6 +21,12 @@ _I = C.c_int
 _D = C.c_double
 
 
+class RAdamTensor(C.Structure):
+    """ex4dgs_radam_tensor (include/ex4dgs_raster.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_size_t), ("lr", C.c_double), ("step", C.c_longlong)]
+
+
 class ArrayDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("buffer", C.c_int), ("offset", C.c_size_t),
                 ("elem_size", C.c_size_t), ("count", C.c_size_t)]
@@ -71,6 +77,8 @@ SIGNATURES = {
                                       _P, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _P,
                                       _P]),
+    "ex4dgs_radam_step": (_I, [C.POINTER(RAdamTensor), _I, _D, _D, _D, _D, _P]),
+    "ex4dgs_radam_scalars": (_I, [_D, C.c_longlong, _D, _D, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
     "ex4dgs_loss_scratch_bytes": (C.c_size_t, [_I, _I]),
     "ex4dgs_loss_forward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "ex4dgs_loss_backward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P]),

@@ -486,4 +486,52 @@ int ex4dgs_loss_backward(int width, int height, const float* image, const float*
     return EX4DGS_OK;
 }
 
+// per-tensor scalars in double, expression for expression as torch/optim/radam.py (_multi_tensor_radam)
+static void radam_scalars(double lr, double step, double beta1, double beta2, float* S, float* U, int* rectified)
+{
+    const double rho_inf = 2.0 / (1.0 - beta2) - 1.0;
+    const double b2t = pow(beta2, step);
+    const double rho_t = rho_inf - 2.0 * step * b2t / (1.0 - b2t);
+    const double rect = rho_t > 5.0 ? sqrt((rho_t - 4.0) * (rho_t - 2.0) * rho_inf / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t)) : 0.0;
+    const double unrectified = rect > 0.0 ? 0.0 : 1.0;
+    const double bc1 = 1.0 - pow(beta1, step);
+    *U = (float)((lr * unrectified / bc1) * -1.0);
+    *S = (float)(sqrt(1.0 - b2t) * (lr * rect / bc1) * -1.0);
+    *rectified = rect > 0.0;
+}
+
+int ex4dgs_radam_scalars(double lr, long long step, double beta1, double beta2, float* S, float* U, int* rectified)
+{
+    if (step < 1 || !S || !U || !rectified) return EX4DGS_ERR_INVALID;
+    radam_scalars(lr, (double)step, beta1, beta2, S, U, rectified);
+    return EX4DGS_OK;
+}
+
+int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                      double grad_scale, void* stream)
+{
+    g_err[0] = 0;
+    if (n < 0 || n > EX4DGS_RADAM_MAX_TENSORS || (n > 0 && !tensors))
+        return fail(EX4DGS_ERR_INVALID, "radam_step: n=%d outside [0, %d]", n, EX4DGS_RADAM_MAX_TENSORS);
+    if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0))
+        return fail(EX4DGS_ERR_INVALID, "radam_step: bad hyper-parameters beta1=%g beta2=%g eps=%g", beta1, beta2, eps);
+    RAdamTensorDesc d[EX_OPT_MAX_TENSORS];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const ex4dgs_radam_tensor& t = tensors[i];
+        if (t.numel == 0) continue;
+        if (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq) return fail(EX4DGS_ERR_INVALID, "radam_step: tensor %d has a NULL pointer", i);
+        if (t.step < 1) return fail(EX4DGS_ERR_INVALID, "radam_step: tensor %d step=%lld (must be >= 1)", i, t.step);
+        d[m].param = t.param; d[m].grad = t.grad; d[m].exp_avg = t.exp_avg; d[m].exp_avg_sq = t.exp_avg_sq;
+        d[m].numel = t.numel;
+        radam_scalars(t.lr, (double)t.step, beta1, beta2, &d[m].S, &d[m].U, &d[m].rectified);
+        d[m].aligned = 0;
+        m++;
+    }
+    cudaError_t e = launch_radam(d, m, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "radam_step: %s", cudaGetErrorString(e));
+    if (m > 0) g_launches += 1;
+    return EX4DGS_OK;
+}
+
 }  // extern "C"

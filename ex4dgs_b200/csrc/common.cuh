@@ -230,6 +230,22 @@ cudaError_t launch_loss_forward(int W, int H, const float* img, const float* gt,
 cudaError_t launch_loss_backward(int W, int H, const float* img, const float* gt, float lambda, const char* scratch,
                                  const float* dL_dloss, float* dL_dimg, cudaStream_t stream);
 
+// fused RAdam step (optim.cu)
+#define EX_OPT_MAX_TENSORS 32
+struct RAdamTensorDesc {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    size_t numel;
+    float S;            // -sqrt(1 - beta2^t) * lr * rect / (1 - beta1^t)
+    float U;            // -lr / (1 - beta1^t) while the variance is not tractable (rho_t <= 5), else 0
+    int rectified;      // rho_t > 5
+    int aligned;        // all four pointers 16-byte aligned (filled by the launcher)
+};
+cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, double beta2, double eps, double grad_scale,
+                         cudaStream_t s);
+
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
 size_t binning_stage1_temp_bytes(int P);
 size_t binning_stage2_temp_bytes(int R);

@@ -1,0 +1,98 @@
+"""Fused optimizer step.
+
+`FusedRAdam` is a drop-in for the optimizer the reference builds in CGaussianModel.training_setup
+(`torch.optim.RAdam(l, lr=0.001)` over 15 named single-tensor groups, scene/c_gaussian_model.py:430-449)
+and steps once per iteration (train.py:250-251): same constructor arguments, same `param_groups`
+(the reference rewrites `group['lr']` per iteration, :461-470, and swaps `group['params'][0]` when it
+densifies/prunes, :674-760), same `state[p] = {'step', 'exp_avg', 'exp_avg_sq'}` layout and therefore
+the same `state_dict()` - a checkpoint written with one loads into the other.  `step()` is ONE CUDA
+kernel for all tensors (csrc/optim.cu) instead of torch's nine foreach passes.  CUDA only.
+
+`allreduce_gradients` is the data-parallel exchange the reference lacks (it is single-GPU): a SUM
+all-reduce of every gradient over the process group (NCCL on GPUs); the division by the world size is
+folded into the optimizer kernel (`grad_scale`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class FusedRAdam(torch.optim.Optimizer):
+    """torch.optim.RAdam semantics (betas, eps; weight_decay must be 0 as in the reference), one fused launch."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: %r" % (lr,))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: %r" % (eps,))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: %r" % (betas[0],))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: %r" % (betas[1],))
+        if weight_decay != 0.0:
+            raise ValueError("FusedRAdam implements weight_decay = 0 (what the reference uses)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        # groups may differ in betas/eps: one launch per distinct (beta1, beta2, eps); the reference has one
+        batches = {}
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError("RAdam does not support sparse gradients")
+                if not p.is_cuda:
+                    raise RuntimeError("ex4dgs_b200: FusedRAdam is CUDA-only")
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedRAdam needs contiguous float32 parameters")
+                st = self.state[p]
+                if len(st) == 0:            # torch/optim/radam.py _init_group
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad if (p.grad.dtype == torch.float32 and p.grad.is_contiguous()) else p.grad.float().contiguous()
+                batches.setdefault((float(beta1), float(beta2), float(group["eps"]), p.device), []).append(
+                    (p, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), int(st["step"].item())))
+        for (beta1, beta2, eps, dev), items in batches.items():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(0, len(items), 32):
+                chunk = items[i:i + 32]
+                arr = (_lib.RAdamTensor * len(chunk))()
+                for a, (p, g, m, v, lr, step) in zip(arr, chunk):
+                    a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+                    a.numel, a.lr, a.step = p.numel(), lr, step
+                with torch.cuda.device(dev):
+                    rc = lib.ex4dgs_radam_step(arr, len(chunk), beta1, beta2, eps, float(grad_scale), C.c_void_p(stream))
+                if rc < 0:
+                    raise RuntimeError("ex4dgs_radam_step failed (%d): %s" % (rc, _lib.last_error()))
+        return loss
+
+
+def allreduce_gradients(params: Iterable[torch.Tensor], group: Optional[dist.ProcessGroup] = None) -> float:
+    """SUM all-reduce of every `.grad` (asynchronously issued, then waited).  Returns the factor
+    1/world_size to hand to FusedRAdam.step(grad_scale=...) so that the update uses the mean gradient.
+    Identity (returns 1.0) when torch.distributed is not initialised."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    works = []
+    for p in params:
+        if p.grad is not None:
+            works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return 1.0 / dist.get_world_size(group)

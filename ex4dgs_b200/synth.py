@@ -229,8 +229,9 @@ def frame_indices(sc: Scene, t: Optional[float] = None):
     return k, d
 
 
-def flat_inputs(sc: Scene, t: Optional[float] = None) -> Dict[str, torch.Tensor]:
-    """What gaussian_renderer/__init__.py:62-95 hands to the rasterizer: static first, then dynamic."""
+def model_getters(sc, t: Optional[float] = None):
+    """get_xyz_at_t / get_rotation_at_t / get_scaling / get_opacity_at_t of CGaussianModel
+    (scene/c_gaussian_model.py:170-215,330-375) in plain differentiable PyTorch: static first, then dynamic."""
     t = sc.timestamp if t is None else t
     k, d = frame_indices(sc, t)
     nd = sc.xyz_motion.shape[0]
@@ -245,10 +246,19 @@ def flat_inputs(sc: Scene, t: Optional[float] = None) -> Dict[str, torch.Tensor]
         rots = torch.cat([sc.rotation, rot_d]).contiguous()
         opac = torch.cat([torch.sigmoid(sc.opacity), op_d]).contiguous()
         scales = torch.exp(torch.cat([sc.scaling, sc.scaling_motion])).contiguous()
-        shs = torch.cat([sc.features, sc.features_motion]).contiguous()
     else:
         means, rots, opac = means_s.contiguous(), sc.rotation, torch.sigmoid(sc.opacity)
-        scales, shs = torch.exp(sc.scaling), sc.features
+        scales = torch.exp(sc.scaling)
+    return means, rots, scales, opac
+
+
+def flat_inputs(sc: Scene, t: Optional[float] = None) -> Dict[str, torch.Tensor]:
+    """What gaussian_renderer/__init__.py:62-95 hands to the rasterizer: static first, then dynamic."""
+    means, rots, scales, opac = model_getters(sc, t)
+    if sc.xyz_motion.shape[0]:
+        shs = torch.cat([sc.features, sc.features_motion]).contiguous()
+    else:
+        shs = sc.features
     P = means.shape[0]
     if getattr(sc, "_dir_nonzero", False):
         g = torch.Generator().manual_seed(getattr(sc, "_seed", SEED) + 1)

@@ -223,6 +223,32 @@ int ex4dgs_loss_forward(int width, int height, const float* image, const float* 
 int ex4dgs_loss_backward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
                          const char* scratch, const float* dL_dloss, float* dL_dimage, void* stream);
 
+/* ---- optimizer step ------------------------------------------------
+ * Replaces `gaussians.optimizer.step()` of the reference's training iteration (train.py:250): the
+ * optimizer is torch.optim.RAdam(l, lr=0.001) over 15 single-tensor parameter groups with per-group
+ * learning rates (scene/c_gaussian_model.py:430-449; betas (0.9, 0.999), eps 1e-8, weight_decay 0).
+ * One launch updates every tensor of the table: param/exp_avg/exp_avg_sq in place, following the
+ * arithmetic of torch's CUDA ("foreach") RAdam operation by operation.
+ *   step        the tensor's step count AFTER this update (state['step'] + 1), >= 1
+ *   grad_scale  multiplies every gradient first (1/world_size after a SUM all-reduce; 1 otherwise)
+ * At most EX4DGS_RADAM_MAX_TENSORS tensors per call.  All pointers: device float, `numel` elements. */
+#define EX4DGS_RADAM_MAX_TENSORS 32
+typedef struct ex4dgs_radam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    size_t numel;
+    double lr;
+    long long step;
+} ex4dgs_radam_tensor;
+int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                      double grad_scale, void* stream);
+/* Host-only helper (no GPU needed): the two per-tensor scalars the kernel receives for step `step`,
+ * p += m * (rectified ? 1 / ((sqrt(v) + eps) / S) : U)  - exposed so the CPU tests can pin them against
+ * torch/optim/radam.py's expressions. */
+int ex4dgs_radam_scalars(double lr, long long step, double beta1, double beta2, float* S, float* U, int* rectified);
+
 /* ---- introspection (used by the parity tests to look inside the opaque scratch buffers) ------- */
 typedef struct ex4dgs_array_desc {
     const char* name;    /* e.g. "point_list"                                  */

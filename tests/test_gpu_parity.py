@@ -310,3 +310,53 @@ def test_bit_exact_stress_against_reference(built, seed):
     vis = b["radii"] > 0
     assert np.array_equal(a["inter"]["conic_opacity"][vis].view(np.uint32), b["inter"]["conic_opacity"][vis].view(np.uint32))
     assert np.array_equal(a["inter"]["rgb"][vis].view(np.uint32), b["inter"]["rgb"][vis].view(np.uint32))
+
+
+def test_flow_free_forward_equals_general_kernel(built, cull):
+    """dir3D all +-0 (what gaussian_renderer/__init__.py:66 always passes) selects the compositing kernel
+    without flow accumulators; a single non-zero component on a VISIBLE Gaussian selects the general one.
+    Every non-flow output and internal list must be bit-identical between the two, the flow image must be
+    exactly +0 in the first case, and a non-zero dir3D on a culled Gaussian must not switch kernels' results."""
+    mod = U.ours_module()
+    dev = "cuda"
+    sc = synth.make_config("C1")
+    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    P = inp["means3D"].shape[0]
+    rs = U.settings_for(mod, sc, dev)
+
+    def run(dir3D):
+        with torch.no_grad():
+            return [t.clone() for t in mod.GaussianRasterizer(rs)(
+                means3D=inp["means3D"], means2D=torch.zeros(P, 3, device=dev), dir3D=dir3D, opacities=inp["opacities"],
+                shs=inp["shs"], scales=inp["scales"], rotations=inp["rotations"])]
+
+    z = torch.zeros(P, 3, device=dev)
+    base = run(z)
+    radii = base[1]
+    assert float(base[3].abs().max()) == 0.0 and not torch.signbit(base[3]).any()
+    vis = int(torch.nonzero(radii > 0)[0])
+    hid = int(torch.nonzero(radii == 0)[0])
+    neg = z.clone()
+    neg[::3] = -0.0                                             # negative zeros still count as "no flow"
+    a = run(neg)
+    one = z.clone()
+    one[vis, 1] = 0.75                                          # general kernel
+    b = run(one)
+    hidden = z.clone()
+    hidden[hid] = torch.tensor([1.0, float("nan"), 2.0])        # culled Gaussian: contributes nothing
+    c = run(hidden)
+    for other in (a, b, c):
+        for i in (0, 1, 2, 4, 5):                               # color, radii, depth, acc, idxs
+            assert torch.equal(base[i], other[i]), i
+    assert float(a[3].abs().max()) == 0.0 and float(c[3].abs().max()) == 0.0
+    assert float(b[3].abs().max()) > 0.0
+    # and the general kernel agrees with the CPU oracle on that flow image
+    sc2 = synth.make_config("C1")
+    ref = U.oracle_module()
+    rso = U.settings_for(ref, sc2, "cpu")
+    inc = synth.flat_inputs(sc2)
+    with torch.no_grad():
+        fo = ref.GaussianRasterizer(rso)(means3D=inc["means3D"], means2D=torch.zeros(P, 3), dir3D=one.cpu(),
+                                         opacities=inc["opacities"], shs=inc["shs"], scales=inc["scales"],
+                                         rotations=inc["rotations"])[3]
+    assert float((fo - b[3].cpu()).abs().max()) <= 1e-5
