@@ -274,6 +274,7 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
         from ex4dgs_b200.frontend import interpolate_gaussians
         from ex4dgs_b200.loss import photometric_loss
         from ex4dgs_b200.optim import FusedRAdam, allreduce_gradients
+        from ex4dgs_b200.rasterizer import SegmentedSH
         opt = FusedRAdam(groups, lr=0.001)
     else:
         opt = torch.optim.RAdam(groups, lr=0.001)
@@ -288,8 +289,11 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
             frame.d_gt.copy_(frame.h_gt, non_blocking=True)
         c = frame.d_cam
         rs = frame.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
-        # get_features (c_gaussian_model.py:337-353): cat(dc, rest) per kind, then static + dynamic
-        shs = torch.cat([torch.cat([f_dc, f_rest], dim=1), torch.cat([f_dc_m, f_rest_m], dim=1)], dim=0)
+        if impl == "ours":
+            shs = SegmentedSH(f_dc, f_rest, f_dc_m, f_rest_m)       # the four tensors read in place, no cat
+        else:
+            # get_features (c_gaussian_model.py:337-353): cat(dc, rest) per kind, then static + dynamic
+            shs = torch.cat([torch.cat([f_dc, f_rest], dim=1), torch.cat([f_dc_m, f_rest_m], dim=1)], dim=0)
         if impl == "ours":
             means, rots, scales, opac = interpolate_gaussians(
                 m.xyz, m.xyz_disp, m.rotation, m.scaling, m.opacity, m.xyz_motion, m.rotation_motion, m.scaling_motion,
@@ -560,9 +564,10 @@ def main():
         train_iter = {"value": ws * Kt / (ms_iter / 1000.0), "unit": "iterations/s", "ms_per_step": ms_iter / Kt, "steps": Kt,
                       "parameters": n_param, "lr_scale": LR_SCALE, "gradient_allreduce": bool(args.dp_grads and ws > 1),
                       "what": "train.py iteration without densification on the 15 native parameter tensors: per-frame getters, "
-                              "get_features cat, render, loss block, backward to the parameters, RAdam step, zero_grad; "
-                              + ("fused front-end + fused loss + FusedRAdam (one kernel each)" if args.impl == "ours" else
-                                 "PyTorch getters + utils/loss_utils.py + torch.optim.RAdam (foreach)")}
+                              "get_features, render, loss block, backward to the parameters, RAdam step, zero_grad; "
+                              + ("fused front-end + segmented SH input (no torch.cat) + fused loss + FusedRAdam (one kernel each)"
+                                 if args.impl == "ours" else
+                                 "PyTorch getters + get_features torch.cat + utils/loss_utils.py + torch.optim.RAdam (foreach)")}
 
     value = ws * K / (ms_total / 1000.0)
     e2e_value = ws * K / (ms_e2e / 1000.0)

@@ -14,11 +14,18 @@ LIB_PATH = os.environ.get("EX4DGS_LIB") or os.path.join(HERE, "libex4dgs_raster.
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 FLAG_TILE_CULL = 1
+FLAG_SH_SEGMENTED = 2
 
 _F = C.c_float
 _P = C.c_void_p
 _I = C.c_int
 _D = C.c_double
+
+
+class ShSegments(C.Structure):
+    """ex4dgs_sh_segments (include/ex4dgs_raster.h)."""
+    _fields_ = [("n_static", C.c_int), ("dc_static", C.c_void_p), ("rest_static", C.c_void_p),
+                ("dc_dynamic", C.c_void_p), ("rest_dynamic", C.c_void_p)]
 
 
 class RAdamTensor(C.Structure):

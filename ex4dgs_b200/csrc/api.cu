@@ -220,6 +220,23 @@ int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_de
     return count;
 }
 
+// EX4DGS_FLAG_SH_SEGMENTED: `ptr` is a host ex4dgs_sh_segments; returns EX4DGS_OK or the (already recorded) error
+static int read_segments(const float* ptr, int P, int M, ShSegments* out, const char* what)
+{
+    memset(out, 0, sizeof(*out));
+    const ex4dgs_sh_segments* h = reinterpret_cast<const ex4dgs_sh_segments*>(ptr);
+    if (!h) return fail(EX4DGS_ERR_INVALID, "%s: NULL ex4dgs_sh_segments", what);
+    if (M != 16) return fail(EX4DGS_ERR_UNSUPPORTED, "%s: segmented SH needs M = 16 coefficients, got %d", what, M);
+    if (h->n_static < 0 || h->n_static > P) return fail(EX4DGS_ERR_INVALID, "%s: n_static=%d outside [0, %d]", what, h->n_static, P);
+    if ((h->n_static > 0 && (!h->dc_static || !h->rest_static)) || (h->n_static < P && (!h->dc_dynamic || !h->rest_dynamic)))
+        return fail(EX4DGS_ERR_INVALID, "%s: a non-empty SH segment has a NULL pointer", what);
+    out->enabled = 1;
+    out->n_static = h->n_static;
+    out->dc[0] = h->dc_static; out->rest[0] = h->rest_static;
+    out->dc[1] = h->dc_dynamic; out->rest[1] = h->rest_dynamic;
+    return EX4DGS_OK;
+}
+
 static void* align256(void* p) { return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
 
 int ex4dgs_forward(
@@ -295,6 +312,11 @@ int ex4dgs_forward(
         pp.P = P; pp.D = D; pp.M = M;
         pp.means3D = means3D; pp.dir3D = dir3D; pp.scales = scales; pp.rotations = rotations;
         pp.opacities = opacities; pp.shs = shs; pp.cov3D_precomp = cov3D_precomp; pp.colors_precomp = colors_precomp;
+        if ((flags & EX4DGS_FLAG_SH_SEGMENTED) && shs != nullptr) {
+            const int rc = read_segments(shs, P, M, &pp.seg, "forward");
+            if (rc < 0) return rc;
+            pp.shs = nullptr;
+        }
         pp.scale_modifier = scale_modifier;
         pp.W = width; pp.H = height;
         pp.tan_fovx = tan_fovx; pp.tan_fovy = tan_fovy;
@@ -425,6 +447,15 @@ int ex4dgs_backward(
 
     bp.P = P; bp.D = D; bp.M = M;
     bp.means3D = means3D; bp.scales = scales; bp.rotations = rotations; bp.shs = shs;
+    if ((flags & EX4DGS_FLAG_SH_SEGMENTED) && shs != nullptr) {
+        int rc = read_segments(shs, P, M, &bp.seg, "backward");
+        if (rc < 0) return rc;
+        rc = read_segments(dL_dsh, P, M, &bp.dseg, "backward (dL_dsh)");
+        if (rc < 0) return rc;
+        if (bp.dseg.n_static != bp.seg.n_static) return fail(EX4DGS_ERR_INVALID, "backward: dL_dsh segments differ from the inputs'");
+        bp.shs = nullptr;
+        dL_dsh = nullptr;
+    }
     bp.cov3D_precomp = cov3D_precomp; bp.colors_precomp = colors_precomp;
     bp.scale_modifier = scale_modifier;
     bp.tan_fovx = tan_fovx; bp.tan_fovy = tan_fovy;

@@ -133,6 +133,15 @@ BinningState carve_binning(void* base, int R, size_t temp_bytes);
 ImageState carve_image(void* base, int width, int height);
 
 // ---- kernel parameter blocks ---------------------------------------------------------------------
+// SH coefficients kept in the model's four tensors (EX4DGS_FLAG_SH_SEGMENTED): index 0 = static
+// Gaussians [0, n_static), 1 = dynamic; dc [n,1,3], rest [n,15,3].  enabled = 0: plain [P,M,3] array.
+struct ShSegments {
+    int enabled;
+    int n_static;
+    float* dc[2];
+    float* rest[2];
+};
+
 struct PreprocessParams {
     int P, D, M;
     const float* means3D;
@@ -141,6 +150,7 @@ struct PreprocessParams {
     const float* rotations;
     const float* opacities;
     const float* shs;
+    ShSegments seg;
     const float* cov3D_precomp;
     const float* colors_precomp;
     float scale_modifier;
@@ -194,6 +204,8 @@ struct PreprocessBwdParams {
     const float* scales;
     const float* rotations;
     const float* shs;
+    ShSegments seg;       // inputs when segmented
+    ShSegments dseg;      // gradient outputs when segmented (dL_dsh unused then)
     const float* cov3D_precomp;
     const float* colors_precomp;
     float scale_modifier;

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
             float dx = fa(mx, -cam[0]), dy = fa(my, -cam[1]), dz = fa(mz, -cam[2]);
             const float len = __fsqrt_rn(sum3(dx, dx, dy, dy, dz, dz));
             dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
-            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            const float* sh = p.seg.enabled ? nullptr : p.shs + (size_t)idx * p.M * 3;
             float b[16];
             int nb = 1;
             b[0] = kC0;
@@ -205,7 +205,24 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
                 }
             }
             float acc[3] = {0.f, 0.f, 0.f};
-            if (p.M == 16) {
+            if (p.seg.enabled) {
+                // the model's own tensors, read in place: 3 floats of dc + 3*(nb-1) floats of the 180-byte rest row
+                const int sgi = idx >= p.seg.n_static;
+                const size_t li = (size_t)(idx - (sgi ? p.seg.n_static : 0));
+                const float* dc = p.seg.dc[sgi] + li * 3;
+                const float* rs = p.seg.rest[sgi] + li * 45;
+                acc[0] = fmaf(b[0], __ldg(dc), acc[0]);
+                acc[1] = fmaf(b[0], __ldg(dc + 1), acc[1]);
+                acc[2] = fmaf(b[0], __ldg(dc + 2), acc[2]);
+#pragma unroll
+                for (int k = 1; k < 16; k++) {
+                    if (k < nb) {
+                        acc[0] = fmaf(b[k], __ldg(rs + 3 * (k - 1)), acc[0]);
+                        acc[1] = fmaf(b[k], __ldg(rs + 3 * (k - 1) + 1), acc[1]);
+                        acc[2] = fmaf(b[k], __ldg(rs + 3 * (k - 1) + 2), acc[2]);
+                    }
+                }
+            } else if (p.M == 16) {
                 // 192-byte row, 16-byte aligned: twelve 128-bit loads
                 const float4* s4 = reinterpret_cast<const float4*>(sh);
                 float v[48];
@@ -561,10 +578,46 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
     const int base = blockIdx.x * kBT;
     const int idx = base + tid;
     const int nvalid = min(kBT, p.P - base);
-    const bool has_sh = (p.shs != nullptr);    // implies M == 16 here
+    const bool has_sh = (p.shs != nullptr) || p.seg.enabled;    // implies M == 16 here
 
     // cooperative, coalesced load of the block's SH rows
-    if (has_sh) {
+    // Segmented SH: the block's dc values (3 floats per Gaussian) and rest rows (45 floats) are contiguous
+    // inside each of the model's tensors, so they are staged FLAT, exactly as they lie in memory:
+    // s_dc[3 * row + c], s_rest[45 * row + 3 * (k - 1) + c] - a pure 128-bit copy in and out, and both
+    // per-thread strides (3, 45) are odd: the per-row accesses of the compute phase are conflict-free.
+    float* s_dc = s_sh;
+    float* s_rest = s_sh + kBT * 3;
+    const int seg_ns = p.seg.n_static;
+    const bool seg_one = p.seg.enabled && ((base >= seg_ns) || (base + nvalid <= seg_ns));
+    const int seg_i = base >= seg_ns;
+    const size_t seg_li0 = (size_t)(base - (seg_i ? seg_ns : 0));
+    if (p.seg.enabled) {
+        if (seg_one) {
+            const float* dc = p.seg.dc[seg_i] + seg_li0 * 3;
+            const float* rs = p.seg.rest[seg_i] + seg_li0 * 45;
+            const int nd = nvalid * 3, nr = nvalid * 45;
+            if (((reinterpret_cast<uintptr_t>(dc) | reinterpret_cast<uintptr_t>(rs)) & 15) == 0 && (nvalid & 3) == 0) {
+                for (int f4 = tid; f4 < nd / 4; f4 += kBT)
+                    reinterpret_cast<float4*>(s_dc)[f4] = __ldg(reinterpret_cast<const float4*>(dc) + f4);
+                for (int f4 = tid; f4 < nr / 4; f4 += kBT)
+                    reinterpret_cast<float4*>(s_rest)[f4] = __ldg(reinterpret_cast<const float4*>(rs) + f4);
+            } else {
+                for (int f = tid; f < nd; f += kBT) s_dc[f] = __ldg(dc + f);
+                for (int f = tid; f < nr; f += kBT) s_rest[f] = __ldg(rs + f);
+            }
+        } else {      // the one block that straddles the static / dynamic boundary
+            for (int f = tid; f < nvalid * 3; f += kBT) {
+                const int row = f / 3, g = base + row;
+                const int sgi = g >= seg_ns;
+                s_dc[f] = __ldg(p.seg.dc[sgi] + (size_t)(g - (sgi ? seg_ns : 0)) * 3 + (f - row * 3));
+            }
+            for (int f = tid; f < nvalid * 45; f += kBT) {
+                const int row = f / 45, g = base + row;
+                const int sgi = g >= seg_ns;
+                s_rest[f] = __ldg(p.seg.rest[sgi] + (size_t)(g - (sgi ? seg_ns : 0)) * 45 + (f - row * 45));
+            }
+        }
+    } else if (has_sh) {
         const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)base * 48);
         const int n4 = nvalid * 12;
         for (int f = tid; f < n4; f += kBT) {
@@ -590,7 +643,9 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float dscale[3] = {0.f, 0.f, 0.f};
         float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-        float* row = s_sh + tid * kRow;
+        // coefficient k of this thread's row lives at (k == 0 ? row0 : row)[3 * k + c]
+        float* row = p.seg.enabled ? s_rest + 45 * tid - 3 : s_sh + tid * kRow;
+        float* row0 = p.seg.enabled ? s_dc + 3 * tid : row;
         if (p.radii[idx] > 0) {
             const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
             float cov3D[6];
@@ -647,11 +702,13 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
                     if (k < nb) {
                         float b, bx, by, bz;
                         sh_basis_and_grad(p.D, x, y, z, k, b, bx, by, bz);
-                        const float s = row[3 * k] * d0 + row[3 * k + 1] * d1 + row[3 * k + 2] * d2;
+                        float* rk = (k == 0) ? row0 : row;
+                        const float s = rk[3 * k] * d0 + rk[3 * k + 1] * d1 + rk[3 * k + 2] * d2;
                         ddx += bx * s; ddy += by * s; ddz += bz * s;
-                        row[3 * k] = b * d0; row[3 * k + 1] = b * d1; row[3 * k + 2] = b * d2;
+                        rk[3 * k] = b * d0; rk[3 * k + 1] = b * d1; rk[3 * k + 2] = b * d2;
                     } else {
-                        row[3 * k] = 0.f; row[3 * k + 1] = 0.f; row[3 * k + 2] = 0.f;
+                        float* rk = (k == 0) ? row0 : row;
+                        rk[3 * k] = 0.f; rk[3 * k + 1] = 0.f; rk[3 * k + 2] = 0.f;
                     }
                 }
                 const float sum2 = ox * ox + oy * oy + oz * oz;
@@ -690,7 +747,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
             }
         } else if (has_sh) {
 #pragma unroll
-            for (int k = 0; k < 48; k++) row[k] = 0.f;
+            for (int k = 0; k < 48; k++) ((k < 3) ? row0 : row)[k] = 0.f;
         }
         s_o3[3 * kBT * 3 + 3 * tid + 0] = dmean[0]; s_o3[3 * kBT * 3 + 3 * tid + 1] = dmean[1]; s_o3[3 * kBT * 3 + 3 * tid + 2] = dmean[2];
         s_o3[4 * kBT * 3 + 3 * tid + 0] = dscale[0]; s_o3[4 * kBT * 3 + 3 * tid + 1] = dscale[1]; s_o3[4 * kBT * 3 + 3 * tid + 2] = dscale[2];
@@ -710,7 +767,31 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         float* dst = outs[a] + (size_t)base * 3;
         for (int f = tid; f < nvalid * 3; f += kBT) dst[f] = s_o3[a * kBT * 3 + f];
     }
-    if (has_sh) {
+    if (p.seg.enabled) {
+        if (seg_one) {
+            float* dc = p.dseg.dc[seg_i] + seg_li0 * 3;
+            float* rs = p.dseg.rest[seg_i] + seg_li0 * 45;
+            const int nd = nvalid * 3, nr = nvalid * 45;
+            if (((reinterpret_cast<uintptr_t>(dc) | reinterpret_cast<uintptr_t>(rs)) & 15) == 0 && (nvalid & 3) == 0) {
+                for (int f4 = tid; f4 < nd / 4; f4 += kBT) reinterpret_cast<float4*>(dc)[f4] = reinterpret_cast<const float4*>(s_dc)[f4];
+                for (int f4 = tid; f4 < nr / 4; f4 += kBT) reinterpret_cast<float4*>(rs)[f4] = reinterpret_cast<const float4*>(s_rest)[f4];
+            } else {
+                for (int f = tid; f < nd; f += kBT) dc[f] = s_dc[f];
+                for (int f = tid; f < nr; f += kBT) rs[f] = s_rest[f];
+            }
+        } else {
+            for (int f = tid; f < nvalid * 3; f += kBT) {
+                const int row = f / 3, g = base + row;
+                const int sgi = g >= seg_ns;
+                p.dseg.dc[sgi][(size_t)(g - (sgi ? seg_ns : 0)) * 3 + (f - row * 3)] = s_dc[f];
+            }
+            for (int f = tid; f < nvalid * 45; f += kBT) {
+                const int row = f / 45, g = base + row;
+                const int sgi = g >= seg_ns;
+                p.dseg.rest[sgi][(size_t)(g - (sgi ? seg_ns : 0)) * 45 + (f - row * 45)] = s_rest[f];
+            }
+        }
+    } else if (has_sh) {
         float4* dst = reinterpret_cast<float4*>(p.dL_dsh + (size_t)base * 48);
         const int n4 = nvalid * 12;
         for (int f = tid; f < n4; f += kBT) {
@@ -732,8 +813,8 @@ void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s)
 {
     if (p.P <= 0) return;
-    if (p.shs == nullptr || p.M == 16) {
-        const size_t smem = sizeof(float) * (40 + 5 * kBT * 3 + (p.shs != nullptr ? kBT * kRow : 0));
+    if (p.shs == nullptr || p.M == 16) {     // segmented SH (shs == nullptr, seg.enabled) always has M == 16
+        const size_t smem = sizeof(float) * (40 + 5 * kBT * 3 + ((p.shs != nullptr || p.seg.enabled) ? kBT * kRow : 0));
         preprocess_bwd_staged_kernel<<<(p.P + kBT - 1) / kBT, kBT, smem, s>>>(p);
     } else {
         preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);

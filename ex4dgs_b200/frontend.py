@@ -89,7 +89,9 @@ class FusedGetters:
     wrapper to the reference's unmodified render() (gaussian_renderer/__init__.py:28,62-95).  The four
     getters that render() calls for one timestamp (get_xyz_at_t twice, get_opacity_at_t,
     get_scaling, get_rotation_at_t) are served from ONE fused kernel launch, cached per timestamp;
-    get_features still concatenates in PyTorch.  Every other attribute is forwarded to the model.
+    get_features returns the model's four SH tensors as a SegmentedSH (no torch.cat: render() only
+    forwards that object to the rasterizer, which reads the tensors in place and writes their gradients
+    directly).  Every other attribute is forwarded to the model.
 
     `model` needs the reference's attribute names: _xyz, _xyz_disp, _rotation, _scaling, _opacity,
     _xyz_motion, _rotation_motion, _scaling_motion, _opacity_motion, _opacity_duration_center,
@@ -133,3 +135,9 @@ class FusedGetters:
     def get_opacity_at_t(self, t, mode=0, training=False):
         assert mode == 0
         return self._frame(t)[3]
+
+    def get_features(self, mode=0):
+        assert mode == 0
+        from .rasterizer import SegmentedSH
+        m = self._m
+        return SegmentedSH(m._features_dc, m._features_rest, m._features_dc_motion, m._features_rest_motion)

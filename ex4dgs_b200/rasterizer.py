@@ -74,11 +74,53 @@ def _alloc_trampoline(user, nbytes):
 _ALLOC_CB = _lib.ALLOC_FN(_alloc_trampoline)
 
 
+class SegmentedSH:
+    """The model's SH coefficients as it stores them - features_dc [Ns,1,3] / features_rest [Ns,15,3] of the
+    static Gaussians and the same pair of the dynamic ones - handed to the rasterizer WITHOUT the two
+    levels of torch.cat of CGaussianModel.get_features() (scene/c_gaussian_model.py:337-353).  Pass it as
+    `shs=`; the reference's render() only forwards `pc.get_features()` to the rasterizer
+    (gaussian_renderer/__init__.py:95-103), so a model wrapper may return this object from get_features()
+    (ex4dgs_b200.frontend.FusedGetters does).  Gradients flow to the four tensors directly."""
+
+    def __init__(self, dc_static, rest_static, dc_dynamic, rest_dynamic):
+        self.parts = (dc_static, rest_static, dc_dynamic, rest_dynamic)
+        for t, k in zip(self.parts, (1, 15, 1, 15)):
+            if t.dim() != 3 or t.shape[1] != k or t.shape[2] != 3:
+                raise ValueError("SegmentedSH needs [N,1,3] / [N,15,3] tensors (SH degree 3 layout), got %s" % (tuple(t.shape),))
+        if dc_static.shape[0] != rest_static.shape[0] or dc_dynamic.shape[0] != rest_dynamic.shape[0]:
+            raise ValueError("SegmentedSH: dc / rest row counts differ")
+
+    @property
+    def shape(self):
+        return (self.parts[0].shape[0] + self.parts[2].shape[0], 16, 3)
+
+    def cat(self) -> torch.Tensor:
+        """What get_features() would have returned."""
+        dc_s, rest_s, dc_d, rest_d = self.parts
+        return torch.cat((torch.cat((dc_s, rest_s), dim=1), torch.cat((dc_d, rest_d), dim=1)), dim=0)
+
+
 def rasterize_gaussians(means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     """__init__.py:22-45"""
+    if isinstance(sh, SegmentedSH):
+        return _RasterizeGaussiansSegmentedSH.apply(means3D, means2D, dir3D, *sh.parts, opacities, scales,
+                                                    rotations, cov3Ds_precomp, raster_settings)
     return _RasterizeGaussians.apply(means3D, means2D, dir3D, sh, colors_precomp, opacities, scales,
                                      rotations, cov3Ds_precomp, raster_settings)
+
+
+def _segments_struct(parts, dev):
+    """(ctypes struct, tensors kept alive) for EX4DGS_FLAG_SH_SEGMENTED."""
+    keep = []
+    for t in parts:
+        if t.numel() and not t.is_cuda:
+            raise RuntimeError("ex4dgs_b200: SegmentedSH tensors must be CUDA tensors")
+        keep.append(_f32c(t, dev))
+    st = _lib.ShSegments()
+    st.n_static = int(keep[0].shape[0])
+    st.dc_static, st.rest_static, st.dc_dynamic, st.rest_dynamic = [_ptr(t) for t in keep]
+    return st, keep
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -89,167 +131,214 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
                 cov3Ds_precomp, raster_settings):
-        rs = raster_settings
-        if means3D.dim() != 2 or means3D.size(1) != 3:
-            raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:62-64
-        if not means3D.is_cuda:
-            raise RuntimeError("ex4dgs_b200: the rasterizer is CUDA-only (as is the reference, "
-                               "rasterize_points.cu:80); got a %s tensor" % means3D.device)
-        lib = _lib.load()
-        dev = means3D.device
-        flags = int(getattr(rs, "_flags", _DEFAULT_FLAGS))
+        return _forward_impl(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
+                             cov3Ds_precomp, raster_settings)
 
-        args = (rs.bg, means3D, dir3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
-                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
-                rs.subpixel_offset, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos,
-                rs.prefiltered, rs.min_depth, rs.max_depth, rs.debug)
-        cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None     # __init__.py:91-93
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_flow, grad_out_acc, grad_out_idx):
+        g = _backward_impl(ctx, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc)
+        # slots whose forward input was "absent" get None (autograd ignores them in the reference too)
+        return (g["means3D"], g["means2D"], g["dir3D"], g["sh"], g["colors"], g["opacities"], g["scales"], g["rotations"],
+                g["cov3D"], None)
 
-        P = means3D.size(0)
-        H, W = int(rs.image_height), int(rs.image_width)
-        means3D_c = _f32c(means3D, dev)
-        dir3D_c = _f32c(dir3D, dev)
+
+class _RasterizeGaussiansSegmentedSH(torch.autograd.Function):
+    """Same operator with the SH input given as the model's four tensors (SegmentedSH): 12 slots
+    (means3D, means2D, dir3D, dc_static, rest_static, dc_dynamic, rest_dynamic, opacities, scales, rotations,
+    cov3Ds_precomp, None)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, dir3D, dc_s, rest_s, dc_d, rest_d, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        return _forward_impl(ctx, means3D, means2D, dir3D, (dc_s, rest_s, dc_d, rest_d), torch.Tensor([]), opacities,
+                             scales, rotations, cov3Ds_precomp, raster_settings)
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_flow, grad_out_acc, grad_out_idx):
+        g = _backward_impl(ctx, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc)
+        return (g["means3D"], g["means2D"], g["dir3D"], *g["sh_parts"], g["opacities"], g["scales"], g["rotations"],
+                g["cov3D"], None)
+
+
+def _forward_impl(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, scales, rotations,
+                  cov3Ds_precomp, raster_settings):
+    rs = raster_settings
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:62-64
+    if not means3D.is_cuda:
+        raise RuntimeError("ex4dgs_b200: the rasterizer is CUDA-only (as is the reference, "
+                           "rasterize_points.cu:80); got a %s tensor" % means3D.device)
+    lib = _lib.load()
+    dev = means3D.device
+    flags = int(getattr(rs, "_flags", _DEFAULT_FLAGS))
+
+    args = (rs.bg, means3D, dir3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+            cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
+            rs.subpixel_offset, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos,
+            rs.prefiltered, rs.min_depth, rs.max_depth, rs.debug)
+    cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None     # __init__.py:91-93
+
+    P = means3D.size(0)
+    H, W = int(rs.image_height), int(rs.image_width)
+    means3D_c = _f32c(means3D, dev)
+    dir3D_c = _f32c(dir3D, dev)
+    seg, seg_keep = None, []
+    if isinstance(sh, tuple):
+        seg, seg_keep = _segments_struct(sh, dev)
+        if seg_keep[0].shape[0] + seg_keep[2].shape[0] != means3D.size(0):
+            raise RuntimeError("SegmentedSH holds %d Gaussians, means3D %d" % (seg_keep[0].shape[0] + seg_keep[2].shape[0], means3D.size(0)))
+        flags |= _lib.FLAG_SH_SEGMENTED
+        sh_c = torch.empty(0, dtype=torch.float32, device=dev)
+    else:
         sh_c = _f32c(sh, dev)
-        colors_c = _f32c(colors_precomp, dev)
-        opac_c = _f32c(opacities, dev)
-        scales_c = _f32c(scales, dev)
-        rot_c = _f32c(rotations, dev)
-        cov_c = _f32c(cov3Ds_precomp, dev)
+    colors_c = _f32c(colors_precomp, dev)
+    opac_c = _f32c(opacities, dev)
+    scales_c = _f32c(scales, dev)
+    rot_c = _f32c(rotations, dev)
+    cov_c = _f32c(cov3Ds_precomp, dev)
+    bg = _f32c(rs.bg, dev)
+    view = _f32c(rs.viewmatrix, dev)
+    proj = _f32c(rs.projmatrix, dev)
+    campos = _f32c(rs.campos, dev)
+    sub = _f32c(rs.subpixel_offset, dev)
+    M = 16 if seg is not None else (sh_c.size(1) if sh_c.numel() != 0 else 0)        # rasterize_points.cu:92-96
+    sh_arg = C.cast(C.pointer(seg), C.c_void_p) if seg is not None else _ptr(sh_c)
+
+    iopt = dict(dtype=torch.int32, device=dev)
+    fopt = dict(dtype=torch.float32, device=dev)
+    if P == 0:
+        # rasterize_points.cu:73-90: nothing runs, outputs keep their fill values
+        color = torch.zeros(3, H, W, **fopt)
+        radii = torch.zeros(0, **iopt)
+        depth = torch.zeros(1, H, W, **fopt)
+        acc = torch.zeros(1, H, W, **fopt)
+        flow = torch.zeros(3, H, W, **fopt)
+        idxs = torch.full((1, H, W), -1, **iopt)
+        empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        ctx.raster_settings = rs
+        ctx.num_rendered = 0
+        ctx.flags = flags
+        ctx.segmented = seg is not None
+        ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, empty, empty, empty, depth, acc,
+                              *seg_keep)
+        return color, radii, depth, flow, acc, idxs
+
+    color = torch.empty(3, H, W, **fopt)
+    radii = torch.empty(P, **iopt)
+    depth = torch.empty(1, H, W, **fopt)
+    acc = torch.empty(1, H, W, **fopt)
+    flow = torch.empty(3, H, W, **fopt)
+    idxs = torch.empty(1, H, W, **iopt)
+    _tls.device = dev
+    _tls.tensors = [None, None, None]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    try:
+        with torch.cuda.device(dev):
+            R = lib.ex4dgs_forward(
+                _ALLOC_CB, C.c_void_p(0), _ALLOC_CB, C.c_void_p(1), _ALLOC_CB, C.c_void_p(2),
+                P, int(rs.sh_degree), int(M),
+                _ptr(bg), W, H,
+                _ptr(means3D_c), _ptr(dir3D_c), sh_arg, _ptr(colors_c),
+                _ptr(opac_c), _ptr(scales_c), float(rs.scale_modifier), _ptr(rot_c),
+                _ptr(cov_c), _ptr(view), _ptr(proj), _ptr(campos),
+                float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), int(bool(rs.prefiltered)),
+                _ptr(color), float(rs.min_depth), float(rs.max_depth), _ptr(depth), _ptr(acc), _ptr(flow),
+                _ptr(idxs), _ptr(radii), int(bool(rs.debug)), flags, C.c_void_p(stream))
+        if R < 0:
+            raise RuntimeError("ex4dgs_forward failed (%d): %s" % (R, _lib.last_error()))
+    except Exception as ex:
+        if rs.debug:                                             # __init__.py:94-99
+            torch.save(cpu_args, "snapshot_fw.dump")
+            print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+        raise ex
+
+    geomBuffer, binningBuffer, imgBuffer = _tls.tensors
+    _tls.tensors = None
+    ctx.raster_settings = rs
+    ctx.num_rendered = int(R)
+    ctx.flags = flags
+    ctx.segmented = seg is not None
+    ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c,
+                          geomBuffer, binningBuffer, imgBuffer, depth, acc, *seg_keep)
+    ctx.mark_non_differentiable(radii, idxs)
+    return color, radii, depth, flow, acc, idxs
+
+
+def _backward_impl(ctx, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc):
+    rs = ctx.raster_settings
+    (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
+     geomBuffer, binningBuffer, imgBuffer, depth, acc) = ctx.saved_tensors[:12]
+    seg_parts = ctx.saved_tensors[12:] if getattr(ctx, "segmented", False) else None
+    lib = _lib.load()
+    dev = means3D.device
+    P = means3D.size(0)
+    H, W = int(rs.image_height), int(rs.image_width)
+    M = 16 if seg_parts is not None else (sh.size(1) if sh.numel() != 0 else 0)
+    fopt = dict(dtype=torch.float32, device=dev)
+
+    args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, depth, acc, rs.min_depth, rs.max_depth,
+            rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+            rs.kernel_size, rs.subpixel_offset, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc,
+            sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug)
+    cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None   # __init__.py:151-153
+
+    use_sr = scales.numel() != 0
+    g_means2D = torch.empty(P, 3, **fopt)
+    g_colors = torch.empty(P, 3, **fopt)
+    g_opac = torch.empty(P, 1, **fopt)
+    g_means3D = torch.empty(P, 3, **fopt)
+    g_cov3D = torch.empty(P, 6, **fopt) if not use_sr else torch.empty(0, **fopt)
+    g_sh = torch.empty(P, M, 3, **fopt) if seg_parts is None else None
+    g_parts = [torch.empty_like(t) for t in seg_parts] if seg_parts is not None else None
+    sh_in, sh_out = _ptr(sh), _ptr(g_sh)
+    if seg_parts is not None:
+        seg_in, _ = _segments_struct(seg_parts, dev)
+        seg_out, _ = _segments_struct(g_parts, dev)
+        sh_in = C.cast(C.pointer(seg_in), C.c_void_p)
+        sh_out = C.cast(C.pointer(seg_out), C.c_void_p)
+    g_scales = torch.empty(P, 3, **fopt) if use_sr else torch.zeros(P, 3, **fopt)
+    g_rot = torch.empty(P, 4, **fopt) if use_sr else torch.zeros(P, 4, **fopt)
+    g_dir = torch.empty(P, 3, **fopt)
+
+    if P != 0:
+        gc = _f32c(grad_out_color, dev)
+        gd = _f32c(grad_out_depth, dev)
+        gf = _f32c(grad_out_flow, dev)
+        ga = _f32c(grad_out_acc, dev)
         bg = _f32c(rs.bg, dev)
         view = _f32c(rs.viewmatrix, dev)
         proj = _f32c(rs.projmatrix, dev)
         campos = _f32c(rs.campos, dev)
         sub = _f32c(rs.subpixel_offset, dev)
-        M = sh_c.size(1) if sh_c.numel() != 0 else 0        # rasterize_points.cu:92-96
-
-        iopt = dict(dtype=torch.int32, device=dev)
-        fopt = dict(dtype=torch.float32, device=dev)
-        if P == 0:
-            # rasterize_points.cu:73-90: nothing runs, outputs keep their fill values
-            color = torch.zeros(3, H, W, **fopt)
-            radii = torch.zeros(0, **iopt)
-            depth = torch.zeros(1, H, W, **fopt)
-            acc = torch.zeros(1, H, W, **fopt)
-            flow = torch.zeros(3, H, W, **fopt)
-            idxs = torch.full((1, H, W), -1, **iopt)
-            empty = torch.empty(0, dtype=torch.uint8, device=dev)
-            ctx.raster_settings = rs
-            ctx.num_rendered = 0
-            ctx.flags = flags
-            ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, empty, empty, empty, depth, acc)
-            return color, radii, depth, flow, acc, idxs
-
-        color = torch.empty(3, H, W, **fopt)
-        radii = torch.empty(P, **iopt)
-        depth = torch.empty(1, H, W, **fopt)
-        acc = torch.empty(1, H, W, **fopt)
-        flow = torch.empty(3, H, W, **fopt)
-        idxs = torch.empty(1, H, W, **iopt)
-        _tls.device = dev
-        _tls.tensors = [None, None, None]
         stream = torch.cuda.current_stream(dev).cuda_stream
         try:
             with torch.cuda.device(dev):
-                R = lib.ex4dgs_forward(
-                    _ALLOC_CB, C.c_void_p(0), _ALLOC_CB, C.c_void_p(1), _ALLOC_CB, C.c_void_p(2),
-                    P, int(rs.sh_degree), int(M),
+                rc = lib.ex4dgs_backward(
+                    P, int(rs.sh_degree), int(M), int(ctx.num_rendered),
                     _ptr(bg), W, H,
-                    _ptr(means3D_c), _ptr(dir3D_c), _ptr(sh_c), _ptr(colors_c),
-                    _ptr(opac_c), _ptr(scales_c), float(rs.scale_modifier), _ptr(rot_c),
-                    _ptr(cov_c), _ptr(view), _ptr(proj), _ptr(campos),
-                    float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), int(bool(rs.prefiltered)),
-                    _ptr(color), float(rs.min_depth), float(rs.max_depth), _ptr(depth), _ptr(acc), _ptr(flow),
-                    _ptr(idxs), _ptr(radii), int(bool(rs.debug)), flags, C.c_void_p(stream))
-            if R < 0:
-                raise RuntimeError("ex4dgs_forward failed (%d): %s" % (R, _lib.last_error()))
+                    _ptr(means3D), sh_in, _ptr(colors_precomp),
+                    _ptr(scales), float(rs.scale_modifier), _ptr(rotations),
+                    _ptr(depth), _ptr(acc), float(rs.min_depth), float(rs.max_depth),
+                    _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos),
+                    float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), _ptr(radii),
+                    _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+                    _ptr(gc), _ptr(gd), _ptr(gf), _ptr(ga),
+                    _ptr(g_means2D), _ptr(g_opac), _ptr(g_colors), _ptr(g_means3D), _ptr(g_cov3D),
+                    sh_out, _ptr(g_scales) if use_sr else None, _ptr(g_rot) if use_sr else None, _ptr(g_dir),
+                    int(bool(rs.debug)), int(ctx.flags), C.c_void_p(stream))
+            if rc < 0:
+                raise RuntimeError("ex4dgs_backward failed (%d): %s" % (rc, _lib.last_error()))
         except Exception as ex:
-            if rs.debug:                                             # __init__.py:94-99
-                torch.save(cpu_args, "snapshot_fw.dump")
-                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            if rs.debug:                                         # __init__.py:156-159
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
             raise ex
 
-        geomBuffer, binningBuffer, imgBuffer = _tls.tensors
-        _tls.tensors = None
-        ctx.raster_settings = rs
-        ctx.num_rendered = int(R)
-        ctx.flags = flags
-        ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c,
-                              geomBuffer, binningBuffer, imgBuffer, depth, acc)
-        ctx.mark_non_differentiable(radii, idxs)
-        return color, radii, depth, flow, acc, idxs
-
-    @staticmethod
-    def backward(ctx, grad_out_color, _, grad_out_depth, grad_out_flow, grad_out_acc, grad_out_idx):
-        rs = ctx.raster_settings
-        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
-         geomBuffer, binningBuffer, imgBuffer, depth, acc) = ctx.saved_tensors
-        lib = _lib.load()
-        dev = means3D.device
-        P = means3D.size(0)
-        H, W = int(rs.image_height), int(rs.image_width)
-        M = sh.size(1) if sh.numel() != 0 else 0
-        fopt = dict(dtype=torch.float32, device=dev)
-
-        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, depth, acc, rs.min_depth, rs.max_depth,
-                rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
-                rs.kernel_size, rs.subpixel_offset, grad_out_color, grad_out_depth, grad_out_flow, grad_out_acc,
-                sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug)
-        cpu_args = cpu_deep_copy_tuple(args) if rs.debug else None   # __init__.py:151-153
-
-        use_sr = scales.numel() != 0
-        g_means2D = torch.empty(P, 3, **fopt)
-        g_colors = torch.empty(P, 3, **fopt)
-        g_opac = torch.empty(P, 1, **fopt)
-        g_means3D = torch.empty(P, 3, **fopt)
-        g_cov3D = torch.empty(P, 6, **fopt) if not use_sr else torch.empty(0, **fopt)
-        g_sh = torch.empty(P, M, 3, **fopt)
-        g_scales = torch.empty(P, 3, **fopt) if use_sr else torch.zeros(P, 3, **fopt)
-        g_rot = torch.empty(P, 4, **fopt) if use_sr else torch.zeros(P, 4, **fopt)
-        g_dir = torch.empty(P, 3, **fopt)
-
-        if P != 0:
-            gc = _f32c(grad_out_color, dev)
-            gd = _f32c(grad_out_depth, dev)
-            gf = _f32c(grad_out_flow, dev)
-            ga = _f32c(grad_out_acc, dev)
-            bg = _f32c(rs.bg, dev)
-            view = _f32c(rs.viewmatrix, dev)
-            proj = _f32c(rs.projmatrix, dev)
-            campos = _f32c(rs.campos, dev)
-            sub = _f32c(rs.subpixel_offset, dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            try:
-                with torch.cuda.device(dev):
-                    rc = lib.ex4dgs_backward(
-                        P, int(rs.sh_degree), int(M), int(ctx.num_rendered),
-                        _ptr(bg), W, H,
-                        _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
-                        _ptr(scales), float(rs.scale_modifier), _ptr(rotations),
-                        _ptr(depth), _ptr(acc), float(rs.min_depth), float(rs.max_depth),
-                        _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos),
-                        float(rs.tanfovx), float(rs.tanfovy), float(rs.kernel_size), _ptr(sub), _ptr(radii),
-                        _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
-                        _ptr(gc), _ptr(gd), _ptr(gf), _ptr(ga),
-                        _ptr(g_means2D), _ptr(g_opac), _ptr(g_colors), _ptr(g_means3D), _ptr(g_cov3D),
-                        _ptr(g_sh), _ptr(g_scales) if use_sr else None, _ptr(g_rot) if use_sr else None, _ptr(g_dir),
-                        int(bool(rs.debug)), int(ctx.flags), C.c_void_p(stream))
-                if rc < 0:
-                    raise RuntimeError("ex4dgs_backward failed (%d): %s" % (rc, _lib.last_error()))
-            except Exception as ex:
-                if rs.debug:                                         # __init__.py:156-159
-                    torch.save(cpu_args, "snapshot_bw.dump")
-                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                raise ex
-
-        # slots whose forward input was "absent" get None (autograd ignores them in the reference too)
-        return (g_means3D, g_means2D, g_dir,
-                g_sh if M != 0 else None,
-                g_colors if colors_precomp.numel() != 0 else None,
-                g_opac,
-                g_scales if use_sr else None,
-                g_rot if use_sr else None,
-                g_cov3D if not use_sr else None,
-                None)
+    return dict(means3D=g_means3D, means2D=g_means2D, dir3D=g_dir,
+                sh=g_sh if (M != 0 and seg_parts is None) else None, sh_parts=g_parts,
+                colors=g_colors if colors_precomp.numel() != 0 else None, opacities=g_opac,
+                scales=g_scales if use_sr else None, rotations=g_rot if use_sr else None,
+                cov3D=g_cov3D if not use_sr else None)
 
 
 class GaussianRasterizationSettings(NamedTuple):

@@ -47,6 +47,23 @@ typedef enum ex4dgs_status {
  * internal tile lists get shorter.  With the flag clear the tile lists (point_list, ranges,
  * n_contrib) are bit-identical to the reference's (rasterizer_impl.cu:72-140). */
 #define EX4DGS_FLAG_TILE_CULL 1u
+/* Segmented SH input (fused model front-end): the model keeps its SH coefficients in
+ * four tensors - features_dc [Ns,1,3] / features_rest [Ns,15,3] for the static Gaussians and the same
+ * pair for the dynamic ones - which CGaussianModel.get_features() concatenates into [P,16,3] on every
+ * frame (scene/c_gaussian_model.py:337-353: ~1.5 GB of copies at 2 M Gaussians, and as much again in
+ * the backward).  With this flag the `shs` argument of ex4dgs_forward / ex4dgs_backward is not a
+ * device array but a HOST pointer to an ex4dgs_sh_segments (cast to const float*), the kernels read
+ * the four tensors in place, and `dL_dsh` of ex4dgs_backward is likewise a host pointer to an
+ * ex4dgs_sh_segments holding the four gradient outputs (every element written).  M must be 16.
+ * Gaussians [0, n_static) are the static ones (static first, as the reference concatenates). */
+#define EX4DGS_FLAG_SH_SEGMENTED 2u
+typedef struct ex4dgs_sh_segments {
+    int n_static;
+    float* dc_static;      /* [n_static, 1, 3]        */
+    float* rest_static;    /* [n_static, 15, 3]       */
+    float* dc_dynamic;     /* [P - n_static, 1, 3]    */
+    float* rest_dynamic;   /* [P - n_static, 15, 3]   */
+} ex4dgs_sh_segments;
 
 /* Resizable scratch buffers, the C form of `std::function<char*(size_t)>` in
  * rasterizer.h:38-40 / rasterize_points.cu:27-33: called once per buffer per forward (the binning

@@ -102,20 +102,27 @@ def test_unmodified_render_runs_on_the_dropin(built):
 
 
 def test_unmodified_render_with_fused_getters(built):
-    """render() + FusedGetters (one kernel for all per-frame getters) == render() + PyTorch getters."""
+    """render() + FusedGetters (one kernel for all per-frame getters, SH handed over as the model's four
+    tensors without torch.cat) == render() + PyTorch getters, values and gradients down to the parameters."""
     if not os.path.exists(os.path.join(CALLERS, "gaussian_renderer", "__init__.py")):
         pytest.skip("reference caller not installed (python oracle/build_ref.py)")
     import diff_gaussian_rasterization_df as ours_pkg
     from ex4dgs_b200.frontend import FusedGetters
+    from ex4dgs_b200.rasterizer import SegmentedSH
     sc = synth.make_config("C1d", pose="tilted")
+
+    def P(t):
+        return t.detach().clone().cuda().requires_grad_(True)
+
     model = types.SimpleNamespace(
-        _xyz=sc.xyz.cuda(), _xyz_disp=sc.xyz_disp.cuda(), _rotation=sc.rotation.cuda(), _scaling=sc.scaling.cuda(),
-        _opacity=sc.opacity.cuda(), _xyz_motion=sc.xyz_motion.cuda(), _rotation_motion=sc.rotation_motion.cuda(),
-        _scaling_motion=sc.scaling_motion.cuda(), _opacity_motion=sc.opacity_motion.cuda(),
-        _opacity_duration_center=sc.opacity_center.cuda(), _opacity_duration_var=sc.opacity_var.cuda(),
+        _xyz=P(sc.xyz), _xyz_disp=P(sc.xyz_disp), _rotation=P(sc.rotation), _scaling=P(sc.scaling),
+        _opacity=P(sc.opacity), _xyz_motion=P(sc.xyz_motion), _rotation_motion=P(sc.rotation_motion),
+        _scaling_motion=P(sc.scaling_motion), _opacity_motion=P(sc.opacity_motion),
+        _opacity_duration_center=P(sc.opacity_center), _opacity_duration_var=P(sc.opacity_var),
+        _features_dc=P(sc.features[:, :1]), _features_rest=P(sc.features[:, 1:]),
+        _features_dc_motion=P(sc.features_motion[:, :1]), _features_rest_motion=P(sc.features_motion[:, 1:]),
         duration=sc.duration, interval=sc.interval, time_shift=sc.time_shift, var_pad=sc.var_pad,
-        kernel_size=sc.cam.kernel_size, active_sh_degree=sc.sh_degree, max_sh_degree=3,
-        get_features=lambda mode=0: torch.cat([sc.features, sc.features_motion]).cuda())
+        kernel_size=sc.cam.kernel_size, active_sh_degree=sc.sh_degree, max_sh_degree=3)
     sys.modules["diff_gaussian_rasterization_df"] = ours_pkg
     sys.path.insert(0, CALLERS)
     try:
@@ -125,9 +132,21 @@ def test_unmodified_render_with_fused_getters(built):
     finally:
         sys.path.remove(CALLERS)
     pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
-    out = gr.render(_camera(sc), FusedGetters(model), pipe, sc.bg.cuda(), near=sc.cam.min_depth, far=sc.cam.max_depth)
-    ref = U.run_impl(ours_pkg, sc, kind="ours", grads=False, intermediates=False)
+    fg = FusedGetters(model)
+    assert isinstance(fg.get_features(), SegmentedSH)
+    out = gr.render(_camera(sc), fg, pipe, sc.bg.cuda(), near=sc.cam.min_depth, far=sc.cam.max_depth)
+    go = synth.grad_outputs(sc)
+    torch.autograd.backward([out["render"], out["opticalflow"]], [go["grad_color"].cuda(), go["grad_flow"].cuda()])
+    ref = U.run_impl(ours_pkg, sc, kind="ours", grads=True, intermediates=False)
     assert float(np.abs(out["render"].detach().cpu().numpy() - ref["color"]).max()) <= 1e-4
     assert np.array_equal(out["radii"].cpu().numpy(), ref["radii"])
+    # SH gradients arrive in the four parameter tensors, equal to the slices of the concatenated gradient
+    Ns = sc.xyz.shape[0]
+    gs = ref["grads"]["shs"]
+    for got, want in ((model._features_dc.grad, gs[:Ns, :1]), (model._features_rest.grad, gs[:Ns, 1:]),
+                      (model._features_dc_motion.grad, gs[Ns:, :1]), (model._features_rest_motion.grad, gs[Ns:, 1:])):
+        assert got is not None and tuple(got.shape) == want.shape
+        assert U.rel_err(got.cpu().numpy(), want, U.grad_floor(gs)) <= 2e-3
+    assert model._xyz_motion.grad is not None and float(model._xyz_motion.grad.abs().max()) > 0
     for m in ("gaussian_renderer", "utils", "utils.sh_utils", "diff_gaussian_rasterization_df"):
         sys.modules.pop(m, None)

@@ -360,3 +360,57 @@ def test_flow_free_forward_equals_general_kernel(built, cull):
                                          opacities=inc["opacities"], shs=inc["shs"], scales=inc["scales"],
                                          rotations=inc["rotations"])[3]
     assert float((fo - b[3].cpu()).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("split", ["C1d", "all-static", "all-dynamic", "odd"])
+def test_segmented_sh_equals_concatenated(built, cull, split):
+    """EX4DGS_FLAG_SH_SEGMENTED: the model's four SH tensors read in place == the [P,16,3] torch.cat of
+    get_features() (scene/c_gaussian_model.py:337-353): bit-identical forward, gradients equal to the
+    slices of dL_dsh; static/dynamic boundaries inside a 128-Gaussian block, empty segments, SH degree 1."""
+    from ex4dgs_b200.rasterizer import SegmentedSH
+    mod = U.ours_module()
+    dev = "cuda"
+    sc = synth.make_config("C1d", pose="tilted")
+    if split == "odd":
+        sc.sh_degree = 1
+    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    P = inp["means3D"].shape[0]
+    Ns = {"C1d": sc.xyz.shape[0], "all-static": P, "all-dynamic": 0, "odd": 4099}[split]
+    rs = U.settings_for(mod, sc, dev)
+    go = {k: v.to(dev) for k, v in synth.grad_outputs(sc).items()}
+
+    def run(shs):
+        t = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations")}
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        d3 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        out = mod.GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, dir3D=d3, opacities=t["opacities"], shs=shs,
+                                         scales=t["scales"], rotations=t["rotations"])
+        torch.autograd.backward([out[0], out[2], out[3], out[4]],
+                                [go["grad_color"], go["grad_depth"], go["grad_flow"], go["grad_acc"]])
+        return out, t, m2, d3
+
+    full = inp["shs"].clone().requires_grad_(True)
+    a_out, a_t, a_m2, a_d3 = run(full)
+    parts = [inp["shs"][:Ns, :1].clone().contiguous().requires_grad_(True), inp["shs"][:Ns, 1:].clone().contiguous().requires_grad_(True),
+             inp["shs"][Ns:, :1].clone().contiguous().requires_grad_(True), inp["shs"][Ns:, 1:].clone().contiguous().requires_grad_(True)]
+    seg = SegmentedSH(*parts)
+    assert tuple(seg.shape) == (P, 16, 3) and torch.equal(seg.cat(), inp["shs"])
+    b_out, b_t, b_m2, b_d3 = run(seg)
+    for x, y in zip(a_out, b_out):
+        assert torch.equal(x, y)
+    gs = full.grad.cpu().numpy()
+    fl = U.grad_floor(gs)
+    want = [gs[:Ns, :1], gs[:Ns, 1:], gs[Ns:, :1], gs[Ns:, 1:]]
+    for g, w in zip(parts, want):
+        assert g.grad is not None and tuple(g.grad.shape) == w.shape
+        assert U.rel_err(g.grad.cpu().numpy(), w, fl) <= 2e-3
+    for k in a_t:
+        ga = a_t[k].grad.cpu().numpy()
+        assert U.rel_err(b_t[k].grad.cpu().numpy(), ga, U.grad_floor(ga)) <= 2e-3, k
+    assert U.rel_err(b_m2.grad.cpu().numpy(), a_m2.grad.cpu().numpy(), U.grad_floor(a_m2.grad.cpu().numpy())) <= 2e-3
+    # argument checks
+    with pytest.raises(ValueError):
+        SegmentedSH(parts[0], parts[0], parts[2], parts[3])
+    with pytest.raises(RuntimeError):
+        mod.GaussianRasterizer(rs)(means3D=inp["means3D"][:-1], means2D=torch.zeros(P - 1, 3, device=dev), dir3D=torch.zeros(P - 1, 3, device=dev),
+                                   opacities=inp["opacities"][:-1], shs=seg, scales=inp["scales"][:-1], rotations=inp["rotations"][:-1])
