@@ -387,7 +387,31 @@ def cpu_oracle_baseline(sc: synth.Scene):
             "sample": "1 full frame (fwd+bwd) of the same workload, oracle/cpu_raster.c with OpenMP, %.1f s" % dt}
 
 
+_JSON_FD = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints
+    "NCCL version ..." to fd 1 under NCCL_DEBUG=VERSION/INFO): keep a private copy of the real stdout for
+    the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -429,7 +453,7 @@ def main():
                     "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0,
                     "note": "reference CUDA extension not available in oracle/_ref; CPU oracle port timed instead"}
-            print(json.dumps(line), flush=True)
+            emit(line)
             return
 
     if not torch.cuda.is_available():
@@ -485,7 +509,7 @@ def main():
             model_step(group)
         ms_iter, _, _ = timed(lambda: model_step(group), K)
         if rank == 0:
-            print(json.dumps({"train_iter_ms": ms_iter / K, "steps": K, "parameters": n_param, "impl": args.impl}), flush=True)
+            emit({"train_iter_ms": ms_iter / K, "steps": K, "parameters": n_param, "impl": args.impl})
         if ws > 1:
             torch.distributed.destroy_process_group()
         return
@@ -635,7 +659,7 @@ def main():
         line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
                                 "sample": "the unmodified reference CUDA extension (oracle/_ref) on the same GPU - the reference "
                                           "path has no CPU implementation (rasterize_points.cu:80)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if ws > 1:
         torch.distributed.destroy_process_group()
 
