@@ -121,6 +121,45 @@ def load_reference_loss():
     return loss_utils
 
 
+def load_reference_model_class():
+    """The reference's CGaussianModel class (scene/c_gaussian_model.py, installed unmodified by oracle/build_ref.py):
+    its statistics methods are what the reference arm's training iteration runs.  Two of its imports do not exist
+    in this image and are never used by those methods: `plyfile` and `simple_knn._C` get empty stand-ins."""
+    d = os.path.join(ROOT, "oracle", "_ref", "callers")
+    path = os.path.join(d, "scene", "c_gaussian_model.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    import types
+    if "plyfile" not in sys.modules:
+        m = types.ModuleType("plyfile")
+        m.PlyData = m.PlyElement = object
+        sys.modules["plyfile"] = m
+    if "simple_knn._C" not in sys.modules:
+        pkg, sub = types.ModuleType("simple_knn"), types.ModuleType("simple_knn._C")
+        sub.distCUDA2 = None
+        pkg._C = sub
+        sys.modules["simple_knn"], sys.modules["simple_knn._C"] = pkg, sub
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    spec = importlib.util.spec_from_file_location("ref_c_gaussian_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.CGaussianModel
+
+
+def stats_tensors(Ns, Nd, dev):
+    """CGaussianModel.training_setup (scene/c_gaussian_model.py:412-428) and :408-409 / :843-844."""
+    z = lambda *s: torch.zeros(*s, device=dev)
+    o = lambda *s: torch.ones(*s, device=dev)
+    return dict(
+        max_radii2D=z(Ns), min_radii2D=o(Ns) * 1000, xyz_gradient_accum=z(Ns, 1), denom=z(Ns, 1), xyz_error_accum=z(Ns, 1),
+        xyz_error_min=o(Ns, 1) * 1000, xyz_error_min_timestamp=o(Ns, 1) * -1, xyz_ssim_error_accum=z(Ns, 1), error_denom=z(Ns, 1),
+        motion_max_radii2D=z(Nd), motion_min_radii2D=o(Nd) * 1000, motion_xyz_gradient_accum=z(Nd, 1), motion_denom=z(Nd, 1),
+        motion_xyz_error_min=o(Nd, 1) * 1000, motion_xyz_error_mean=z(Nd, 1), motion_xyz_error_min_timestamp=o(Nd, 1) * -1,
+        motion_xyz_ssim_error_accum=z(Nd, 1), motion_error_denom=z(Nd, 1))
+
+
 class Frame:
     """Resident inputs of one rank + the step functions."""
 
@@ -172,7 +211,10 @@ class Frame:
     def step_device(self):
         color, radii, depth, flow, acc, idxs = self._raster(self.settings(self.view, self.proj, self.campos))
         go = self.go
-        torch.autograd.backward([color, depth, flow, acc], [go["grad_color"], go["grad_depth"], go["grad_flow"], go["grad_acc"]])
+        # dense grad_color, the hook tensor as grad_flow, grad_depth = grad_acc = 0.  As in train.py
+        # the depth / acc images simply do not enter the loss: autograd hands the reference materialised zero
+        # tensors for them (its Function keeps the default), this repo's Function receives None -> NULL.
+        torch.autograd.backward([color, flow], [go["grad_color"], go["grad_flow"]])
         self.last = color
         if color.grad_fn is not None and hasattr(color.grad_fn, "num_rendered"):
             self.R = int(color.grad_fn.num_rendered)
@@ -244,12 +286,19 @@ MODEL_GROUPS = [("xyz", 1.6e-4), ("f_dc", 2.5e-3), ("f_rest", 2.5e-3 / 20), ("op
 LR_SCALE = 1e-3     # keeps the synthetic scene stationary over the timed steps; RAdam's work is lr-independent
 
 
-def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_dssim=0.2):
-    """One full training iteration on the MODEL's native parameters (train.py:124-251 minus
-    densification): per-frame getters (fused front-end kernel, row N1 / the PyTorch getters of
+STATIC_REG, MOTION_REG = 0.0001, 0.0001      # arguments/__init__.py:134-135 (rot_reg = 0.0: its branch never runs)
+
+
+def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_dssim=0.2, bookkeeping=True, ref_model_cls=None):
+    """One full training iteration on the MODEL's native parameters (train.py:124-253 minus
+    densify_and_prune): per-frame getters (fused front-end kernel, row N1 / the PyTorch getters of
     scene/c_gaussian_model.py:170-215,330-375 restated in synth.py), get_features' torch.cat, render,
     loss block (row N2 / utils/loss_utils.py), backward down to the 15 parameter tensors,
-    optimizer.step() (FusedRAdam, row N4 / torch.optim.RAdam) and zero_grad(set_to_none=True)."""
+    optimizer.step() (FusedRAdam, row N4 / torch.optim.RAdam) and zero_grad(set_to_none=True).
+    bookkeeping adds what train.py does around that every iteration: the static / motion regularisation terms
+    (:156-162), mark_prune_stats + max_radii2D + add_densification_stats + add_l1_ssim_stats (:196-212), the
+    nan_to_num of one gradient (:246-248) and prune_nan_points' NaN test (:253) - fused kernels
+    (ex4dgs_b200/stats.py, FusedRAdam guards) against the reference's own methods and expressions."""
     import copy
     sc, dev = frame.sc, frame.dev
     m = copy.copy(sc)
@@ -270,15 +319,31 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
                "motion_rotation": m.rotation_motion}
     groups = [{"params": [by_name[n]], "lr": lr * LR_SCALE, "name": n} for n, lr in MODEL_GROUPS]
     params = [g["params"][0] for g in groups]
+    Ns, Nd = sc.xyz.shape[0], sc.xyz_motion.shape[0]
     if impl == "ours":
+        from types import SimpleNamespace
+        from ex4dgs_b200 import stats as fstats
         from ex4dgs_b200.frontend import interpolate_gaussians
         from ex4dgs_b200.loss import photometric_loss
         from ex4dgs_b200.optim import FusedRAdam, allreduce_gradients
         from ex4dgs_b200.rasterizer import SegmentedSH
-        opt = FusedRAdam(groups, lr=0.001)
+        if bookkeeping:
+            opt = FusedRAdam(groups, lr=0.001, check_nan=("xyz", "motion_xyz"), sanitize_grad=("motion_opacity_var",))
+        else:
+            opt = FusedRAdam(groups, lr=0.001)
+        gaussians = SimpleNamespace(_xyz=m.xyz, **stats_tensors(Ns, Nd, dev))
     else:
         opt = torch.optim.RAdam(groups, lr=0.001)
-    P = sc.xyz.shape[0] + sc.xyz_motion.shape[0]
+        gaussians = None
+        if bookkeeping:
+            if ref_model_cls is None:
+                raise SystemExit("reference arm: oracle/_ref/callers/scene/c_gaussian_model.py is missing (run oracle/build_ref.py)")
+            gaussians = ref_model_cls.__new__(ref_model_cls)      # __init__ would build an empty model; only the
+            for k, v in stats_tensors(Ns, Nd, dev).items():       # statistics tensors and the two tested parameters are used
+                setattr(gaussians, k, v)
+            gaussians._xyz, gaussians._xyz_motion = m.xyz, m.xyz_motion
+            gaussians._xyz_disp, gaussians._opacity_duration_var = m.xyz_disp, m.opacity_var
+    P = Ns + Nd
     n_param = sum(p.numel() for p in params)
 
     def step(group=None):
@@ -317,8 +382,37 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
         hook_tensor = torch.stack([acc[0], l1_errors, ssim_errors])
         flow_h = flow.register_hook(lambda grad: hook_tensor)
         loss = loss + flow.mean() * 0
+        if bookkeeping and impl != "ours":
+            # train.py:156-162, verbatim
+            loss += STATIC_REG * torch.log(gaussians._xyz_disp.norm(dim=-1) + 0.001).mean()
+            diff1 = (gaussians._xyz_motion[:, :1] - gaussians._xyz_motion[:, 1:])
+            loss += MOTION_REG * diff1.norm(dim=-1).mean()
         loss.backward()
         flow_h.remove()
+        if bookkeeping and impl == "ours":
+            # same two terms: values added to the reported loss, gradients added to the .grad of the two tensors
+            loss = loss.detach() + fstats.regularizers_(m.xyz_disp, m.xyz_motion, STATIC_REG, MOTION_REG).sum()
+        if bookkeeping:
+            with torch.no_grad():
+                if impl == "ours":
+                    fstats.iteration_stats(gaussians, radii, means2D.grad, flow_in.grad, sc.timestamp, densify=True, static_num=Ns)
+                else:
+                    # train.py:196-212, verbatim (viewspace_point_tensor = means2D, viewspace_point_error_tensor = flow_in)
+                    viewspace_point_tensor, viewspace_point_error_tensor, visibility_filter = means2D, flow_in, radii > 0
+                    gaussians.mark_prune_stats(radii, viewspace_point_error_tensor)
+                    static_num = gaussians._xyz.shape[0]
+                    static_vis_filter = visibility_filter[:static_num]
+                    static_radii = radii[:static_num]
+                    dynamic_vis_filter = visibility_filter[static_num:]
+                    dynamic_radii = radii[static_num:]
+                    gaussians.max_radii2D[static_vis_filter] = torch.max(gaussians.max_radii2D[static_vis_filter], static_radii[static_vis_filter])
+                    gaussians.motion_max_radii2D[dynamic_vis_filter] = torch.max(gaussians.motion_max_radii2D[dynamic_vis_filter], dynamic_radii[dynamic_vis_filter])
+                    gaussians.add_densification_stats(viewspace_point_tensor, static_vis_filter, dynamic_vis_filter, static_num)
+                    gaussians.add_l1_ssim_stats(viewspace_point_error_tensor, static_vis_filter, dynamic_vis_filter, static_num, sc.timestamp)
+                    # train.py:244-248
+                    if gaussians._opacity_duration_var.shape[0] != 0:
+                        if not gaussians._opacity_duration_var.grad is None:
+                            gaussians._opacity_duration_var.grad = gaussians._opacity_duration_var.grad.nan_to_num()
         scale = 1.0
         if dp_grads and group is not None:
             if impl == "ours":
@@ -333,6 +427,13 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
         else:
             opt.step()
         opt.zero_grad(set_to_none=True)
+        if bookkeeping:
+            if impl == "ours":
+                if any(opt.poll_nan().values()):                  # flags raised by the step kernel, read without waiting
+                    raise RuntimeError("NaN parameters")
+            else:
+                with torch.no_grad():
+                    gaussians.prune_nan_points()                  # train.py:253
         l = loss.detach().reshape(1)
         if group is not None:
             torch.distributed.all_reduce(l)
@@ -426,6 +527,8 @@ def main():
                     help="record per-stage CUDA events inside the timed region (1) or in a separate pass (0)")
     ap.add_argument("--no-train-iter", action="store_true", help="skip the full-training-iteration leg")
     ap.add_argument("--only-train-iter", action="store_true", help="profiling aid: run only the train_iter leg")
+    ap.add_argument("--bookkeeping", type=int, default=1,
+                    help="--only-train-iter: include the per-iteration regularisers / statistics / NaN guards (train_iter_full)")
     ap.add_argument("--dp-grads", action="store_true",
                     help="train_iter leg under torchrun: SUM all-reduce of all gradients before the optimizer step")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
@@ -504,12 +607,15 @@ def main():
         rl = None
         if args.impl != "ours":
             rl = load_reference_loss()
-        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", rl, args.dp_grads)
+        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", rl, args.dp_grads,
+                                              bookkeeping=bool(args.bookkeeping),
+                                              ref_model_cls=load_reference_model_class() if args.impl != "ours" else None)
         for _ in range(W):
             model_step(group)
         ms_iter, _, _ = timed(lambda: model_step(group), K)
         if rank == 0:
-            emit({"train_iter_ms": ms_iter / K, "steps": K, "parameters": n_param, "impl": args.impl})
+            emit({"train_iter_ms": ms_iter / K, "steps": K, "parameters": n_param, "impl": args.impl,
+                  "bookkeeping": bool(args.bookkeeping)})
         if ws > 1:
             torch.distributed.destroy_process_group()
         return
@@ -578,12 +684,30 @@ def main():
                             "the reference's utils/loss_utils.py (torch conv2d)")}
 
     # full training iteration on the model's native parameters (rows N1 + N2 + N4 around the path)
-    train_iter = None
+    train_iter = train_iter_full = None
     if not args.fwd_only and not args.no_train_iter:
-        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", ref_loss, args.dp_grads)
+        Kt = max(20, K // 3)
+        ref_cls = load_reference_model_class() if args.impl != "ours" else None
+        if args.impl == "ours" or ref_cls is not None:
+            model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", ref_loss, args.dp_grads,
+                                                  bookkeeping=True, ref_model_cls=ref_cls)
+            for _ in range(W):
+                model_step(group)
+            ms_full, _, _ = timed(lambda: model_step(group), Kt)
+            train_iter_full = {"value": ws * Kt / (ms_full / 1000.0), "unit": "iterations/s", "ms_per_step": ms_full / Kt, "steps": Kt,
+                               "what": "train_iter + everything else train.py does every iteration outside densify_and_prune: "
+                                       "static / motion regularisation terms (:156-162), mark_prune_stats, max_radii2D, "
+                                       "add_densification_stats, add_l1_ssim_stats (:196-212), nan_to_num of one gradient (:246-248), "
+                                       "prune_nan_points' NaN test (:253); "
+                                       + ("fused statistics kernel + regulariser kernel + guards inside the RAdam kernel"
+                                          if args.impl == "ours" else
+                                          "the reference's own CGaussianModel methods and train.py expressions")}
+            del model_step
+            torch.cuda.empty_cache()
+        model_step, n_param = make_model_step(frame, "ours" if args.impl == "ours" else "reference", ref_loss, args.dp_grads,
+                                              bookkeeping=False)
         for _ in range(W):
             model_step(group)
-        Kt = max(20, K // 3)
         ms_iter, _, _ = timed(lambda: model_step(group), Kt)
         train_iter = {"value": ws * Kt / (ms_iter / 1000.0), "unit": "iterations/s", "ms_per_step": ms_iter / Kt, "steps": Kt,
                       "parameters": n_param, "lr_scale": LR_SCALE, "gradient_allreduce": bool(args.dp_grads and ws > 1),
@@ -613,6 +737,8 @@ def main():
         line["train_step"] = train
     if train_iter is not None:
         line["train_iter"] = train_iter
+    if train_iter_full is not None:
+        line["train_iter_full"] = train_iter_full
     if args.impl == "ours":
         st = frame_stats(frame)
         peaks = {}

@@ -34,6 +34,12 @@ class RAdamTensor(C.Structure):
                 ("numel", C.c_size_t), ("lr", C.c_double), ("step", C.c_longlong)]
 
 
+class StatsArrays(C.Structure):
+    """ex4dgs_stats_arrays (include/ex4dgs_raster.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("max_radii2D", "min_radii2D", "xyz_gradient_accum", "denom", "error_accum",
+                                          "error_min", "error_min_timestamp", "ssim_error_accum", "error_denom")]
+
+
 class ArrayDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("buffer", C.c_int), ("offset", C.c_size_t),
                 ("elem_size", C.c_size_t), ("count", C.c_size_t)]
@@ -85,7 +91,11 @@ SIGNATURES = {
                                       _P, _P, _P, _P, _P, _P,
                                       _P]),
     "ex4dgs_radam_step": (_I, [C.POINTER(RAdamTensor), _I, _D, _D, _D, _D, _P]),
+    "ex4dgs_radam_step_ex": (_I, [C.POINTER(RAdamTensor), _I, _D, _D, _D, _D, C.c_uint, C.c_uint, _P, _P]),
     "ex4dgs_radam_scalars": (_I, [_D, C.c_longlong, _D, _D, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
+    "ex4dgs_iteration_stats": (_I, [_I, _I, _P, _P, _P, _F, _I, C.POINTER(StatsArrays), C.POINTER(StatsArrays), _P]),
+    "ex4dgs_regularizer_scratch_bytes": (C.c_size_t, []),
+    "ex4dgs_regularizers": (_I, [_I, _I, _I, _P, _P, _F, _F, _P, _P, _I, _P, _I, _P, _P, _P]),
     "ex4dgs_loss_scratch_bytes": (C.c_size_t, [_I, _I]),
     "ex4dgs_loss_forward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "ex4dgs_loss_backward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P]),

@@ -413,7 +413,8 @@ int ex4dgs_backward(
     Prof prof(true, s);
     if (P <= 0) return EX4DGS_OK;
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(EX4DGS_ERR_INVALID, "scratch buffers of the forward are required");
-    if (!dL_dpix || !dL_ddepth || !dL_dflow || !dL_dacc) return fail(EX4DGS_ERR_INVALID, "upstream gradients are required");
+    // dL_ddepth / dL_dflow / dL_dacc may be NULL = "no upstream gradient" (all zero): their terms are skipped
+    if (!dL_dpix) return fail(EX4DGS_ERR_INVALID, "the upstream colour gradient is required");
     if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_ddir) return fail(EX4DGS_ERR_INVALID, "gradient outputs are required");
     if (shs && !dL_dsh) return fail(EX4DGS_ERR_INVALID, "dL_dsh is required when shs is given");
     if (scales && (!dL_dscale || !dL_drot)) return fail(EX4DGS_ERR_INVALID, "dL_dscale/dL_drot are required when scales are given");
@@ -538,14 +539,16 @@ int ex4dgs_radam_scalars(double lr, long long step, double beta1, double beta2, 
     return EX4DGS_OK;
 }
 
-int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
-                      double grad_scale, void* stream)
+int ex4dgs_radam_step_ex(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                         double grad_scale, unsigned check_nan_mask, unsigned sanitize_grad_mask, int* nan_flags,
+                         void* stream)
 {
     g_err[0] = 0;
     if (n < 0 || n > EX4DGS_RADAM_MAX_TENSORS || (n > 0 && !tensors))
         return fail(EX4DGS_ERR_INVALID, "radam_step: n=%d outside [0, %d]", n, EX4DGS_RADAM_MAX_TENSORS);
     if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0))
         return fail(EX4DGS_ERR_INVALID, "radam_step: bad hyper-parameters beta1=%g beta2=%g eps=%g", beta1, beta2, eps);
+    if (check_nan_mask && !nan_flags) return fail(EX4DGS_ERR_INVALID, "radam_step: check_nan_mask needs nan_flags");
     RAdamTensorDesc d[EX_OPT_MAX_TENSORS];
     int m = 0;
     for (int i = 0; i < n; i++) {
@@ -557,11 +560,89 @@ int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, d
         d[m].numel = t.numel;
         radam_scalars(t.lr, (double)t.step, beta1, beta2, &d[m].S, &d[m].U, &d[m].rectified);
         d[m].aligned = 0;
+        d[m].index = i;
+        d[m].check_nan = (check_nan_mask >> i) & 1u;
+        d[m].sanitize_grad = (sanitize_grad_mask >> i) & 1u;
         m++;
     }
-    cudaError_t e = launch_radam(d, m, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+    cudaError_t e = launch_radam(d, m, beta1, beta2, eps, grad_scale, nan_flags, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "radam_step: %s", cudaGetErrorString(e));
     if (m > 0) g_launches += 1;
+    return EX4DGS_OK;
+}
+
+int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                      double grad_scale, void* stream)
+{
+    return ex4dgs_radam_step_ex(tensors, n, beta1, beta2, eps, grad_scale, 0u, 0u, nullptr, stream);
+}
+
+int ex4dgs_iteration_stats(int Ns, int Nd, const int* radii, const float* grad_means2D, const float* grad_error,
+                           float timestamp, int densify,
+                           const ex4dgs_stats_arrays* stat, const ex4dgs_stats_arrays* dyn, void* stream)
+{
+    g_err[0] = 0;
+    if (Ns < 0 || Nd < 0) return fail(EX4DGS_ERR_INVALID, "iteration_stats: negative counts");
+    if (Ns + Nd == 0) return EX4DGS_OK;
+    if (!radii || !grad_means2D) return fail(EX4DGS_ERR_INVALID, "iteration_stats: radii and grad_means2D are required");
+    IterStatsParams p;
+    memset(&p, 0, sizeof(p));
+    p.Ns = Ns; p.Nd = Nd; p.radii = radii; p.grad_means2D = grad_means2D; p.grad_error = grad_error;
+    p.timestamp = timestamp; p.densify = densify ? 1 : 0;
+    const ex4dgs_stats_arrays* src[2] = {stat, dyn};
+    StatsArrays* dst[2] = {&p.stat, &p.dyn};
+    const int cnt[2] = {Ns, Nd};
+    for (int i = 0; i < 2; i++) {
+        if (cnt[i] == 0) continue;
+        const ex4dgs_stats_arrays* a = src[i];
+        if (!a) return fail(EX4DGS_ERR_INVALID, "iteration_stats: %s arrays are required", i ? "dynamic" : "static");
+        const bool need_err = grad_error != nullptr;
+        if ((need_err && !a->min_radii2D) ||
+            (densify && (!a->max_radii2D || !a->xyz_gradient_accum || !a->denom)) ||
+            (densify && need_err && (!a->error_accum || !a->error_min || !a->error_min_timestamp || !a->ssim_error_accum || !a->error_denom)))
+            return fail(EX4DGS_ERR_INVALID, "iteration_stats: a %s statistics array is NULL", i ? "dynamic" : "static");
+        dst[i]->max_radii2D = a->max_radii2D; dst[i]->min_radii2D = a->min_radii2D;
+        dst[i]->xyz_gradient_accum = a->xyz_gradient_accum; dst[i]->denom = a->denom;
+        dst[i]->error_accum = a->error_accum; dst[i]->error_min = a->error_min;
+        dst[i]->error_min_timestamp = a->error_min_timestamp; dst[i]->ssim_error_accum = a->ssim_error_accum;
+        dst[i]->error_denom = a->error_denom;
+    }
+    cudaError_t e = launch_iteration_stats(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "iteration_stats: %s", cudaGetErrorString(e));
+    g_launches += 1;
+    return EX4DGS_OK;
+}
+
+size_t ex4dgs_regularizer_scratch_bytes(void)
+{
+    return (size_t)regularizer_blocks() * 2 * sizeof(double) + 256;
+}
+
+int ex4dgs_regularizers(int Ns, int Nd, int K, const float* xyz_disp, const float* xyz_motion,
+                        float static_reg, float motion_reg, const float* dL_dloss,
+                        float* dL_dxyz_disp, int accumulate_disp, float* dL_dxyz_motion, int accumulate_motion,
+                        float* out_terms, char* scratch, void* stream)
+{
+    g_err[0] = 0;
+    if (Ns < 0 || Nd < 0 || K < 0) return fail(EX4DGS_ERR_INVALID, "regularizers: negative sizes");
+    if (!out_terms || !scratch) return fail(EX4DGS_ERR_INVALID, "regularizers: out_terms and scratch are required");
+    RegParams p;
+    memset(&p, 0, sizeof(p));
+    p.Ns = Ns; p.Nd = Nd; p.K = K;
+    p.xyz_disp = xyz_disp; p.xyz_motion = xyz_motion;
+    // mean() over an empty tensor is NaN in torch; the reference only evaluates the motion term when
+    // _xyz_motion has rows (train.py:159) and always has static Gaussians: empty inputs switch a term off
+    p.static_coef = (static_reg != 0.0f && Ns > 0) ? static_reg / (float)Ns : 0.0f;
+    p.motion_coef = (motion_reg != 0.0f && Nd > 0 && K > 1) ? motion_reg / ((float)Nd * (float)(K - 1)) : 0.0f;
+    if (p.static_coef != 0.0f && !xyz_disp) return fail(EX4DGS_ERR_INVALID, "regularizers: xyz_disp is NULL");
+    if (p.motion_coef != 0.0f && !xyz_motion) return fail(EX4DGS_ERR_INVALID, "regularizers: xyz_motion is NULL");
+    p.dL_dloss = dL_dloss;
+    p.dL_dxyz_disp = dL_dxyz_disp; p.dL_dxyz_motion = dL_dxyz_motion;
+    p.accumulate_disp = accumulate_disp ? 1 : 0; p.accumulate_motion = accumulate_motion ? 1 : 0;
+    p.part = reinterpret_cast<double*>(align256(scratch));
+    cudaError_t e = launch_regularizers(p, out_terms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "regularizers: %s", cudaGetErrorString(e));
+    g_launches += 2;
     return EX4DGS_OK;
 }
 

@@ -254,9 +254,50 @@ struct RAdamTensorDesc {
     float U;            // -lr / (1 - beta1^t) while the variance is not tractable (rho_t <= 5), else 0
     int rectified;      // rho_t > 5
     int aligned;        // all four pointers 16-byte aligned (filled by the launcher)
+    int index;          // position in the caller's table (slot of nan_flags)
+    int check_nan;      // report NaN parameters of this tensor in nan_flags[index]
+    int sanitize_grad;  // nan_to_num the gradient first
 };
 cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, double beta2, double eps, double grad_scale,
-                         cudaStream_t s);
+                         int* nan_flags, cudaStream_t s);
+
+// per-iteration statistics and regularisers (stats.cu)
+struct StatsArrays {          // one set for the static Gaussians, one for the dynamic ones
+    float* max_radii2D;
+    float* min_radii2D;
+    float* xyz_gradient_accum;
+    float* denom;
+    float* error_accum;       // xyz_error_accum / motion_xyz_error_mean
+    float* error_min;
+    float* error_min_timestamp;
+    float* ssim_error_accum;
+    float* error_denom;
+};
+struct IterStatsParams {
+    int Ns, Nd;
+    const int* radii;             // [Ns + Nd]
+    const float* grad_means2D;    // [Ns + Nd, 3]
+    const float* grad_error;      // [Ns + Nd, 3] or nullptr (l1_accum off)
+    float timestamp;
+    int densify;
+    StatsArrays stat, dyn;
+};
+struct RegParams {
+    long long Ns, Nd;
+    int K;
+    const float* xyz_disp;        // [Ns, 3]
+    const float* xyz_motion;      // [Nd, K, 3]
+    float static_coef;            // static_reg / Ns          (0: term off)
+    float motion_coef;            // motion_reg / (Nd (K-1))  (0: term off)
+    const float* dL_dloss;        // device scalar or nullptr (= 1)
+    float* dL_dxyz_disp;          // nullptr: value only
+    float* dL_dxyz_motion;
+    int accumulate_disp, accumulate_motion;   // 1: += into the existing gradient, 0: overwrite
+    double* part;                 // 2 * regularizer_blocks() doubles
+};
+cudaError_t launch_iteration_stats(const IterStatsParams& p, cudaStream_t s);
+int regularizer_blocks();
+cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s);
 
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
 size_t binning_stage1_temp_bytes(int P);

@@ -32,6 +32,7 @@ struct RAdamKernelParams {
     float w2;            // 1 - beta2
     float eps;
     float grad_scale;    // gradients are multiplied by this first (1/world_size after a sum all-reduce)
+    int* nan_flags;      // device int[n] or nullptr: nan_flags[i] = 1 when tensor i (check_nan set) received a NaN parameter
     unsigned chunk_end[EX_OPT_MAX_TENSORS];      // exclusive prefix of chunks per tensor
     RAdamTensorDesc t[EX_OPT_MAX_TENSORS];
 };
@@ -41,6 +42,10 @@ __device__ __forceinline__ void radam_elem(float& p, float g, float& m, float& v
 {
     // FMA placement = what nvcc makes of the foreach functors (lerp: self + w * (end - self);
     // addcmul: self + value * (t1 * t2))
+    if (d.sanitize_grad) {       // torch.nan_to_num (train.py:246-248): NaN -> 0, +-inf -> +-FLT_MAX
+        if (g != g) g = 0.0f;
+        else g = fminf(fmaxf(g, -3.402823466e+38f), 3.402823466e+38f);
+    }
     g = __fmul_rn(g, k.grad_scale);
     m = __fmaf_rn(k.w1, __fsub_rn(g, m), m);
     v = __fmul_rn(v, k.beta2);
@@ -66,6 +71,7 @@ __global__ void __launch_bounds__(kOptThreads) radam_kernel(const __grid_constan
         const float* __restrict__ G = d.grad + base;
         float* __restrict__ M = d.exp_avg + base;
         float* __restrict__ V = d.exp_avg_sq + base;
+        bool bad = false;
         if (d.aligned && cnt == kChunk) {
 #pragma unroll
             for (int i = 0; i < kChunk / (4 * kOptThreads); i++) {
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(kOptThreads) radam_kernel(const __grid_constan
                 radam_elem(p.y, g.y, m.y, v.y, k, d);
                 radam_elem(p.z, g.z, m.z, v.z, k, d);
                 radam_elem(p.w, g.w, m.w, v.w, k, d);
+                bad |= (p.x != p.x) | (p.y != p.y) | (p.z != p.z) | (p.w != p.w);
                 reinterpret_cast<float4*>(P)[f] = p;
                 reinterpret_cast<float4*>(M)[f] = m;
                 reinterpret_cast<float4*>(V)[f] = v;
@@ -86,16 +93,20 @@ __global__ void __launch_bounds__(kOptThreads) radam_kernel(const __grid_constan
             for (int f = threadIdx.x; f < cnt; f += kOptThreads) {
                 float p = P[f], m = M[f], v = V[f];
                 radam_elem(p, __ldg(G + f), m, v, k, d);
+                bad |= (p != p);
                 P[f] = p; M[f] = m; V[f] = v;
             }
         }
+        // prune_nan_points (c_gaussian_model.py:1229-1241) tests _xyz / _xyz_motion for NaN after every step with
+        // two reductions and two host waits; here the written values are tested on the fly
+        if (d.check_nan && k.nan_flags && bad) k.nan_flags[d.index] = 1;
     }
 }
 
 }  // namespace
 
 cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, double beta2, double eps, double grad_scale,
-                         cudaStream_t s)
+                         int* nan_flags, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     RAdamKernelParams k;
@@ -105,6 +116,7 @@ cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, do
     k.w2 = (float)(1.0 - beta2);
     k.eps = (float)eps;
     k.grad_scale = (float)grad_scale;
+    k.nan_flags = nan_flags;
     unsigned long long chunks = 0;
     for (int i = 0; i < n; i++) {
         k.t[i] = tensors[i];

@@ -93,7 +93,10 @@ __device__ __forceinline__ void acc_to(float& dst, float x, int u)
 // 8x8 block (a lane owns pixels (x, y) and (x, y + 4)): the per-lane gradient terms of the two
 // pixels are added before the warp butterfly, so one butterfly + one reduction instruction serves
 // 64 pixels instead of 32.
-template <int PPT>
+// DA = false: the caller has no upstream gradient for the depth and accumulated-alpha images (NULL
+// dL_ddepth and dL_dacc - what autograd reports when the loss does not use them, as in train.py): their
+// terms are exactly zero and are dropped at compile time.  A NULL dL_dflow is read as zeros.
+template <int PPT, bool DA>
 __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
 {
     constexpr int NW = 8 / PPT;            // warps per tile
@@ -144,14 +147,18 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
             T_final[u] = p.final_T[pix_id];
             last_contributor[u] = (int)p.n_contrib[pix_id];
             const float final_acc = __ldg(p.out_acc + pix_id);
-            final_depth[u] = __ldg(p.out_depth + pix_id);
-            dL_ddepth[u] = __ldg(p.dL_ddepth + pix_id);
+            if (DA) {
+                final_depth[u] = __ldg(p.out_depth + pix_id);
+                if (p.dL_ddepth) dL_ddepth[u] = __ldg(p.dL_ddepth + pix_id);
+            }
             if (final_acc > 0.0f) {
-                dL_ddepth[u] = dL_ddepth[u] / final_acc;
-                dflow0[u] = __ldg(p.dL_dflow + pix_id) / final_acc;
-                dflow1[u] = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
-                dflow2[u] = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
-                dL_dacc[u] = __ldg(p.dL_dacc + pix_id);
+                if (DA) dL_ddepth[u] = dL_ddepth[u] / final_acc;
+                if (p.dL_dflow) {
+                    dflow0[u] = __ldg(p.dL_dflow + pix_id) / final_acc;
+                    dflow1[u] = __ldg(p.dL_dflow + HW + pix_id) / final_acc;
+                    dflow2[u] = __ldg(p.dL_dflow + 2 * HW + pix_id) / final_acc;
+                }
+                if (DA && p.dL_dacc) dL_dacc[u] = __ldg(p.dL_dacc + pix_id);
             }
             dpix0[u] = __ldg(p.dL_dpix + pix_id);
             dpix1[u] = __ldg(p.dL_dpix + HW + pix_id);
@@ -283,9 +290,11 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
                     const float w = alpha[u] * T[u];               // dchannel_dcolor
                     float dL_dalpha = 0.0f;
                     const float dep = a.z;
-                    if ((dep > p.min_depth) & (w > 0.0f)) {
-                        acc_to(v[2], dL_ddepth[u] * w, u);
-                        dL_dalpha += (final_depth[u] - dep) * dL_ddepth[u] * T[u];
+                    if (DA) {
+                        if ((dep > p.min_depth) & (w > 0.0f)) {
+                            acc_to(v[2], dL_ddepth[u] * w, u);
+                            dL_dalpha += (final_depth[u] - dep) * dL_ddepth[u] * T[u];
+                        }
                     }
                     accum_rec0[u] = last_alpha[u] * last_c0[u] + (1.f - last_alpha[u]) * accum_rec0[u];
                     accum_rec1[u] = last_alpha[u] * last_c1[u] + (1.f - last_alpha[u]) * accum_rec1[u];
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
                     acc_to(v[8], w * dpix0[u], u); acc_to(v[9], w * dpix1[u], u); acc_to(v[10], w * dpix2[u], u);
                     acc_to(v[12], w * dflow0[u], u); acc_to(v[13], w * dflow1[u], u); acc_to(v[14], w * dflow2[u], u);
                     dL_dalpha *= T[u];
-                    dL_dacc[u] *= T[u];
+                    if (DA) dL_dacc[u] *= T[u];
                     last_alpha[u] = alpha[u];
                     dL_dalpha += (-T_final[u] * inv1ma) * bg_dot_dpixel[u];
                     // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
@@ -308,7 +317,8 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
                     acc_to(v[4], X * dx[u], u);
                     acc_to(v[5], X * dy[u], u);
                     acc_to(v[6], Y * dy[u], u);
-                    acc_to(v[3], G[u] * dL_dalpha + G[u] * dL_dacc[u], u);
+                    if (DA) acc_to(v[3], G[u] * dL_dalpha + G[u] * dL_dacc[u], u);
+                    else acc_to(v[3], G[u] * dL_dalpha, u);
                 }
             }
             const float tot = butterfly16(v, lane);
@@ -329,5 +339,6 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
     dim3 grid(grid_x, grid_y, 1);
-    render_bwd_kernel<EX_BWD_PPT><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
+    if (p.dL_ddepth || p.dL_dacc) render_bwd_kernel<EX_BWD_PPT, true><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
+    else render_bwd_kernel<EX_BWD_PPT, false><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
 }

@@ -26,7 +26,17 @@ from . import _lib
 class FusedRAdam(torch.optim.Optimizer):
     """torch.optim.RAdam semantics (betas, eps; weight_decay must be 0 as in the reference), one fused launch."""
 
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 check_nan=(), sanitize_grad=()):
+        """check_nan / sanitize_grad: group names (the reference names every group, c_gaussian_model.py:430-449).
+        The two per-iteration guards of train.py:244-253 are folded into the step kernel: the gradient of a
+        `sanitize_grad` group goes through nan_to_num first (train.py:246-248 does that for "motion_opacity_var"),
+        and a NaN parameter written into a `check_nan` group raises that group's flag (prune_nan_points,
+        c_gaussian_model.py:1229-1241, tests "xyz" and "motion_xyz" with reductions + host waits after every step).
+        Read the flags with nan_detected() (waits for the device) or poll_nan() (no wait, one step late)."""
+        self._check_nan = frozenset(check_nan)
+        self._sanitize = frozenset(sanitize_grad)
+        self._flags = {}          # device -> int32[32 * launches-per-step] flag words, [device tensor, pinned copy, names]
         if not 0.0 <= lr:
             raise ValueError("Invalid learning rate: %r" % (lr,))
         if not 0.0 <= eps:
@@ -67,20 +77,66 @@ class FusedRAdam(torch.optim.Optimizer):
                 st["step"] += 1
                 g = p.grad if (p.grad.dtype == torch.float32 and p.grad.is_contiguous()) else p.grad.float().contiguous()
                 batches.setdefault((float(beta1), float(beta2), float(group["eps"]), p.device), []).append(
-                    (p, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), int(st["step"].item())))
+                    (p, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), int(st["step"].item()), group.get("name")))
+        slot = {}
         for (beta1, beta2, eps, dev), items in batches.items():
             stream = torch.cuda.current_stream(dev).cuda_stream
             for i in range(0, len(items), 32):
                 chunk = items[i:i + 32]
                 arr = (_lib.RAdamTensor * len(chunk))()
-                for a, (p, g, m, v, lr, step) in zip(arr, chunk):
+                check = sanitize = 0
+                for j, (a, (p, g, m, v, lr, step, name)) in enumerate(zip(arr, chunk)):
                     a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
                     a.numel, a.lr, a.step = p.numel(), lr, step
+                    check |= int(name in self._check_nan) << j
+                    sanitize |= int(name in self._sanitize) << j
+                flags_ptr = None
+                if check:
+                    fl = self._flags.get(dev)
+                    base = slot.get(dev, 0)
+                    if fl is None or fl[0].numel() < base + 32:
+                        old = fl
+                        fl = self._flags[dev] = [torch.zeros(base + 32, dtype=torch.int32, device=dev),
+                                                 torch.zeros(base + 32, dtype=torch.int32).pin_memory(), {}]
+                        if old is not None:
+                            fl[0][:old[0].numel()] = old[0]
+                            fl[2] = old[2]
+                    for j, it in enumerate(chunk):
+                        if (check >> j) & 1:
+                            fl[2][it[6]] = base + j
+                    flags_ptr = fl[0].data_ptr() + 4 * base
+                    slot[dev] = base + 32
                 with torch.cuda.device(dev):
-                    rc = lib.ex4dgs_radam_step(arr, len(chunk), beta1, beta2, eps, float(grad_scale), C.c_void_p(stream))
+                    rc = lib.ex4dgs_radam_step_ex(arr, len(chunk), beta1, beta2, eps, float(grad_scale), check, sanitize,
+                                                  C.c_void_p(flags_ptr) if flags_ptr else None, C.c_void_p(stream))
                 if rc < 0:
                     raise RuntimeError("ex4dgs_radam_step failed (%d): %s" % (rc, _lib.last_error()))
         return loss
+
+    def nan_detected(self) -> dict:
+        """{group name: bool} for the check_nan groups: has any step so far written a NaN into the parameter?
+        Waits for the device (like the reference's per-step `isnan().any()` test)."""
+        out = {n: False for n in self._check_nan}
+        for fl in self._flags.values():
+            host = fl[0].cpu()
+            for name, j in fl[2].items():
+                out[name] = out[name] or bool(host[j].item())
+        return out
+
+    def poll_nan(self) -> dict:
+        """Same without waiting: returns what the PREVIOUS poll's asynchronous copy delivered (valid once the
+        stream has passed that point, e.g. after the training loop's `loss.item()`), then queues a new copy."""
+        out = {n: False for n in self._check_nan}
+        for fl in self._flags.values():
+            for name, j in fl[2].items():
+                out[name] = out[name] or bool(fl[1][j].item())
+            fl[1].copy_(fl[0], non_blocking=True)
+        return out
+
+    def clear_nan(self) -> None:
+        for fl in self._flags.values():
+            fl[0].zero_()
+            fl[1].zero_()
 
 
 def allreduce_gradients(params: Iterable[torch.Tensor], group: Optional[dist.ProcessGroup] = None) -> float:

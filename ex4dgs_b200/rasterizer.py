@@ -24,6 +24,11 @@ from . import _lib
 _DEFAULT_FLAGS = int(os.environ.get("EX4DGS_TILE_CULL", "1")) & 1
 
 
+# EX4DGS_MATERIALIZE_GRADS=1: A/B knob - let autograd hand zero tensors to the backward for unused outputs
+# (the reference's behaviour) instead of None.
+_MATERIALIZE_GRADS = os.environ.get("EX4DGS_MATERIALIZE_GRADS", "0") == "1"
+
+
 def set_default_flags(tile_cull: bool) -> None:
     global _DEFAULT_FLAGS
     _DEFAULT_FLAGS = _lib.FLAG_TILE_CULL if tile_cull else 0
@@ -254,6 +259,10 @@ def _forward_impl(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, s
 
     geomBuffer, binningBuffer, imgBuffer = _tls.tensors
     _tls.tensors = None
+    # outputs the loss does not use arrive as None in backward (instead of the zero tensors the reference
+    # receives, __init__.py:110): the C ABI takes NULL for them and skips their terms
+    if not _MATERIALIZE_GRADS:
+        ctx.set_materialize_grads(False)
     ctx.raster_settings = rs
     ctx.num_rendered = int(R)
     ctx.flags = flags
@@ -301,10 +310,10 @@ def _backward_impl(ctx, grad_out_color, grad_out_depth, grad_out_flow, grad_out_
     g_dir = torch.empty(P, 3, **fopt)
 
     if P != 0:
-        gc = _f32c(grad_out_color, dev)
-        gd = _f32c(grad_out_depth, dev)
-        gf = _f32c(grad_out_flow, dev)
-        ga = _f32c(grad_out_acc, dev)
+        gc = _f32c(grad_out_color, dev) if grad_out_color is not None else torch.zeros(3, H, W, **fopt)
+        gd = _f32c(grad_out_depth, dev) if grad_out_depth is not None else None
+        gf = _f32c(grad_out_flow, dev) if grad_out_flow is not None else None
+        ga = _f32c(grad_out_acc, dev) if grad_out_acc is not None else None
         bg = _f32c(rs.bg, dev)
         view = _f32c(rs.viewmatrix, dev)
         proj = _f32c(rs.projmatrix, dev)

@@ -156,9 +156,9 @@ int ex4dgs_backward(
     void* binning_buffer,
     void* image_buffer,
     const float* dL_dpix,        /* [3,H,W] */
-    const float* dL_ddepth,      /* [H,W]   */
-    const float* dL_dflow,       /* [3,H,W] */
-    const float* dL_dacc,        /* [H,W]   */
+    const float* dL_ddepth,      /* [H,W]   or NULL = no upstream gradient (read as zeros, terms skipped) */
+    const float* dL_dflow,       /* [3,H,W] or NULL */
+    const float* dL_dacc,        /* [H,W]   or NULL */
     float* dL_dmean2D,
     float* dL_dopacity,
     float* dL_dcolor,
@@ -261,10 +261,65 @@ typedef struct ex4dgs_radam_tensor {
 } ex4dgs_radam_tensor;
 int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
                       double grad_scale, void* stream);
+/* Same step with the two per-iteration guards of train.py:244-253 folded in (bit i of a mask = tensors[i]):
+ *   sanitize_grad_mask  the gradient is passed through torch.nan_to_num first (NaN -> 0, +-inf -> +-FLT_MAX;
+ *                       train.py:246-248 does it for _opacity_duration_var.grad)
+ *   check_nan_mask      nan_flags[i] (device int[n], caller-zeroed, only ever set to 1) reports that tensor i
+ *                       received a NaN parameter - what CGaussianModel.prune_nan_points
+ *                       (scene/c_gaussian_model.py:1229-1241) finds out with isnan().any() reductions and a host
+ *                       wait for _xyz and _xyz_motion after every step. */
+int ex4dgs_radam_step_ex(const ex4dgs_radam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                         double grad_scale, unsigned check_nan_mask, unsigned sanitize_grad_mask, int* nan_flags,
+                         void* stream);
 /* Host-only helper (no GPU needed): the two per-tensor scalars the kernel receives for step `step`,
  * p += m * (rectified ? 1 / ((sqrt(v) + eps) / S) : U)  - exposed so the CPU tests can pin them against
  * torch/optim/radam.py's expressions. */
 int ex4dgs_radam_scalars(double lr, long long step, double beta1, double beta2, float* S, float* U, int* rectified);
+
+/* ---- per-iteration statistics (SURVEY.md section 8, row N4 "stats updates") -----------------------
+ * Replaces, in ONE launch without host synchronisation, the bookkeeping train.py:196-215 performs after
+ * loss.backward() through boolean-mask indexing (~60 PyTorch kernels, a nonzero() + host wait per mask):
+ *   CGaussianModel.mark_prune_stats      (scene/c_gaussian_model.py:1105-1117)   when grad_error != NULL
+ *   max_radii2D / motion_max_radii2D     (train.py:205-206)                      when densify
+ *   CGaussianModel.add_densification_stats (:1095-1103)                          when densify
+ *   CGaussianModel.add_l1_ssim_stats       (:1119-1145)                          when densify && grad_error
+ * for the Ns static Gaussians (arrays `stat`) followed by the Nd dynamic ones (arrays `dyn`; the model's
+ * motion_* tensors, `error_accum` being motion_xyz_error_mean).  All arrays: device float, one element per
+ * Gaussian, updated in place.
+ *   radii         [Ns+Nd] int32, the rasterizer's output (visibility_filter = radii > 0)
+ *   grad_means2D  [Ns+Nd,3] = viewspace_point_tensor.grad
+ *   grad_error    [Ns+Nd,3] = viewspace_point_error_tensor.grad (acc, l1, ssim back-projections), or NULL
+ *                 when opt.l1_accum is off
+ *   timestamp     the camera's timestamp (stored into *_error_min_timestamp)
+ *   densify       iteration < opt.densify_until_iter */
+typedef struct ex4dgs_stats_arrays {
+    float* max_radii2D;
+    float* min_radii2D;
+    float* xyz_gradient_accum;
+    float* denom;
+    float* error_accum;
+    float* error_min;
+    float* error_min_timestamp;
+    float* ssim_error_accum;
+    float* error_denom;
+} ex4dgs_stats_arrays;
+int ex4dgs_iteration_stats(int Ns, int Nd, const int* radii, const float* grad_means2D, const float* grad_error,
+                           float timestamp, int densify,
+                           const ex4dgs_stats_arrays* stat, const ex4dgs_stats_arrays* dyn, void* stream);
+
+/* ---- regularisation terms of the loss (train.py:156-162) ------------------------------------------
+ *   out_terms[0] = static_reg * mean_i log(|xyz_disp[i]| + 0.001)                     (Ns > 0, static_reg != 0)
+ *   out_terms[1] = motion_reg * mean_{i,k>=1} |xyz_motion[i,0] - xyz_motion[i,k]|     (Nd > 0, K > 1, motion_reg != 0)
+ * and their gradients times *dL_dloss (device scalar; NULL = 1), written to (accumulate = 0) or added in
+ * place to (accumulate = 1, the gradient the backward pass has already produced) dL_dxyz_disp [Ns,3] /
+ * dL_dxyz_motion [Nd,K,3]; a NULL gradient pointer computes the value only.  A term whose weight is 0 is
+ * skipped (train.py tests `opt.*_reg > 0`) and reports 0.  scratch: ex4dgs_regularizer_scratch_bytes()
+ * device bytes.  Sums are reduced in a fixed order (bit-reproducible). */
+size_t ex4dgs_regularizer_scratch_bytes(void);
+int ex4dgs_regularizers(int Ns, int Nd, int K, const float* xyz_disp, const float* xyz_motion,
+                        float static_reg, float motion_reg, const float* dL_dloss,
+                        float* dL_dxyz_disp, int accumulate_disp, float* dL_dxyz_motion, int accumulate_motion,
+                        float* out_terms, char* scratch, void* stream);
 
 /* ---- introspection (used by the parity tests to look inside the opaque scratch buffers) ------- */
 typedef struct ex4dgs_array_desc {

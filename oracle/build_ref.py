@@ -87,10 +87,13 @@ def install_callers():
     GPU box can run the unmodified render() against this repository's drop-in package
     (tests/test_gpu_dropin.py); plus utils/loss_utils.py (and its import utils/graphics_utils.py),
     the loss block of train.py:144-151, so that `bench.py --impl reference` can time the reference's
-    own training-step loss next to the fused one (row N2)."""
+    own training-step loss next to the fused one (row N2); plus scene/c_gaussian_model.py and the utils modules it
+    imports, so that the reference arm's training iteration runs the reference's OWN statistics methods
+    (mark_prune_stats, add_densification_stats, add_l1_ssim_stats, prune_nan_points) next to the fused kernel."""
     root = "/root/reference"
     dst = os.path.join(HERE, "_ref", "callers")
-    for rel in ("gaussian_renderer/__init__.py", "utils/sh_utils.py", "utils/loss_utils.py", "utils/graphics_utils.py"):
+    for rel in ("gaussian_renderer/__init__.py", "utils/sh_utils.py", "utils/loss_utils.py", "utils/graphics_utils.py",
+                "scene/c_gaussian_model.py", "utils/general_utils.py", "utils/system_utils.py", "utils/interpolations.py"):
         os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
         shutil.copyfile(os.path.join(root, rel), os.path.join(dst, rel))
     open(os.path.join(dst, "utils", "__init__.py"), "a").close()

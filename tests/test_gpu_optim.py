@@ -85,3 +85,50 @@ def test_fused_radam_grad_scale_views_and_edge_sizes():
     e = torch.nn.Parameter(torch.zeros(0, 3, device=dev))
     e.grad = torch.zeros(0, 3, device=dev)
     fopt.FusedRAdam([e]).step()
+
+
+def test_fused_radam_nan_guards():
+    """train.py:244-253 folded into the step: nan_to_num on a named group's gradient == torch's nan_to_num followed
+    by RAdam; a NaN written into a `check_nan` group raises its flag (and only its flag); groups outside the two
+    name lists behave exactly as before."""
+    dev = torch.device("cuda:0")
+    init = _make(dev, seed=5)
+    pr = [torch.nn.Parameter(t.clone()) for _, t, _ in init]
+    po = [torch.nn.Parameter(t.clone()) for _, t, _ in init]
+    ref = torch.optim.RAdam([{"params": [p], "lr": lr, "name": n} for p, (n, _, lr) in zip(pr, init)], lr=0.001)
+    ours = fopt.FusedRAdam([{"params": [p], "lr": lr, "name": n} for p, (n, _, lr) in zip(po, init)], lr=0.001,
+                           check_nan=("xyz", "motion_xyz"), sanitize_grad=("motion_opacity_var",))
+    names = [n for n, _, _ in init]
+    iv = names.index("motion_opacity_var")
+    g = torch.Generator().manual_seed(11)
+    for step in range(1, 9):
+        for i, (a, b) in enumerate(zip(pr, po)):
+            gr = (torch.randn(a.shape, generator=g) * 1e-2).to(dev)
+            if i == iv:
+                gr.view(-1)[3] = float("nan")
+                gr.view(-1)[5] = float("inf")
+                gr.view(-1)[9] = float("-inf")
+                a.grad, b.grad = gr.nan_to_num(), gr.clone()      # the reference sanitises before optimizer.step()
+            else:
+                a.grad, b.grad = gr.clone(), gr.clone()
+        ref.step()
+        ours.step()
+        for n, a, b in zip(names, pr, po):
+            assert torch.allclose(a, b, rtol=2e-6, atol=5e-8, equal_nan=True), (step, n)
+        assert ours.nan_detected() == {"xyz": False, "motion_xyz": False}
+        assert not torch.isnan(po[iv]).any()
+    ours.poll_nan()
+    # a NaN gradient in one keyframe of one dynamic Gaussian -> NaN parameter -> flag of that group only
+    for a, b in zip(pr, po):
+        b.grad = torch.zeros_like(b)
+    po[names.index("motion_xyz")].grad[17, 4, 1] = float("nan")
+    po[names.index("f_rest")].grad[0, 0, 0] = float("nan")       # not a checked group
+    ours.step()
+    torch.cuda.synchronize()
+    assert ours.poll_nan() == {"xyz": False, "motion_xyz": False}     # first poll after the step: copy only queued
+    torch.cuda.synchronize()
+    assert ours.poll_nan() == {"xyz": False, "motion_xyz": True}
+    assert ours.nan_detected() == {"xyz": False, "motion_xyz": True}
+    assert torch.isnan(po[names.index("motion_xyz")][17, 4, 1])
+    ours.clear_nan()
+    assert ours.nan_detected() == {"xyz": False, "motion_xyz": False}

@@ -414,3 +414,45 @@ def test_segmented_sh_equals_concatenated(built, cull, split):
     with pytest.raises(RuntimeError):
         mod.GaussianRasterizer(rs)(means3D=inp["means3D"][:-1], means2D=torch.zeros(P - 1, 3, device=dev), dir3D=torch.zeros(P - 1, 3, device=dev),
                                    opacities=inp["opacities"][:-1], shs=seg, scales=inp["scales"][:-1], rotations=inp["rotations"][:-1])
+
+
+@pytest.mark.parametrize("used", ["color", "color+flow", "color+acc", "color+depth", "flow"])
+def test_absent_upstream_gradients_equal_zero_gradients(built, cull, used):
+    """Outputs the loss does not use reach backward as None (set_materialize_grads(False)), cross the C ABI
+    as NULL and select the compositing backward without depth / acc terms; the reference gets zero tensors
+    for them (__init__.py:110-178).  Every gradient must equal the one computed with explicit zeros (same
+    kernel arithmetic, only the exactly-zero terms are dropped), and must agree with the CPU oracle."""
+    mod = U.ours_module()
+    dev = "cuda"
+    sc = synth.make_config("C1d", pose="tilted")
+    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    P = inp["means3D"].shape[0]
+    rs = U.settings_for(mod, sc, dev)
+    go = {k: v.to(dev) for k, v in synth.grad_outputs(sc).items()}
+    g = torch.Generator().manual_seed(5)
+    go["grad_depth"] = (torch.randn(1, sc.cam.H, sc.cam.W, generator=g) * 1e-3).to(dev)
+    go["grad_acc"] = (torch.randn(1, sc.cam.H, sc.cam.W, generator=g) * 1e-3).to(dev)
+    names = ("grad_color", "grad_depth", "grad_flow", "grad_acc")
+    on = {"grad_color": "color" in used, "grad_depth": "depth" in used, "grad_flow": "flow" in used, "grad_acc": "acc" in used}
+
+    def run(explicit_zeros):
+        t = {k: inp[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        d3 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        out = mod.GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, dir3D=d3, opacities=t["opacities"], shs=t["shs"],
+                                         scales=t["scales"], rotations=t["rotations"])
+        outs = dict(grad_color=out[0], grad_depth=out[2], grad_flow=out[3], grad_acc=out[4])
+        if explicit_zeros:
+            torch.autograd.backward([outs[n] for n in names], [go[n] if on[n] else torch.zeros_like(go[n]) for n in names])
+        else:
+            torch.autograd.backward([outs[n] for n in names if on[n]], [go[n] for n in names if on[n]])
+        res = {k: v.grad.cpu().numpy() for k, v in t.items()}
+        res["means2D"] = m2.grad.cpu().numpy()
+        res["dir3D"] = d3.grad.cpu().numpy()
+        return res
+
+    a, b = run(True), run(False)
+    for k in a:
+        assert U.rel_err(b[k], a[k], U.grad_floor(a[k])) <= 2e-3, k
+    if used == "color":
+        assert float(np.abs(b["dir3D"]).max()) == 0.0           # no flow gradient: dL_ddir3D is exactly zero
