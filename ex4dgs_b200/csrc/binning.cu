@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
         const float4 a = rec[id].a;
         int x0, y0, x1, y1;
         tile_rect(a.x, a.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
-        area = (x1 - x0) * (y1 - y0);
         if (cull) {
             const float4 b = rec[id].b;
+            tight_rect(a.x, a.y, b.x, b.y, b.z, a.w, pad, x0, y0, x1, y1);     // the rectangle preprocess counted
             c = cull_prepare(a.x, a.y, b.x, b.y, b.z, a.w, x0, y0, x1 - x0, id, pad);
         } else {
             c.x0 = x0; c.y0 = y0; c.w = x1 - x0; c.id = id;
         }
+        area = (x1 - x0) * (y1 - y0);
     }
     int incl = area;
 #pragma unroll

@@ -30,6 +30,9 @@
 #ifndef EX_BWD_FAST_RCP
 #define EX_BWD_FAST_RCP 1       // T /= (1 - alpha) with MUFU.RCP: 1.011 vs 1.075 ms at C3, gradients within the 1e-3 budget
 #endif
+#ifndef EX_BWD_FAST_EXP
+#define EX_BWD_FAST_EXP 1       // backward recomputes G = exp(power) with MUFU.EX2 directly (see render_bwd.cu)
+#endif
 #ifndef EX_BWD_PPT
 #define EX_BWD_PPT 2            // pixels per thread in the backward compositing kernel (1: 8 warps x 8x4, 2: 4 warps x 8x8);
                                 // PPT = 1 needs EX_BWD_MINBLOCKS <= 4 (256-thread CTAs); measured 0.982 (1) vs 0.926 ms (2)
@@ -390,6 +393,53 @@ __device__ __forceinline__ bool cull_test(const CullCtx& c, int tx, int ty, floa
         qmin = fminf(qmin, q);
     }
     return fm(qmin, c.shrink) > c.tq;
+}
+
+// Conservative pre-filter in front of cull_test (EX4DGS_FLAG_TILE_CULL only): the reference's tile rectangle
+// is the square of half-width ceil(3 sigma_max) around the centre; the pixels that can pass `alpha >= 1/255`
+// lie inside the ellipse q(d) <= L with L = tq / shrink (same tq, shrink as cull_prepare), whose axis-aligned
+// bounding box has half-extents sqrt(2 L C / det), sqrt(2 L A / det) - much narrower than the square for
+// elongated or faint splats.  The rectangle is cut down to the tiles whose pixel-centre range (widened by
+// pad) meets that box.  Evaluated by preprocess (tiles_touched, hence the scan and num_rendered) and by the
+// duplicate kernel from the same stored floats with pinned operations, so both agree bit for bit; tiles it
+// drops would all be dropped by cull_test as well (guards: +1e-4 relative, +1e-3 + 1e-6 |c| absolute).
+__device__ __forceinline__ float approx_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void tight_rect(float cx, float cy, float A, float B, float C, float thr, float pad,
+                                           int& x0, int& y0, int& x1, int& y1)
+{
+    // MUFU-based reciprocal / square root (2 ulp, deterministic: both call sites execute the same instructions
+    // on the same inputs); the 1e-4 relative guard below is 400x their error
+    const float detc = fa(fm(A, C), -fm(B, B));
+    if (!((A > 0.f) && (C > 0.f) && (detc > 0.f) && (pad <= 4096.f))) return;
+    const float rdet = __fdividef(1.0f, detc);
+    const float sAC = fa(approx_sqrt(fm(A, C)), fabsf(B));
+    const float kappa = fm(fm(sAC, sAC), rdet);
+    const float shrink = fa(1.0f, -fm(2.01e-5f, kappa));
+    if (!(shrink > 0.5f)) return;
+    const float tq = fa(1e-3f, -thr);
+    if (!(tq > 0.f)) return;                       // nothing can pass anyway; cull_test sorts it out
+    const float twoL = fm(__fdividef(fm(2.0f, tq), shrink), rdet);
+    float ex = approx_sqrt(fm(twoL, C));
+    float ey = approx_sqrt(fm(twoL, A));
+    if (!(ex < 1e6f) || !(ey < 1e6f)) return;      // NaN / huge: keep the reference rectangle
+    ex = fa(fa(fm(ex, 1.0001f), 1e-3f), fm(fabsf(cx), 1e-6f));
+    ey = fa(fa(fm(ey, 1.0001f), 1e-3f), fm(fabsf(cy), 1e-6f));
+    // tile t holds pixel centres in [16 t - pad, 16 t + 15 + pad]
+    const float lx = fm(fa(fa(fa(cx, -ex), -pad), -15.0f), 0.0625f), hx = fm(fa(fa(cx, ex), pad), 0.0625f);
+    const float ly = fm(fa(fa(fa(cy, -ey), -pad), -15.0f), 0.0625f), hy = fm(fa(fa(cy, ey), pad), 0.0625f);
+    // clamp before the float -> int conversion (far off-screen centres)
+    const int tx0 = (int)ceilf(fmaxf(lx, -1.0f)), tx1 = (int)floorf(fminf(hx, 70000.0f)) + 1;
+    const int ty0 = (int)ceilf(fmaxf(ly, -1.0f)), ty1 = (int)floorf(fminf(hy, 70000.0f)) + 1;
+    x0 = max(x0, tx0); x1 = min(x1, tx1);
+    y0 = max(y0, ty0); y1 = min(y1, ty1);
+    if (x1 < x0) x1 = x0;
+    if (y1 < y0) y1 = y0;
 }
 
 // Warp-cooperative enumeration of the (lane, tile) items of 32 rectangles: `area` items per lane,

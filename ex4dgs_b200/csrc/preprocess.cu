@@ -105,12 +105,52 @@ __device__ __forceinline__ Cov2D cov2d_project(float mx, float my, float mz, con
     return o;
 }
 
+// Real SH basis of the view direction up to degree D (forward.cu:20-71).  The expressions are NOT pinned: the
+// forward image is bit-identical to the reference's because nvcc contracts them like the reference build does,
+// and that choice depends on the surrounding code (inlined into the two instantiations of the kernel the
+// degree >= 2 terms came out 1 ulp apart).  EX_PRE_FWD_TEMPLATE = 1 (default) compiles the function once
+// (__noinline__) so that both instantiations share one contraction - verified bit-identical to the reference
+// on every golden / live case; = 0 keeps a single kernel with a run-time test of p.seg.enabled (0.136 vs 0.127 ms).
+#ifndef EX_PRE_FWD_TEMPLATE
+#define EX_PRE_FWD_TEMPLATE 1
+#endif
+#if EX_PRE_FWD_TEMPLATE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+int sh_basis_fwd(int D, float dx, float dy, float dz, float* b)
+{
+    int nb = 1;
+    b[0] = kC0;
+    if (D > 0) {
+        b[1] = -kC1 * dy; b[2] = kC1 * dz; b[3] = -kC1 * dx; nb = 4;
+        if (D > 1) {
+            const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+            b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy);
+            b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy); nb = 9;
+            if (D > 2) {
+                b[9] = kC3[0] * dy * (3.0f * xx - yy);
+                b[10] = kC3[1] * xy * dz;
+                b[11] = kC3[2] * dy * (4.0f * zz - xx - yy);
+                b[12] = kC3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                b[13] = kC3[4] * dx * (4.0f * zz - xx - yy);
+                b[14] = kC3[5] * dz * (xx - yy);
+                b[15] = kC3[6] * dx * (xx - 3.0f * yy);
+                nb = 16;
+            }
+        }
+    }
+    return nb;
+}
+
 // SEG: the SH coefficients arrive as the model's four tensors (EX4DGS_FLAG_SH_SEGMENTED).  A template
 // parameter, not a run-time test of SEG: with the test inside, the contiguous-SH instantiation
 // pays for address selects in its inner loops (measured 0.122 -> 0.130 ms forward, 0.237 -> 0.277 ms backward).
-template <bool SEG>
+template <bool SEG_T>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p)
 {
+    const bool SEG = EX_PRE_FWD_TEMPLATE ? SEG_T : (p.seg.enabled != 0);
     __shared__ float s_cam[36];   // view[16] | proj[16] | campos[3]
     if (threadIdx.x < 16) s_cam[threadIdx.x] = __ldg(p.view + threadIdx.x);
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg(p.proj + threadIdx.x - 16);
@@ -176,8 +216,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         const float py = (float)((((double)ndc_y + 1.0) * (double)p.H - 1.0) * 0.5);
         int x0, y0, x1, y1;
         tile_rect(px, py, radius, p.grid_x, p.grid_y, x0, y0, x1, y1);
-        const uint32_t area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
-        if (area == 0) break;
+        if ((uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) == 0) break;
 
         // ---- colour
         float rgb[3];
@@ -188,26 +227,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
             dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
             const float* sh = SEG ? nullptr : p.shs + (size_t)idx * p.M * 3;
             float b[16];
-            int nb = 1;
-            b[0] = kC0;
-            if (p.D > 0) {
-                b[1] = -kC1 * dy; b[2] = kC1 * dz; b[3] = -kC1 * dx; nb = 4;
-                if (p.D > 1) {
-                    const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-                    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy);
-                    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy); nb = 9;
-                    if (p.D > 2) {
-                        b[9] = kC3[0] * dy * (3.0f * xx - yy);
-                        b[10] = kC3[1] * xy * dz;
-                        b[11] = kC3[2] * dy * (4.0f * zz - xx - yy);
-                        b[12] = kC3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                        b[13] = kC3[4] * dx * (4.0f * zz - xx - yy);
-                        b[14] = kC3[5] * dz * (xx - yy);
-                        b[15] = kC3[6] * dx * (xx - 3.0f * yy);
-                        nb = 16;
-                    }
-                }
-            }
+            const int nb = sh_basis_fwd(p.D, dx, dy, dz, b);
             float acc[3] = {0.f, 0.f, 0.f};
             if (SEG) {
                 // the model's own tensors, read in place: 3 floats of dc + 3*(nb-1) floats of the 180-byte rest row
@@ -266,9 +286,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
         const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
 
-        // with EX4DGS_FLAG_TILE_CULL the duplicate kernel keys culled instances to the dump tile;
-        // the count stays the full rectangle so that no second pass is needed before the scan
-        const uint32_t count = area;
+        // with EX4DGS_FLAG_TILE_CULL the rectangle is first cut down to the bounding box of the alpha >= 1/255
+        // ellipse (tight_rect); the duplicate kernel then keys the instances its exact test rejects to the
+        // dump tile, so that no second counting pass is needed before the scan.  A Gaussian whose box meets no
+        // pixel centre keeps its radius (it is "visible" to the caller, as in the reference) but enters no list.
+        if (p.flags & 1u)     // EX4DGS_FLAG_TILE_CULL
+            tight_rect(px, py, conA, conB, conC, thr, __ldg(p.pad_ptr), x0, y0, x1, y1);
+        const uint32_t count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
 
         SplatRec rc;
         rc.a = make_float4(px, py, depth, thr);
@@ -812,7 +836,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s)
 {
     if (p.P <= 0) return;
-    if (p.seg.enabled) preprocess_fwd_kernel<true><<<(p.P + 255) / 256, 256, 0, s>>>(p);
+    if (EX_PRE_FWD_TEMPLATE && p.seg.enabled) preprocess_fwd_kernel<true><<<(p.P + 255) / 256, 256, 0, s>>>(p);
     else preprocess_fwd_kernel<false><<<(p.P + 255) / 256, 256, 0, s>>>(p);
 }
 
