@@ -438,6 +438,10 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
         if group is not None:
             torch.distributed.all_reduce(l)
         frame.h_loss.copy_(l, non_blocking=True)
+    # handles for tests/test_gpu_train_iter.py (trajectory parity of the two arms)
+    step.params = dict(zip([n for n, _ in MODEL_GROUPS], params))
+    step.gaussians = gaussians
+    step.optimizer = opt
     return step, n_param
 
 

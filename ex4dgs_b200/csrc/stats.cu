@@ -14,7 +14,8 @@
 //          motion_reg * mean_{i, k>=1} |xyz_motion[i,0] - xyz_motion[i,k]|
 //      (rot_reg is 0.0 in arguments/__init__.py:136 and `if opt.rot_reg > 0` never runs.)  The reference
 //      lets autograd run slice, sub, norm, mean and their backward over the [Nd,K,3] keyframe tensor
-//      (eight passes); here the tensor is read once and its gradient read-modify-written once.  Sums are
+//      (eight passes); here the tensor is read once and its gradient read-modify-written once, one warp per
+//      [K,3] row, staged through shared memory so that both cross HBM as whole 128-bit lines.  Sums are
 //      reduced in a fixed order (per-block partials in double, then one block): bit-reproducible.
 #include "common.cuh"
 
@@ -74,12 +75,14 @@ __global__ void __launch_bounds__(256) iteration_stats_kernel(const __grid_const
 
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
+constexpr int kRegMaxK = 64;          // keyframes per row the staged path holds (2 x 768 B per warp); more: direct path
 
 // One warp per dynamic Gaussian row ([K,3] floats, contiguous) and one thread per static Gaussian; block
 // partial sums (double) go to part[2 * block + {0,1}].
 __global__ void __launch_bounds__(kRegThreads) regularizer_kernel(const __grid_constant__ RegParams p)
 {
     __shared__ double s_part[2][kRegWarps];
+    __shared__ __align__(16) float s_row[kRegWarps][2][kRegMaxK * 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const float gscale = p.dL_dloss ? __ldg(p.dL_dloss) : 1.0f;
@@ -103,21 +106,50 @@ __global__ void __launch_bounds__(kRegThreads) regularizer_kernel(const __grid_c
     if (p.motion_coef != 0.0f && p.K > 1) {
         const float c = p.motion_coef * gscale;        // motion_reg / (Nd (K - 1))
         const long long wid = (long long)blockIdx.x * kRegWarps + warp;
+        const int row_f = p.K * 3;                     // floats per row
+        // rows are staged through shared memory so that the keyframe tensor and its gradient cross HBM as whole
+        // 128-bit lines (a lane's own (x, y, z) triple sits at a 12-byte stride)
+        const bool staged = (p.K <= kRegMaxK) && (row_f % 4 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.xyz_motion) | reinterpret_cast<uintptr_t>(p.dL_dxyz_motion)) & 15) == 0;
+        float* sv = s_row[warp][0];
+        float* sg = s_row[warp][1];
         for (long long i = wid; i < p.Nd; i += (long long)gridDim.x * kRegWarps) {
-            const float* row = p.xyz_motion + i * (long long)p.K * 3;
-            float* grow = p.dL_dxyz_motion ? p.dL_dxyz_motion + i * (long long)p.K * 3 : nullptr;
-            const float x0 = __ldg(row), y0 = __ldg(row + 1), z0 = __ldg(row + 2);
+            const float* row = p.xyz_motion + i * (long long)row_f;
+            float* grow = p.dL_dxyz_motion ? p.dL_dxyz_motion + i * (long long)row_f : nullptr;
             float s0x = 0.f, s0y = 0.f, s0z = 0.f, sn = 0.f;
-            for (int k = 1 + lane; k < p.K; k += 32) {
-                const float dx = x0 - __ldg(row + 3 * k), dy = y0 - __ldg(row + 3 * k + 1), dz = z0 - __ldg(row + 3 * k + 2);
-                const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-                sn += n;
-                if (grow) {
-                    const float s = (n == 0.0f) ? 0.0f : c / n;
-                    const float gx = dx * s, gy = dy * s, gz = dz * s;     // d/d y_0 ; d/d y_k is the negative
-                    s0x += gx; s0y += gy; s0z += gz;
-                    if (p.accumulate_motion) { grow[3 * k] -= gx; grow[3 * k + 1] -= gy; grow[3 * k + 2] -= gz; }
-                    else { grow[3 * k] = -gx; grow[3 * k + 1] = -gy; grow[3 * k + 2] = -gz; }
+            if (staged) {
+                const int n4 = row_f / 4;
+                for (int f = lane; f < n4; f += 32) {
+                    reinterpret_cast<float4*>(sv)[f] = __ldg(reinterpret_cast<const float4*>(row) + f);
+                    if (grow) reinterpret_cast<float4*>(sg)[f] = p.accumulate_motion ? reinterpret_cast<const float4*>(grow)[f]
+                                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();
+                const float x0 = sv[0], y0 = sv[1], z0 = sv[2];
+                for (int k = 1 + lane; k < p.K; k += 32) {
+                    const float dx = x0 - sv[3 * k], dy = y0 - sv[3 * k + 1], dz = z0 - sv[3 * k + 2];
+                    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+                    sn += n;
+                    if (grow) {
+                        const float s = (n == 0.0f) ? 0.0f : c / n;
+                        const float gx = dx * s, gy = dy * s, gz = dz * s;     // d/d y_0 ; d/d y_k is the negative
+                        s0x += gx; s0y += gy; s0z += gz;
+                        sg[3 * k] -= gx; sg[3 * k + 1] -= gy; sg[3 * k + 2] -= gz;
+                    }
+                }
+            } else {
+                const float x0 = __ldg(row), y0 = __ldg(row + 1), z0 = __ldg(row + 2);
+                for (int k = 1 + lane; k < p.K; k += 32) {
+                    const float dx = x0 - __ldg(row + 3 * k), dy = y0 - __ldg(row + 3 * k + 1), dz = z0 - __ldg(row + 3 * k + 2);
+                    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+                    sn += n;
+                    if (grow) {
+                        const float s = (n == 0.0f) ? 0.0f : c / n;
+                        const float gx = dx * s, gy = dy * s, gz = dz * s;
+                        s0x += gx; s0y += gy; s0z += gz;
+                        if (p.accumulate_motion) { grow[3 * k] -= gx; grow[3 * k + 1] -= gy; grow[3 * k + 2] -= gz; }
+                        else { grow[3 * k] = -gx; grow[3 * k + 1] = -gy; grow[3 * k + 2] = -gz; }
+                    }
                 }
             }
 #pragma unroll
@@ -127,12 +159,17 @@ __global__ void __launch_bounds__(kRegThreads) regularizer_kernel(const __grid_c
                 s0z += __shfl_xor_sync(full, s0z, o);
                 sn += __shfl_xor_sync(full, sn, o);
             }
-            if (lane == 0) {
-                sum_motion += (double)sn;
+            if (lane == 0) sum_motion += (double)sn;
+            if (staged) {
                 if (grow) {
-                    if (p.accumulate_motion) { grow[0] += s0x; grow[1] += s0y; grow[2] += s0z; }
-                    else { grow[0] = s0x; grow[1] = s0y; grow[2] = s0z; }
+                    if (lane == 0) { sg[0] += s0x; sg[1] += s0y; sg[2] += s0z; }
+                    __syncwarp();
+                    for (int f = lane; f < row_f / 4; f += 32) reinterpret_cast<float4*>(grow)[f] = reinterpret_cast<const float4*>(sg)[f];
                 }
+                __syncwarp();                      // the buffers are reused by the warp's next row
+            } else if (lane == 0 && grow) {
+                if (p.accumulate_motion) { grow[0] += s0x; grow[1] += s0y; grow[2] += s0z; }
+                else { grow[0] = s0x; grow[1] = s0y; grow[2] = s0z; }
             }
         }
     }
@@ -152,14 +189,21 @@ __global__ void __launch_bounds__(kRegThreads) regularizer_kernel(const __grid_c
     }
 }
 
-__global__ void regularizer_finish_kernel(const double* part, int blocks, float static_coef, float motion_coef, float* out2)
+// fixed-order reduction of the per-block partials: thread t sums blocks t, t + 256, ... ; then a fixed tree
+__global__ void __launch_bounds__(256) regularizer_finish_kernel(const double* part, int blocks, float static_coef, float motion_coef, float* out2)
 {
-    // one thread: `blocks` is a few hundred
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < blocks; i++) { a += part[2 * i]; b += part[2 * i + 1]; }
-        out2[0] = (float)(a * (double)static_coef);
-        out2[1] = (float)(b * (double)motion_coef);
+    __shared__ double sa[256], sb[256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < blocks; i += 256) { a += part[2 * i]; b += part[2 * i + 1]; }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = (float)(sa[0] * (double)static_coef);
+        out2[1] = (float)(sb[0] * (double)motion_coef);
     }
 }
 
@@ -187,6 +231,6 @@ cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s)
     regularizer_kernel<<<blocks, kRegThreads, 0, s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    regularizer_finish_kernel<<<1, 32, 0, s>>>(p.part, blocks, p.static_coef, p.motion_coef, out2);
+    regularizer_finish_kernel<<<1, 256, 0, s>>>(p.part, blocks, p.static_coef, p.motion_coef, out2);
     return cudaGetLastError();
 }

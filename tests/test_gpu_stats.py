@@ -126,3 +126,41 @@ def test_regularizers_equal_oracle_and_accumulate(built, Ns, Nd, K):
     before = d.grad.clone()
     t0 = stats.regularizers_(d, mo, 0.0, 0.0)
     assert float(t0.abs().sum()) == 0.0 and torch.equal(before, d.grad)
+
+
+def test_stats_live_against_reference_class_on_gpu(built):
+    """The reference's UNMODIFIED CGaussianModel methods (oracle/_ref/callers/scene/c_gaussian_model.py, installed by
+    oracle/build_ref.py) and the verbatim train.py:196-212 block on CUDA tensors, against the fused kernel acting on a
+    second instance of the same class: the model object is used as it is, attribute names and shapes included."""
+    import bench
+    cls = bench.load_reference_model_class()
+    if cls is None:
+        pytest.skip("oracle/_ref/callers not installed (no /root/reference at build time)")
+    dev = torch.device("cuda")
+    Ns, Nd = 4001, 1777
+
+    def model():
+        g = cls.__new__(cls)
+        for k, v in fresh_state(Ns, Nd).items():
+            setattr(g, k, v.to(dev))
+        g._xyz = torch.zeros(Ns, 3, device=dev)
+        return g
+
+    ref, ours = model(), model()
+    for it in make_inputs(Ns, Nd, 4321, 3):
+        radii, grad, err = it["radii"].to(dev), it["grad"].to(dev), it["err"].to(dev)
+        vp, ve = SimpleNamespace(grad=grad), SimpleNamespace(grad=err)
+        gaussians, visibility_filter = ref, radii > 0
+        gaussians.mark_prune_stats(radii, ve)
+        if it["densify"]:
+            static_num = gaussians._xyz.shape[0]
+            static_vis_filter = visibility_filter[:static_num]
+            static_radii = radii[:static_num]
+            dynamic_vis_filter = visibility_filter[static_num:]
+            dynamic_radii = radii[static_num:]
+            gaussians.max_radii2D[static_vis_filter] = torch.max(gaussians.max_radii2D[static_vis_filter], static_radii[static_vis_filter])
+            gaussians.motion_max_radii2D[dynamic_vis_filter] = torch.max(gaussians.motion_max_radii2D[dynamic_vis_filter], dynamic_radii[dynamic_vis_filter])
+            gaussians.add_densification_stats(vp, static_vis_filter, dynamic_vis_filter, static_num)
+            gaussians.add_l1_ssim_stats(ve, static_vis_filter, dynamic_vis_filter, static_num, it["timestamp"])
+        stats.iteration_stats(ours, radii, grad, err, it["timestamp"], densify=it["densify"])
+    _compare(ours, {k: getattr(ref, k).cpu().numpy() for k in SO.ALL_NAMES}, "live ")
