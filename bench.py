@@ -185,6 +185,12 @@ class Frame:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.R = -1
         self.last = None
+        # the L1 loss of the e2e step: utils/loss_utils.py:22-25 (torch ops) for the reference arm, this repository's
+        # drop-in for it (ex4dgs_b200/loss.py::l1_loss, one kernel each way) for our arm
+        self.l1 = None
+        if getattr(mod, "__name__", "") == "ex4dgs_b200":
+            from ex4dgs_b200.loss import l1_loss
+            self.l1 = l1_loss
 
     def settings(self, view, proj, campos):
         cam = self.sc.cam
@@ -232,7 +238,7 @@ class Frame:
         rs = self.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
         color, radii, depth, flow, acc, idxs = self._raster(rs)
         main.wait_stream(self.copy_stream)
-        loss = (color - self.d_gt).abs().mean()
+        loss = self.l1(color, self.d_gt) if self.l1 is not None else torch.abs((color - self.d_gt)).mean()
         torch.autograd.backward([loss, flow], [None, self.go["grad_flow"]])
         l = loss.detach().reshape(1)
         if group is not None:
@@ -734,8 +740,9 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K,
-                    "what": "per frame: H2D camera (35 floats) + ground-truth image from pinned memory, forward, L1 loss, "
-                            "backward, loss (all-reduced over ranks) D2H; Gaussian parameters resident"},
+                    "what": "per frame: H2D camera (35 floats) + ground-truth image from pinned memory, forward, L1 loss "
+                            + ("(ex4dgs_b200.loss.l1_loss)" if args.impl == "ours" else "(utils/loss_utils.py l1_loss: torch abs/mean)")
+                            + ", backward, loss (all-reduced over ranks) D2H; Gaussian parameters resident"},
             "clocks": clocks}
     if train is not None:
         line["train_step"] = train

@@ -96,6 +96,9 @@ SIGNATURES = {
     "ex4dgs_iteration_stats": (_I, [_I, _I, _P, _P, _P, _F, _I, C.POINTER(StatsArrays), C.POINTER(StatsArrays), _P]),
     "ex4dgs_regularizer_scratch_bytes": (C.c_size_t, []),
     "ex4dgs_regularizers": (_I, [_I, _I, _I, _P, _P, _F, _F, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "ex4dgs_l1_scratch_bytes": (C.c_size_t, []),
+    "ex4dgs_l1_forward": (_I, [C.c_size_t, _P, _P, _P, _P, _P]),
+    "ex4dgs_l1_backward": (_I, [C.c_size_t, _P, _P, _P, _P, _P]),
     "ex4dgs_loss_scratch_bytes": (C.c_size_t, [_I, _I]),
     "ex4dgs_loss_forward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "ex4dgs_loss_backward": (_I, [_I, _I, _P, _P, _F, _P, _P, _P, _P]),

@@ -34,7 +34,16 @@ struct Readback {
         }
         return host;
     }
+    // event recorded right after the read-back copies: the host waits for it instead of the whole stream, so
+    // that work queued behind the copies (the speculative duplicate kernel) runs while the host wakes up
+    cudaEvent_t event()
+    {
+        if (!ev_ok) ev_ok = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+        return ev_ok ? ev : nullptr;
+    }
     ~Readback() { if (host) cudaFreeHost(host); }
+    cudaEvent_t ev = nullptr;
+    bool ev_ok = false;
 };
 thread_local Readback g_readback;
 // Measurement state is process-wide: autograd runs the backward on its own thread.
@@ -124,18 +133,26 @@ GeometryState carve_geometry(void* base, int P, size_t temp_bytes)
     return g;
 }
 
-BinningState carve_binning(void* base, int R, size_t temp_bytes)
+// Layout of the binning buffer.  The two SORTED arrays - what the compositing kernels, the backward and the tests
+// read - sit at the front at offsets that depend on R alone (point_list at 0); the two UNSORTED arrays, which only
+// live between the duplicate kernel and the sort, sit behind the space the sorted arrays would need at full capacity.
+// So a buffer sized for a guess `cap` >= R can be filled by the duplicate kernel before R is known on the host, and
+// everything read later is found from R.  With cap == R this is simply four consecutive arrays.
+BinningState carve_binning(void* base, int R, int cap, size_t temp_bytes)
 {
     BinningState b;
+    const size_t n = (size_t)(R > 0 ? R : 0), m = (size_t)(cap > R ? cap : (R > 0 ? R : 0));
     Carver c(base);
-    const size_t n = (size_t)(R > 0 ? R : 0);
-    b.tile_unsorted = c.take<uint16_t>(n);
-    b.val_unsorted = c.take<uint32_t>(n);
-    b.tile_sorted = c.take<uint16_t>(n);
     b.point_list = c.take<uint32_t>(n);
-    b.temp = c.take<char>(temp_bytes);
+    b.tile_sorted = c.take<uint16_t>(n);
+    Carver d(base);
+    d.take<uint32_t>(m);
+    d.take<uint16_t>(m);
+    b.val_unsorted = d.take<uint32_t>(m);
+    b.tile_unsorted = d.take<uint16_t>(m);
+    b.temp = d.take<char>(temp_bytes);
     b.temp_bytes = temp_bytes;
-    b.total = c.off + 256;
+    b.total = d.off + 256;
     return b;
 }
 
@@ -187,13 +204,13 @@ int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
 const char* ex4dgs_last_error(void) { return g_err; }
 
 size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
-size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, binning_stage2_temp_bytes(R)).total; }
+size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R)).total; }
 size_t ex4dgs_image_bytes(int width, int height) { return carve_image(nullptr, width, height).total; }
 
 int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_desc* out, int max)
 {
     const GeometryState g = carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1));
-    const BinningState b = carve_binning(nullptr, R, binning_stage2_temp_bytes(R));
+    const BinningState b = carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R));
     const ImageState im = carve_image(nullptr, width, height);
     const size_t n = (size_t)P, r = (size_t)(R > 0 ? R : 0), px = (size_t)width * height;
     const size_t tiles = (size_t)((width + EX_TILE - 1) / EX_TILE) * ((height + EX_TILE - 1) / EX_TILE);
@@ -347,35 +364,47 @@ int ex4dgs_forward(
         if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
         CK(cudaMemcpyAsync(rb, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(rb + 1, geom.meta + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning
-        // buffer sized from the previous frame of this thread (+25 %): the allocator callback (a trip
-        // into Python) then overlaps the device work instead of extending the idle gap after the sync.
-        if (g_last_R > 0) {
+        cudaEvent_t rb_ev = g_readback.event();
+        if (rb_ev) CK(cudaEventRecord(rb_ev, s));
+        // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning buffer sized
+        // from the previous frames of this thread (+25 %) and queue the duplicate kernel into it (its grid
+        // depends on P only; entries beyond the guessed capacity are dropped): the allocator callback (a trip
+        // into Python), the host's wake-up after the wait and the launches of the sort then overlap device work
+        // instead of leaving the GPU idle between the scan and the duplicate kernel.
+        if (g_last_R > 0 && rb_ev) {
             const long long guess = (long long)g_last_R + g_last_R / 4 + 65536;
             if (guess < 0x7fffffffLL) {
                 spec_R = (int)guess;
-                const size_t spec_bytes = carve_binning(nullptr, spec_R, binning_stage2_temp_bytes(spec_R)).total;
+                const size_t spec_temp = binning_stage2_temp_bytes(spec_R);
+                const size_t spec_bytes = carve_binning(nullptr, spec_R, spec_R, spec_temp).total;
                 spec_base = binningBuffer(binning_user, spec_bytes);
                 if (!spec_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", spec_bytes);
+                const BinningState sb = carve_binning(align256(spec_base), 0, spec_R, spec_temp);
+                CK(binning_duplicate(geom, sb, radii, P, spec_R, grid_x, grid_y, flags, s));
             }
         }
-        CK(cudaStreamSynchronize(s));
+        if (rb_ev) CK(cudaEventSynchronize(rb_ev));
+        else CK(cudaStreamSynchronize(s));
         R = (int)rb[0];
         flow32 = rb[1];
-        g_last_R = R;
+        // sizing hint for the next frame: follows R upwards at once, downwards slowly (views alternate in training)
+        g_last_R = R > g_last_R ? R : (int)(((long long)g_last_R * 15 + R) / 16);
     }
 
-    const size_t temp2 = binning_stage2_temp_bytes(R);
+    const bool spec_hit = spec_base != nullptr && R <= spec_R;
+    const int cap = spec_hit ? spec_R : R;
+    const size_t temp2 = binning_stage2_temp_bytes(cap);
     void* bin_base = spec_base;
-    if (bin_base == nullptr || R > spec_R) {
-        const size_t bin_bytes = carve_binning(nullptr, R, temp2).total;
+    if (!spec_hit) {
+        const size_t bin_bytes = carve_binning(nullptr, R, R, temp2).total;
         bin_base = binningBuffer(binning_user, bin_bytes);
         if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
     }
-    bin = carve_binning(align256(bin_base), R, temp2);     // arrays are laid out from R alone (temp is last)
+    bin = carve_binning(align256(bin_base), R, cap, temp2);     // sorted arrays are laid out from R alone
 
     if (P > 0) {
-        CK(binning_stage2(geom, bin, img, radii, P, R, grid_x, grid_y, flags, s));
+        if (!spec_hit) CK(binning_duplicate(geom, bin, radii, P, R, grid_x, grid_y, flags, s));   // no guess, or it was too small
+        CK(binning_sort_ranges(bin, img, R, grid_x, grid_y, flags, s));
         g_launches += (R > 0) ? 2 : 0;
     } else {
         CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
@@ -422,7 +451,7 @@ int ex4dgs_backward(
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
     // the CUB temp areas are the last sub-arrays and are not used by the backward
     const GeometryState geom = carve_geometry(align256(geom_buffer), P, 0);
-    const BinningState bin = carve_binning(align256(binning_buffer), R, 0);
+    const BinningState bin = carve_binning(align256(binning_buffer), R, R, 0);
     const ImageState img = carve_image(align256(image_buffer), width, height);
 
     PreprocessBwdParams bp;
@@ -575,6 +604,28 @@ int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, d
                       double grad_scale, void* stream)
 {
     return ex4dgs_radam_step_ex(tensors, n, beta1, beta2, eps, grad_scale, 0u, 0u, nullptr, stream);
+}
+
+size_t ex4dgs_l1_scratch_bytes(void) { return l1_scratch_bytes(); }
+
+int ex4dgs_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out_loss, void* stream)
+{
+    g_err[0] = 0;
+    if (n == 0 || !a || !b || !scratch || !out_loss) return fail(EX4DGS_ERR_INVALID, "l1_forward: bad arguments");
+    cudaError_t e = launch_l1_forward(n, a, b, scratch, out_loss, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "l1_forward: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return EX4DGS_OK;
+}
+
+int ex4dgs_l1_backward(size_t n, const float* a, const float* b, const float* dL_dloss, float* dL_da, void* stream)
+{
+    g_err[0] = 0;
+    if (n == 0 || !a || !b || !dL_dloss || !dL_da) return fail(EX4DGS_ERR_INVALID, "l1_backward: bad arguments");
+    cudaError_t e = launch_l1_backward(n, a, b, dL_dloss, dL_da, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "l1_backward: %s", cudaGetErrorString(e));
+    g_launches += 1;
+    return EX4DGS_OK;
 }
 
 int ex4dgs_iteration_stats(int Ns, int Nd, const int* radii, const float* grad_means2D, const float* grad_error,

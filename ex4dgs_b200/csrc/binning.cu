@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
                                                                 const uint32_t* __restrict__ offsets,
                                                                 const SplatRec* __restrict__ rec, const int* __restrict__ radii,
                                                                 int grid_x, int grid_y, unsigned flags, const float* __restrict__ pad_ptr,
-                                                                uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out)
+                                                                uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out, uint32_t cap)
 {
     __shared__ CullCtx s_ctx[kDupThreads / 32][32];
     __shared__ int s_prefix[kDupThreads / 32][32];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
         }
         // culled instances keep their slot (the scan counted the full rectangle) but are keyed to
         // the dump tile 0xFFFF, which the stable tile sort moves behind every real tile
-        if (item < total) {
+        if (item < total && wbase + item < cap) {      // cap: capacity of a speculatively sized buffer (api.cu)
             tile_out[wbase + item] = keep ? tile : (uint16_t)0xFFFF;
             val_out[wbase + item] = id;
         }
@@ -223,16 +223,22 @@ cudaError_t binning_stage1(const GeometryState& g, int P, cudaStream_t s)
     return cub::DeviceScan::InclusiveSum(g.temp, tb, it, g.offsets, P, s);
 }
 
-cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const ImageState& img,
-                           const int* radii, int P, int R, int grid_x, int grid_y, unsigned flags,
-                           cudaStream_t s)
+cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, const int* radii, int P, int cap,
+                              int grid_x, int grid_y, unsigned flags, cudaStream_t s)
+{
+    if (P <= 0 || cap <= 0) return cudaSuccess;
+    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
+        P, g.order, g.key_sorted, g.offsets, g.rec, radii, grid_x, grid_y, flags,
+        reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted, (uint32_t)cap);
+    return cudaGetLastError();
+}
+
+cudaError_t binning_sort_ranges(const BinningState& b, const ImageState& img, int R, int grid_x, int grid_y,
+                                unsigned flags, cudaStream_t s)
 {
     const int tiles = grid_x * grid_y;
     cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, s);
     if (e != cudaSuccess || R <= 0) return e;
-    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
-        P, g.order, g.key_sorted, g.offsets, g.rec, radii, grid_x, grid_y, flags,
-        reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted);
     size_t tb = b.temp_bytes;
     const int bit = (int)higher_msb((uint32_t)tiles);
     const bool cull = (flags & 1u) != 0;

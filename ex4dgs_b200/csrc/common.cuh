@@ -132,7 +132,7 @@ struct ImageState {
 };
 
 GeometryState carve_geometry(void* base, int P, size_t temp_bytes);
-BinningState carve_binning(void* base, int R, size_t temp_bytes);
+BinningState carve_binning(void* base, int R, int cap, size_t temp_bytes);
 ImageState carve_image(void* base, int width, int height);
 
 // ---- kernel parameter blocks ---------------------------------------------------------------------
@@ -264,6 +264,10 @@ struct RAdamTensorDesc {
 cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, double beta2, double eps, double grad_scale,
                          int* nan_flags, cudaStream_t s);
 
+size_t l1_scratch_bytes();
+cudaError_t launch_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out, cudaStream_t s);
+cudaError_t launch_l1_backward(size_t n, const float* a, const float* b, const float* g, float* da, cudaStream_t s);
+
 // per-iteration statistics and regularisers (stats.cu)
 struct StatsArrays {          // one set for the static Gaussians, one for the dynamic ones
     float* max_radii2D;
@@ -307,10 +311,13 @@ size_t binning_stage1_temp_bytes(int P);
 size_t binning_stage2_temp_bytes(int R);
 // sort Gaussians by depth bits, scan tiles_touched in that order; returns cudaError
 cudaError_t binning_stage1(const GeometryState& g, int P, cudaStream_t s);
-// emit (tile, id) pairs in depth order, stable-sort by tile, find per-tile ranges
-cudaError_t binning_stage2(const GeometryState& g, const BinningState& b, const ImageState& img,
-                           const int* radii, int P, int R, int grid_x, int grid_y, unsigned flags,
-                           cudaStream_t s);
+// emit (tile, id) pairs in depth order (entries at positions >= cap are dropped: speculative launch before the
+// instance count is known on the host) ...
+cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, const int* radii, int P, int cap,
+                              int grid_x, int grid_y, unsigned flags, cudaStream_t s);
+// ... stable-sort the R pairs by tile, find per-tile ranges
+cudaError_t binning_sort_ranges(const BinningState& b, const ImageState& img, int R, int grid_x, int grid_y,
+                                unsigned flags, cudaStream_t s);
 
 // ---- tile rectangle (auxiliary.h:46-56), shared by preprocess and the duplicate kernel -----------------
 __device__ __forceinline__ void tile_rect(float px, float py, int radius, int grid_x, int grid_y,

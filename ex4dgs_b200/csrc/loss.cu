@@ -274,3 +274,102 @@ cudaError_t launch_loss_backward(int W, int H, const float* img, const float* gt
     return cudaGetLastError();
 }
 
+// ---- plain L1 loss (utils/loss_utils.py:22-25: torch.abs(network_output - gt).mean()) ---------------------
+// What an L1-only training or evaluation step computes around the rasterizer.  torch: sub, abs, mean forward and
+// fill, div, sign, mul backward - seven element-wise passes (~7 N floats of traffic each way); here one read of both
+// images per direction.  Per-block partial sums in double, reduced in a fixed order (bit-reproducible).
+namespace {
+
+constexpr int kL1Threads = 256;
+
+__global__ void __launch_bounds__(kL1Threads) l1_fwd_kernel(size_t n, const float* __restrict__ a, const float* __restrict__ b,
+                                                             double* __restrict__ part)
+{
+    __shared__ double s_w[kL1Threads / 32];
+    double acc = 0.0;
+    const size_t n4 = n / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+    const size_t stride = (size_t)gridDim.x * kL1Threads;
+    if (vec) {
+        for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n4; i += stride) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+            acc += (double)(fabsf(x.x - y.x) + fabsf(x.y - y.y)) + (double)(fabsf(x.z - y.z) + fabsf(x.w - y.w));
+        }
+        for (size_t i = n4 * 4 + (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += stride) acc += (double)fabsf(a[i] - b[i]);
+    } else {
+        for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += stride) acc += (double)fabsf(a[i] - b[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kL1Threads / 32; w++) t += s_w[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) l1_finish_kernel(const double* __restrict__ part, int blocks, double inv_n, float* out)
+{
+    __shared__ double s[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < blocks; i += 256) t += part[i];
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (float)(s[0] * inv_n);
+}
+
+// dL/da = sgn(a - b) * (g / n)   (torch: abs backward = grad * sgn(x), sgn(0) = 0; mean backward = grad / n, which
+// torch's division-by-a-scalar kernel evaluates as grad * (1.0f / n): reproduced, the gradient is bit-identical)
+__global__ void __launch_bounds__(kL1Threads) l1_bwd_kernel(size_t n, const float* __restrict__ a, const float* __restrict__ b,
+                                                             const float* __restrict__ g, float n_f, float* __restrict__ da)
+{
+    const float s = __fmul_rn(__ldg(g), __fdiv_rn(1.0f, n_f));
+    const size_t n4 = n / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+    const size_t stride = (size_t)gridDim.x * kL1Threads;
+    auto sg = [s](float d) { return d > 0.f ? s : (d < 0.f ? -s : (d == 0.f ? 0.f * s : d * s)); };   // NaN propagates
+    if (vec) {
+        for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n4; i += stride) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+            reinterpret_cast<float4*>(da)[i] = make_float4(sg(x.x - y.x), sg(x.y - y.y), sg(x.z - y.z), sg(x.w - y.w));
+        }
+        for (size_t i = n4 * 4 + (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += stride) da[i] = sg(a[i] - b[i]);
+    } else {
+        for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += stride) da[i] = sg(a[i] - b[i]);
+    }
+}
+
+int l1_blocks()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * 8;
+}
+
+}  // namespace
+
+size_t l1_scratch_bytes() { return (size_t)l1_blocks() * sizeof(double) + 256; }
+
+cudaError_t launch_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out, cudaStream_t s)
+{
+    double* part = reinterpret_cast<double*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    const int blocks = l1_blocks();
+    l1_fwd_kernel<<<blocks, kL1Threads, 0, s>>>(n, a, b, part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    l1_finish_kernel<<<1, 256, 0, s>>>(part, blocks, 1.0 / (double)n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_l1_backward(size_t n, const float* a, const float* b, const float* g, float* da, cudaStream_t s)
+{
+    l1_bwd_kernel<<<l1_blocks(), kL1Threads, 0, s>>>(n, a, b, g, (float)n, da);
+    return cudaGetLastError();
+}

@@ -66,6 +66,56 @@ class _PhotometricLoss(torch.autograd.Function):
         return grad, None, None
 
 
+class _L1Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, network_output, gt):
+        if not network_output.is_cuda:
+            raise RuntimeError("ex4dgs_b200: the fused loss is CUDA-only")
+        if gt.shape != network_output.shape:
+            raise ValueError("l1_loss: shapes differ: %s vs %s" % (tuple(network_output.shape), tuple(gt.shape)))
+        lib = _lib.load()
+        dev = network_output.device
+        a = network_output.detach().float().contiguous()
+        b = gt.detach().float().contiguous()
+        out = torch.empty(1, device=dev)
+        sc = _l1_scratch.get(dev)
+        if sc is None:
+            sc = _l1_scratch[dev] = torch.empty(int(lib.ex4dgs_l1_scratch_bytes()), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if a.numel() == 0:
+            return torch.full((), float("nan"), device=dev)            # torch: mean of an empty tensor
+        with torch.cuda.device(dev):
+            rc = lib.ex4dgs_l1_forward(a.numel(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), out.data_ptr(), C.c_void_p(stream))
+        if rc < 0:
+            raise RuntimeError("ex4dgs_l1_forward failed (%d): %s" % (rc, _lib.last_error()))
+        ctx.save_for_backward(a, b)
+        ctx.shape = network_output.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = _lib.load()
+        a, b = ctx.saved_tensors
+        dev = a.device
+        g = g_loss.detach().float().reshape(1).contiguous()
+        grad = torch.empty_like(a)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.ex4dgs_l1_backward(a.numel(), a.data_ptr(), b.data_ptr(), g.data_ptr(), grad.data_ptr(), C.c_void_p(stream))
+        if rc < 0:
+            raise RuntimeError("ex4dgs_l1_backward failed (%d): %s" % (rc, _lib.last_error()))
+        return grad.view(ctx.shape), None
+
+
+_l1_scratch = {}
+
+
+def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """utils/loss_utils.py:22-25 `torch.abs((network_output - gt)).mean()` - one kernel each way instead of torch's
+    seven element-wise passes.  The gradient flows to `network_output` (the rendered image); `gt` is data."""
+    return _L1Loss.apply(network_output, gt)
+
+
 def photometric_loss(image: torch.Tensor, gt_image: torch.Tensor, lambda_dssim: float = 0.2):
     """(loss, Ll1, ssim_value, l1_errors[H,W], ssim_errors[H,W]); see the module docstring."""
     return _PhotometricLoss.apply(image, gt_image, lambda_dssim)

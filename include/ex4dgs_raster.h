@@ -240,6 +240,13 @@ int ex4dgs_loss_forward(int width, int height, const float* image, const float* 
 int ex4dgs_loss_backward(int width, int height, const float* image, const float* gt_image, float lambda_dssim,
                          const char* scratch, const float* dL_dloss, float* dL_dimage, void* stream);
 
+/* Plain L1 loss, utils/loss_utils.py:22-25 `torch.abs((network_output - gt)).mean()` over n floats: value
+ * (device float) and, in the backward, dL_da = sgn(a - b) * dL_dloss / n.  scratch: ex4dgs_l1_scratch_bytes()
+ * device bytes.  Fixed-order double accumulation (bit-reproducible). */
+size_t ex4dgs_l1_scratch_bytes(void);
+int ex4dgs_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out_loss, void* stream);
+int ex4dgs_l1_backward(size_t n, const float* a, const float* b, const float* dL_dloss, float* dL_da, void* stream);
+
 /* ---- optimizer step ------------------------------------------------
  * Replaces `gaussians.optimizer.step()` of the reference's training iteration (train.py:250): the
  * optimizer is torch.optim.RAdam(l, lr=0.001) over 15 single-tensor parameter groups with per-group

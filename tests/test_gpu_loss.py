@@ -113,3 +113,31 @@ def test_loss_drives_the_rasterizer_backward(built):
     (loss + flow.mean() * 0).backward()
     assert torch.isfinite(means.grad).all() and means.grad.abs().sum() > 0
     assert torch.isfinite(opac.grad).all()
+
+
+@pytest.mark.parametrize("shape", [(3, 1014, 1352), (3, 37, 53), (7,), (1, 4099)])
+def test_l1_loss_equals_torch(shape):
+    """ex4dgs_b200.loss.l1_loss == utils/loss_utils.py:22-25 `torch.abs((network_output - gt)).mean()`: value to float
+    rounding (double accumulation here), gradient bit for bit (sgn(a - b) * g / n, sgn(0) = 0), unaligned views, an
+    upstream gradient other than 1, bit-reproducible."""
+    from ex4dgs_b200.loss import l1_loss
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(sum(shape))
+    n = int(np.prod(shape))
+    base_a = torch.rand(n + 1, generator=g).to(dev)
+    base_b = torch.rand(n + 1, generator=g).to(dev)
+    base_b[1 + 5 % n] = base_a[1 + 5 % n]                          # an exact zero difference
+    for off in (0, 1):                                             # off = 1: views at +4 bytes -> the scalar path
+        b = base_b.clone()[off:off + n].view(shape)
+        a1 = base_a.clone()[off:off + n].view(shape).requires_grad_(True)
+        a2 = base_a.clone()[off:off + n].view(shape).requires_grad_(True)
+        assert (a2.data_ptr() % 16 == 0) == (off == 0)
+        ref = torch.abs((a1 - b)).mean()
+        (ref * 0.37).backward()
+        ours = l1_loss(a2, b)
+        (ours * 0.37).backward()
+        assert abs(float(ours.detach()) - float(ref.detach())) <= 2e-6 * abs(float(ref.detach()))
+        assert torch.equal(a2.grad, a1.grad)
+        assert torch.equal(l1_loss(a2.detach(), b), ours.detach())
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        l1_loss(torch.zeros(3), torch.zeros(3))
