@@ -775,7 +775,23 @@ def main():
                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[3],
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                            "note": "the kernel is instruction-issue-bound (ncu: ~84 % issue slots, ~4 % DRAM): see profiles/SUMMARY.md"}
+                            "note": "the kernel is instruction-issue-bound (ncu: 81 % issue slots, 5 % DRAM): see issue_slots and profiles/SUMMARY.md"}
+        # what actually bounds the two compositing kernels: warp instructions issued (smsp__inst_executed.sum of the committed
+        # ncu capture - a property of the workload, identical in every launch) over the live kernel time, against the SMs'
+        # issue rate (4 schedulers x 1 warp instruction per clock x SM count x the SM clock measured under load)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            props = torch.cuda.get_device_properties(dev)
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = props.multi_processor_count * 4 * mhz * 1e6
+            line["issue_slots"] = {
+                k: {"warp_inst_per_launch": tj[k + "_kernel"]["inst_executed_per_launch"], "kernel_ms": ms,
+                    "achieved_Ginst_s": tj[k + "_kernel"]["inst_executed_per_launch"] / (ms * 1e-3) / 1e9,
+                    "peak_Ginst_s": peak_issue / 1e9,
+                    "frac": tj[k + "_kernel"]["inst_executed_per_launch"] / (ms * 1e-3) / peak_issue}
+                for k, ms in (("render_fwd", stage_ms[3]), ("render_bwd", stage_ms[4])) if ms > 0 and args.workload == "C3" and args.tile_cull}
+        except Exception:
+            pass
         names = ["preprocess_fwd", "depth_sort_scan", "sync_duplicate_tilesort_ranges", "render_fwd", "render_bwd", "preprocess_bwd"]
         line["stage_ms"] = dict(zip(names, stage_ms))
         # algorithmic bytes per stage (with this design's record sizes) against the same HBM peak
