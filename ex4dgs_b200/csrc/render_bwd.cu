@@ -8,16 +8,20 @@
 //
 // B200 design (DESIGN.md "render backward"):
 //  * the reference issues 14 float atomicAdd per contributing (pixel, splat) pair
-//    (backward.cu:613-679).  Here the 13 distinct values of a splat are first reduced across the
-//    32 pixels of a warp with a 16-value butterfly (16 SHFL instead of 13x5), the 8 warps of the
-//    tile deposit their partial sums in private shared-memory slices (no shared atomics), and one
-//    thread per (splat, 4-value group) folds the 8 slices and issues a single 16-byte vector
-//    reduction (REDG.E.ADD.F32x4) into a 64-byte per-Gaussian accumulator: at most 4 global
-//    reductions per (tile, splat) instead of 14 per (pixel, splat);
+//    (backward.cu:613-679).  Here a lane owns PPT = 2 pixels, sums their gradient terms in registers, the 13
+//    distinct values of a splat are reduced across the warp with a 16-value butterfly (16 SHFL instead of
+//    13x5) and 13 lanes issue ONE warp-level reduction instruction (REDG.E.ADD.F32) into the splat's 64-byte
+//    accumulator line: one butterfly + one reduction per (64 pixels, splat) instead of 14 atomics per
+//    (pixel, splat); constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian when the line is read;
 //  * traversal starts at the tile's largest `n_contrib` instead of the end of the range
 //    (backward.cu:552-577 re-loads the whole range and skips entries one by one);
-//  * splat records are gathered with TMA bulk copies (48 bytes per splat, mbarrier-tracked) one
-//    sub-batch ahead.
+//  * splat records are gathered with TMA bulk copies (48 bytes per splat, mbarrier-tracked) kAhead
+//    sub-batches ahead through a ring of kRing buffers guarded by full / empty mbarriers: no block barrier in
+//    the loop, the warps of a tile may drift kRing - kAhead sub-batches apart;
+//  * per warp and sub-batch the splats that cannot touch the warp's 8x8 pixel block are dropped first
+//    (block_reject, exact), as in the forward;
+//  * NULL upstream gradients for depth / acc (autograd: "not used by the loss") select an instantiation
+//    without those terms.
 #include "common.cuh"
 
 namespace {
@@ -42,12 +46,6 @@ constexpr int kUnroll = EX_BWD_UNROLL;
 __device__ __forceinline__ void red_add_f32(float* addr, float v)
 {
     asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float4 v)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
 }
 
 // Reduce 16 per-lane value slots over the warp; afterwards lane L holds the total of slot
