@@ -102,3 +102,35 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "liboracle" not in src and "cpu_raster" not in src, f
+
+
+def test_training_side_entry_points_reject_bad_arguments_before_touching_cuda(built):
+    """ex4dgs_iteration_stats / ex4dgs_regularizers / ex4dgs_l1_* / ex4dgs_radam_step_ex validate their arguments on
+    the host and report through ex4dgs_last_error (no GPU needed to see that)."""
+    from ex4dgs_b200 import _lib
+    lib = _lib.load()
+    st = _lib.StatsArrays()
+    assert lib.ex4dgs_iteration_stats(-1, 0, None, None, None, 0.0, 1, ctypes.byref(st), ctypes.byref(st), None) < 0
+    assert "negative" in _lib.last_error()
+    assert lib.ex4dgs_iteration_stats(0, 0, None, None, None, 0.0, 1, None, None, None) == 0          # empty model: nothing to do
+    assert lib.ex4dgs_iteration_stats(4, 0, None, None, None, 0.0, 1, ctypes.byref(st), None, None) < 0
+    assert "required" in _lib.last_error()
+    buf = (ctypes.c_int * 4)()
+    fbuf = (ctypes.c_float * 12)()
+    p, f = ctypes.addressof(buf), ctypes.addressof(fbuf)
+    assert lib.ex4dgs_iteration_stats(4, 0, p, f, None, 0.0, 1, ctypes.byref(st), None, None) < 0     # densify needs the arrays
+    assert "NULL" in _lib.last_error()
+    assert lib.ex4dgs_regularizers(4, 0, 0, f, None, 1e-4, 0.0, None, None, 0, None, 0, None, None, None) < 0
+    assert "required" in _lib.last_error()
+    assert lib.ex4dgs_regularizers(-1, 0, 0, None, None, 0.0, 0.0, None, None, 0, None, 0, f, f, None) < 0
+    assert lib.ex4dgs_l1_forward(0, f, f, f, f, None) < 0 and "bad arguments" in _lib.last_error()
+    assert lib.ex4dgs_l1_backward(12, f, f, None, f, None) < 0
+    t = (_lib.RAdamTensor * 1)()
+    t[0].param = t[0].grad = t[0].exp_avg = t[0].exp_avg_sq = f
+    t[0].numel, t[0].lr, t[0].step = 12, 1e-3, 1
+    assert lib.ex4dgs_radam_step_ex(t, 1, 0.9, 0.999, 1e-8, 1.0, 1, 0, None, None) < 0                # check mask without flags
+    assert "nan_flags" in _lib.last_error()
+    assert lib.ex4dgs_radam_step_ex(t, 33, 0.9, 0.999, 1e-8, 1.0, 0, 0, None, None) < 0
+    t[0].step = 0
+    assert lib.ex4dgs_radam_step_ex(t, 1, 0.9, 0.999, 1e-8, 1.0, 0, 0, None, None) < 0 and "step" in _lib.last_error()
+    assert lib.ex4dgs_regularizer_scratch_bytes() >= 2 * 8 and lib.ex4dgs_l1_scratch_bytes() >= 8
