@@ -1,0 +1,151 @@
+/* CPU restatement of the exact-output tile culling of ex4dgs_b200 (TEST INFRASTRUCTURE, see oracle/README.md):
+ *   tile_rect      the reference's rectangle, auxiliary.h:46-56 (getRect)
+ *   tight_rect     the bounding-box cut of ex4dgs_b200/csrc/common.cuh
+ *   cull_prepare / cull_test   the exact per-tile test of ex4dgs_b200/csrc/common.cuh
+ * followed by a brute-force verifier: for every (splat, tile) instance of the reference rectangle that the two steps
+ * drop, the compositing loop's own arithmetic (forward.cu:365-381: power with the FMA placement of the reference build,
+ * alpha = min(0.99, o * exp(power)), the `power > 0` and `alpha < 1/255` rejections) is evaluated at all 256 pixel
+ * centres of the tile, each shifted to the four corners and the centre of the +-pad subpixel box (power is a concave
+ * quadratic in the pixel position, so its maximum over the pad box is bounded by the value at the pixel nearest to the
+ * splat centre - also sampled): a dropped instance with a contributing pixel is a violation.  Float operations are
+ * spelled out one by one (compiled with -ffp-contract=off) so that they round like the CUDA code; where the CUDA code
+ * uses MUFU approximations (tight_rect) the exact operation is used here - its guard bands are 400x wider than the
+ * difference. */
+#include <math.h>
+#include <stdint.h>
+
+#define TILE 16
+
+static void tile_rect(float px, float py, int radius, int gx, int gy, int* x0, int* y0, int* x1, int* y1)
+{
+    const float r = (float)radius;
+    int ax0 = (int)((px - r) * 0.0625f), ay0 = (int)((py - r) * 0.0625f);
+    int ax1 = (int)((((px + r) + 16.0f) - 1.0f) * 0.0625f), ay1 = (int)((((py + r) + 16.0f) - 1.0f) * 0.0625f);
+    *x0 = ax0 < 0 ? 0 : (ax0 > gx ? gx : ax0);
+    *y0 = ay0 < 0 ? 0 : (ay0 > gy ? gy : ay0);
+    *x1 = ax1 < 0 ? 0 : (ax1 > gx ? gx : ax1);
+    *y1 = ay1 < 0 ? 0 : (ay1 > gy ? gy : ay1);
+}
+
+static void tight_rect(float cx, float cy, float A, float B, float C, float thr, float pad, int* x0, int* y0, int* x1, int* y1)
+{
+    const float detc = A * C - B * B;
+    if (!((A > 0.f) && (C > 0.f) && (detc > 0.f) && (pad <= 4096.f))) return;
+    const float rdet = 1.0f / detc;
+    const float sAC = sqrtf(A * C) + fabsf(B);
+    const float kappa = (sAC * sAC) * rdet;
+    const float shrink = 1.0f - 2.01e-5f * kappa;
+    if (!(shrink > 0.5f)) return;
+    const float tq = 1e-3f - thr;
+    if (!(tq > 0.f)) return;
+    const float twoL = ((2.0f * tq) / shrink) * rdet;
+    float ex = sqrtf(twoL * C), ey = sqrtf(twoL * A);
+    if (!(ex < 1e6f) || !(ey < 1e6f)) return;
+    ex = (ex * 1.0001f + 1e-3f) + fabsf(cx) * 1e-6f;
+    ey = (ey * 1.0001f + 1e-3f) + fabsf(cy) * 1e-6f;
+    const float lx = (((cx - ex) - pad) - 15.0f) * 0.0625f, hx = ((cx + ex) + pad) * 0.0625f;
+    const float ly = (((cy - ey) - pad) - 15.0f) * 0.0625f, hy = ((cy + ey) + pad) * 0.0625f;
+    const int tx0 = (int)ceilf(fmaxf(lx, -1.0f)), tx1 = (int)floorf(fminf(hx, 70000.0f)) + 1;
+    const int ty0 = (int)ceilf(fmaxf(ly, -1.0f)), ty1 = (int)floorf(fminf(hy, 70000.0f)) + 1;
+    if (tx0 > *x0) *x0 = tx0;
+    if (tx1 < *x1) *x1 = tx1;
+    if (ty0 > *y0) *y0 = ty0;
+    if (ty1 < *y1) *y1 = ty1;
+    if (*x1 < *x0) *x1 = *x0;
+    if (*y1 < *y0) *y1 = *y0;
+}
+
+typedef struct { float cx, cy, A, B, C, nBoC, nBoA, shrink, tq; int ok; } Ctx;
+
+static Ctx cull_prepare(float cx, float cy, float A, float B, float C, float thr, float pad)
+{
+    Ctx c;
+    c.cx = cx; c.cy = cy; c.A = A; c.B = B; c.C = C;
+    const float detc = A * C - B * B;
+    c.ok = (A > 0.f) && (C > 0.f) && (detc > 0.f) && (pad <= 4096.f);
+    c.nBoC = -B / C;
+    c.nBoA = -B / A;
+    const float sAC = sqrtf(A * C) + fabsf(B);
+    const float kappa = (sAC * sAC) / detc;
+    c.shrink = 1.0f - 2e-5f * kappa;
+    if (!(c.shrink > 0.5f)) c.ok = 0;
+    c.tq = 1e-3f - thr;
+    return c;
+}
+
+static int cull_test(const Ctx* c, int tx, int ty, float pad)
+{
+    if (!c->ok) return 0;
+    const float dx0 = ((float)(tx * TILE) - pad) - c->cx, dx1 = ((float)(tx * TILE + TILE - 1) + pad) - c->cx;
+    const float dy0 = ((float)(ty * TILE) - pad) - c->cy, dy1 = ((float)(ty * TILE + TILE - 1) + pad) - c->cy;
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return 0;
+    float qmin = 3.4e38f;
+    for (int e = 0; e < 2; e++) {
+        const float dx = e ? dx1 : dx0;
+        const float dy = fminf(dy1, fmaxf(dy0, c->nBoC * dx));
+        const float q = 0.5f * ((c->A * dx) * dx + (c->C * dy) * dy) + (c->B * dx) * dy;
+        qmin = fminf(qmin, q);
+    }
+    for (int e = 0; e < 2; e++) {
+        const float dy = e ? dy1 : dy0;
+        const float dx = fminf(dx1, fmaxf(dx0, c->nBoA * dy));
+        const float q = 0.5f * ((c->A * dx) * dx + (c->C * dy) * dy) + (c->B * dx) * dy;
+        qmin = fminf(qmin, q);
+    }
+    return qmin * c->shrink > c->tq;
+}
+
+/* the compositing loop's test for one pixel centre (forward.cu:365-381) */
+static int contributes(float cx, float cy, float A, float B, float C, float opac, float pxf, float pyf)
+{
+    const float dx = cx - pxf, dy = cy - pyf;
+    const float power = fmaf(fmaf(dx, A * dx, (C * dy) * dy), -0.5f, -((B * dx) * dy));
+    if (power > 0.0f) return 0;
+    const float alpha = fminf(0.99f, opac * expf(power));
+    return !(alpha < 1.0f / 255.0f);
+}
+
+/* For n splats (pixel centre cx, cy; conic A, B, C; opacity o; integer radius): counts[0] += instances of the reference
+ * rectangles, [1] += instances of the tight rectangles, [2] += instances surviving the exact test, [3] += instances with
+ * a contributing pixel (brute force, pad box sampled), [4] += VIOLATIONS (dropped although a pixel contributes).
+ * Returns the number of violations; the index of the first offending splat goes to *first_bad (or -1). */
+long cull_check(int n, const float* cx, const float* cy, const float* A, const float* B, const float* C, const float* opac,
+                const int* radius, float pad, int grid_x, int grid_y, long long* counts, int* first_bad)
+{
+    long bad = 0;
+    *first_bad = -1;
+    for (int i = 0; i < n; i++) {
+        int x0, y0, x1, y1;
+        tile_rect(cx[i], cy[i], radius[i], grid_x, grid_y, &x0, &y0, &x1, &y1);
+        if ((x1 - x0) * (y1 - y0) == 0) continue;
+        const float thr = logf(1.0f / (255.0f * opac[i])) - 1e-3f;
+        int tx0 = x0, ty0 = y0, tx1 = x1, ty1 = y1;
+        tight_rect(cx[i], cy[i], A[i], B[i], C[i], thr, pad, &tx0, &ty0, &tx1, &ty1);
+        const Ctx c = cull_prepare(cx[i], cy[i], A[i], B[i], C[i], thr, pad);
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) {
+                counts[0]++;
+                const int in_tight = tx >= tx0 && tx < tx1 && ty >= ty0 && ty < ty1;
+                const int kept = in_tight && !cull_test(&c, tx, ty, pad);
+                counts[1] += in_tight;
+                counts[2] += kept;
+                int any = 0;
+                for (int py = 0; py < TILE && !any; py++)
+                    for (int px = 0; px < TILE && !any; px++) {
+                        const float bx = (float)(tx * TILE + px), by = (float)(ty * TILE + py);
+                        /* centre, four corners of the pad box, and the point of the box nearest to the splat centre */
+                        const float nx = fminf(bx + pad, fmaxf(bx - pad, cx[i])), ny = fminf(by + pad, fmaxf(by - pad, cy[i]));
+                        const float sx[6] = {bx, bx - pad, bx + pad, bx - pad, bx + pad, nx};
+                        const float sy[6] = {by, by - pad, by - pad, by + pad, by + pad, ny};
+                        for (int s = 0; s < 6 && !any; s++) any = contributes(cx[i], cy[i], A[i], B[i], C[i], opac[i], sx[s], sy[s]);
+                    }
+                counts[3] += any;
+                if (any && !kept) {
+                    counts[4]++;
+                    if (bad == 0) *first_bad = i;
+                    bad++;
+                }
+            }
+    }
+    return bad;
+}
