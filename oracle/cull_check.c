@@ -149,3 +149,57 @@ long cull_check(int n, const float* cx, const float* cy, const float* A, const f
     }
     return bad;
 }
+
+/* ---- the two finer culling levels of the compositing kernels --------------------------------------------------
+ * block_reject (csrc/common.cuh): a warp drops a splat for its whole 8 x bh pixel block (bh = 4 forward, 8 backward)
+ * when the block's bounding box of pixel centres lies outside the alpha >= 1/255 ellipse's axis-aligned box;
+ * skip threshold (render_fwd.cu / render_bwd.cu): a (pixel, splat) pair with power < thr = log(1/(255 o)) - 1e-3 is
+ * skipped without evaluating exp().  Both are verified against the compositing loop's own test at every pixel. */
+static int block_reject(float cx, float cy, float thr, float A, float B, float C, float x0, float x1, float y0, float y1)
+{
+    const float det = A * C - B * B;
+    if (!(A > 0.f) || !(C > 0.f) || !(det > 0.f)) return 0;
+    const float inv = 1.0f / det;
+    const float shrink = 1.0f - 8e-5f * (A * C * inv);
+    if (!(shrink > 0.5f)) return 0;
+    const float tq = 1e-3f - thr;
+    const float lim = 2.0f * tq * inv / shrink * 1.0001f;
+    const float dx = fmaxf(fmaxf(x0 - cx, cx - x1), 0.f);
+    const float dy = fmaxf(fmaxf(y0 - cy, cy - y1), 0.f);
+    return (dx * dx > lim * C) || (dy * dy > lim * A);
+}
+
+/* counts[0] += (splat, block) pairs examined, [1] += rejected blocks, [2] += (pixel, splat) pairs below the skip
+ * threshold, [3] += contributing pairs, [4] += violations of block_reject, [5] += violations of the skip threshold.
+ * (ox, oy): a subpixel offset applied to every pixel centre of the run. */
+long block_check(int n, const float* cx, const float* cy, const float* A, const float* B, const float* C, const float* opac,
+                 const int* radius, int bh, float ox, float oy, int grid_x, int grid_y, long long* counts)
+{
+    long bad = 0;
+    for (int i = 0; i < n; i++) {
+        int x0, y0, x1, y1;
+        tile_rect(cx[i], cy[i], radius[i], grid_x, grid_y, &x0, &y0, &x1, &y1);
+        const float thr = logf(1.0f / (255.0f * opac[i])) - 1e-3f;
+        for (int by = y0 * TILE; by < y1 * TILE; by += bh)
+            for (int bx = x0 * TILE; bx < x1 * TILE; bx += 8) {
+                const float fx0 = (float)bx + ox, fx1 = (float)(bx + 7) + ox, fy0 = (float)by + oy, fy1 = (float)(by + bh - 1) + oy;
+                const int rej = block_reject(cx[i], cy[i], thr, A[i], B[i], C[i], fx0, fx1, fy0, fy1);
+                counts[0]++;
+                counts[1] += rej;
+                for (int py = 0; py < bh; py++)
+                    for (int px = 0; px < 8; px++) {
+                        const float pxf = (float)(bx + px) + ox, pyf = (float)(by + py) + oy;
+                        const float dx = cx[i] - pxf, dy = cy[i] - pyf;
+                        const float power = fmaf(fmaf(dx, A[i] * dx, (C[i] * dy) * dy), -0.5f, -((B[i] * dx) * dy));
+                        const int con = contributes(cx[i], cy[i], A[i], B[i], C[i], opac[i], pxf, pyf);
+                        counts[3] += con;
+                        if (power < thr) {
+                            counts[2]++;
+                            if (con) { counts[5]++; bad++; }
+                        }
+                        if (rej && con) { counts[4]++; bad++; }
+                    }
+            }
+    }
+    return bad;
+}

@@ -74,3 +74,21 @@ def test_dropped_instances_never_contribute(pad, seed):
     # ... and the culling is tight, not just safe: what it keeps beyond the contributing instances are sub-pixel
     # needles that cross a tile between its pixel centres (the test works on the tile's continuous rectangle)
     assert kept <= 2.0 * need
+
+
+@pytest.mark.parametrize("bh,ox,oy,seed", [(4, 0.0, 0.0, 5), (8, 0.0, 0.0, 6), (4, 0.37, -0.45, 7), (8, -2.5, 3.0, 8)])
+def test_block_reject_and_skip_threshold_never_drop_a_contribution(bh, ox, oy, seed):
+    """The per-warp block test (8x4 pixel blocks in the forward, 8x8 in the backward) and the per-pair skip threshold
+    of the compositing kernels against the compositing loop's own alpha test at every pixel."""
+    lib = _lib()
+    lib.block_check.restype = C.c_long
+    lib.block_check.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    n = 5000
+    arrs = [np.ascontiguousarray(x) for x in _splats(n, seed)]
+    counts = np.zeros(6, np.int64)
+    bad = lib.block_check(n, *[x.ctypes.data for x in arrs], bh, ox, oy, 85, 64, counts.ctypes.data)
+    blocks, rejected, skipped, contributing, v_block, v_skip = [int(v) for v in counts]
+    print("8x%d blocks %d, rejected %d (%.0f %%); pairs below the skip threshold %d, contributing %d"
+          % (bh, blocks, rejected, 100.0 * rejected / blocks, skipped, contributing))
+    assert bad == 0 and v_block == 0 and v_skip == 0
+    assert rejected > 0.3 * blocks and contributing > 100000 and skipped > contributing
