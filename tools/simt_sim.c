@@ -207,3 +207,99 @@ void simulate_cursor(int W, int H, int bw, int bh, int batch,
     }
     for (int i = 0; i < 5; i++) out[i] = acc[i];
 }
+
+/* Broadcast test as today + a per-lane FIFO (depth Q) of candidates that passed the cheap test; a blend round (every
+ * lane with a non-empty FIFO pops one and runs the blend body) is issued whenever some lane's FIFO is full, and the
+ * FIFOs are drained at the end of the batch.  out[0] blend rounds, out[1] lane-slots active in them, out[2] blends. */
+void simulate_queue(int W, int H, int bw, int bh, int batch, int Q,
+                    const float* means2D, const float* conic_opacity, const uint32_t* point_list, const uint32_t* ranges,
+                    long long* out)
+{
+    const int gx = (W + 15) / 16, gy = (H + 15) / 16;
+    long long acc[3];
+    memset(acc, 0, sizeof(acc));
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : acc[:3])
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const int tx = tile % gx, ty = tile / gx;
+        const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+        uint32_t* list = (uint32_t*)malloc(sizeof(uint32_t) * (r1 - r0 + 1));
+        int n = 0;
+        for (uint32_t q = r0; q < r1; q++) {
+            const uint32_t id = point_list[q];
+            const float cx = means2D[2 * id], cy = means2D[2 * id + 1];
+            const float A = conic_opacity[4 * id], B = conic_opacity[4 * id + 1], C = conic_opacity[4 * id + 2], o = conic_opacity[4 * id + 3];
+            const float thr = logf(1.0f / (255.0f * o)) - 1e-3f;
+            const Ctx c = cull_prepare(cx, cy, A, B, C, thr, 0.f);
+            if (cull_test(&c, tx, ty, 0.f)) continue;
+            list[n++] = id;
+        }
+        const int nbx = 16 / bw, nby = 16 / bh, nblk = nbx * nby, lanes = bw * bh;
+        float T[256];
+        int done[256];
+        for (int i = 0; i < 256; i++) { T[i] = 1.0f; done[i] = 0; }
+        for (int p = 0; p < 256; p++) {
+            const int px = tx * 16 + p % 16, py = ty * 16 + p / 16;
+            if (px >= W || py >= H) done[p] = 1;
+        }
+        for (int b0 = 0; b0 < n; b0 += batch) {
+            int alive = 0;
+            for (int p = 0; p < 256; p++) alive += !done[p];
+            if (!alive) break;
+            const int cnt = (n - b0 < batch) ? n - b0 : batch;
+            for (int blk = 0; blk < nblk; blk++) {
+                const int ox = (blk % nbx) * bw, oy = (blk / nbx) * bh;
+                const float fx0 = (float)(tx * 16 + ox), fx1 = fx0 + (float)(bw - 1), fy0 = (float)(ty * 16 + oy), fy1 = fy0 + (float)(bh - 1);
+                float qa[64][64];        /* FIFO of alphas (-1: passed the cheap test but alpha < 1/255) */
+                int qn[64];
+                for (int l = 0; l < lanes; l++) qn[l] = 0;
+                for (int j = 0; j <= cnt; j++) {
+                    int full = 0;
+                    if (j < cnt) {
+                        const uint32_t id = list[b0 + j];
+                        const float cx = means2D[2 * id], cy = means2D[2 * id + 1];
+                        const float A = conic_opacity[4 * id], B = conic_opacity[4 * id + 1], C = conic_opacity[4 * id + 2], o = conic_opacity[4 * id + 3];
+                        const float thr = logf(1.0f / (255.0f * o)) - 1e-3f;
+                        if (block_reject(cx, cy, thr, A, B, C, fx0, fx1, fy0, fy1)) continue;
+                        for (int l = 0; l < lanes; l++) {
+                            const int p = (oy + l / bw) * 16 + ox + l % bw;
+                            if (done[p]) continue;
+                            float alpha = 0.f;
+                            const int st = pair_state(cx, cy, A, B, C, o, thr, (float)(tx * 16 + ox + l % bw), (float)(ty * 16 + oy + l / bw), &alpha);
+                            if (st == 0) continue;
+                            qa[l][qn[l]++] = (st == 2) ? alpha : -1.f;
+                            if (qn[l] >= Q) full = 1;
+                        }
+                    }
+                    /* one round when a FIFO is full; drain completely at the end of the batch */
+                    for (;;) {
+                        int any = 0, act = 0;
+                        if (!(full || j == cnt)) break;
+                        for (int l = 0; l < lanes; l++) {
+                            if (qn[l] == 0) continue;
+                            const int p = (oy + l / bw) * 16 + ox + l % bw;
+                            const float alpha = qa[l][0];
+                            for (int k = 1; k < qn[l]; k++) qa[l][k - 1] = qa[l][k];
+                            qn[l]--;
+                            if (done[p]) { qn[l] = 0; continue; }
+                            any = 1; act++;
+                            if (alpha >= 0.f) {
+                                const float test_T = T[p] * (1.0f - alpha);
+                                if (test_T < 0.0001f) { done[p] = 1; qn[l] = 0; continue; }
+                                T[p] = test_T;
+                                acc[2]++;
+                            }
+                        }
+                        if (any) { acc[0]++; acc[1] += act; }
+                        full = 0;
+                        if (j < cnt) break;
+                        int left = 0;
+                        for (int l = 0; l < lanes; l++) left += qn[l];
+                        if (!left) break;
+                    }
+                }
+            }
+        }
+        free(list);
+    }
+    for (int i = 0; i < 3; i++) out[i] = acc[i];
+}

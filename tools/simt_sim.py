@@ -29,6 +29,7 @@ def main():
     lib = C.CDLL(so)
     lib.simulate.argtypes = [C.c_int] * 6 + [C.c_void_p] * 5
     lib.simulate_cursor.argtypes = [C.c_int] * 5 + [C.c_void_p] * 5
+    lib.simulate_queue.argtypes = [C.c_int] * 6 + [C.c_void_p] * 5
     sc = synth.make_config(args.workload)
     inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
     cam = sc.cam
@@ -64,6 +65,12 @@ def main():
             print("%2dx%-7d %-6d | %11.2fM %7.1f%% | %11.2fM %7.1f%% | %9.1fM"
                   % (bw, bh, batch, out[0] / 1e6, 100.0 * out[3] / max(1, out[0] * lanes), out[1] / 1e6,
                      100.0 * out[2] / max(1, out[1] * lanes), out[4] / 1e6))
+    print()
+    print("broadcast test + per-lane FIFO of depth Q in front of the blend body (8x4 blocks, batches of 256):")
+    for Q in (1, 2, 4, 8, 16, 64):
+        out = np.zeros(3, np.int64)
+        lib.simulate_queue(cam.W, cam.H, 8, 4, 256, Q, m2.ctypes.data, co.ctypes.data, pl.ctypes.data, rg.ctypes.data, out.ctypes.data)
+        print("Q = %-3d blend rounds %6.2fM, lanes %5.1f%%, blends %.1fM" % (Q, out[0] / 1e6, 100.0 * out[1] / max(1, out[0] * 32), out[2] / 1e6))
 
 
 if __name__ == "__main__":
