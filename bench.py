@@ -541,6 +541,7 @@ def main():
                     help="--only-train-iter: include the per-iteration regularisers / statistics / NaN guards (train_iter_full)")
     ap.add_argument("--dp-grads", action="store_true",
                     help="train_iter leg under torchrun: SUM all-reduce of all gradients before the optimizer step")
+    ap.add_argument("--value-only", action="store_true", help="tuning aid (tools/tune.py): only the device-timed leg + stage timers")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
     args = ap.parse_args()
     rank, local_rank, ws = dist_env()
@@ -662,6 +663,14 @@ def main():
             timed(frame.step_device, min(K, 20))
         stage_ms = read_stages()
     clocks = sampler.stop(t0, t1) if sampler else None
+    if args.value_only:
+        if rank == 0:
+            names = ["preprocess_fwd", "depth_sort_scan", "sync_duplicate_tilesort_ranges", "render_fwd", "render_bwd", "preprocess_bwd"]
+            emit({"value": ws * K / (ms_total / 1000.0), "ms_per_step": ms_total / K, "steps": K,
+                  "stage_ms": dict(zip(names, stage_ms)) if stage_ms else None, "clocks": clocks, "tuning_run": True})
+        if ws > 1:
+            torch.distributed.destroy_process_group()
+        return
 
     # end-to-end leg
     for _ in range(W):

@@ -16,6 +16,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_last_R = 0;     // sizing hint only (previous frame of this thread)
+thread_local unsigned g_last_inexact = 0;   // Gaussians of the last forward whose alpha threshold fell back (preprocess.cu)
 
 // Pinned landing pad of the forward's one read-back (R and the flow flag), one per host thread and
 // device: with pinned memory both 4-byte copies are truly asynchronous and cost a single sync.
@@ -202,6 +203,7 @@ int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
     return EX4DGS_OK;
 }
 const char* ex4dgs_last_error(void) { return g_err; }
+unsigned ex4dgs_last_inexact_thresholds(void) { return g_last_inexact; }
 
 size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
 size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R)).total; }
@@ -347,7 +349,8 @@ int ex4dgs_forward(
         pp.rec = geom.rec; pp.clamped = geom.clamped;
         pp.pad_ptr = reinterpret_cast<const float*>(geom.meta);
         pp.flow_flag = geom.meta + 1;
-        CK(cudaMemsetAsync(geom.meta, 0, 2 * sizeof(uint32_t), s));     // [0] max |subpixel offset| bits, [1] flow flag
+        pp.inexact_thr = geom.meta + 2;
+        CK(cudaMemsetAsync(geom.meta, 0, 3 * sizeof(uint32_t), s));     // [0] max |subpixel offset| bits, [1] flow flag, [2] inexact thresholds
         if (flags & EX4DGS_FLAG_TILE_CULL)
             CK(launch_subpixel_absmax(subpixel_offset, (size_t)width * height * 2, geom.meta, s));
         prof.mark();
@@ -363,7 +366,7 @@ int ex4dgs_forward(
         uint32_t* rb = g_readback.get();
         if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
         CK(cudaMemcpyAsync(rb, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(rb + 1, geom.meta + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rb + 1, geom.meta + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         cudaEvent_t rb_ev = g_readback.event();
         if (rb_ev) CK(cudaEventRecord(rb_ev, s));
         // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning buffer sized
@@ -387,6 +390,7 @@ int ex4dgs_forward(
         else CK(cudaStreamSynchronize(s));
         R = (int)rb[0];
         flow32 = rb[1];
+        g_last_inexact = rb[2];
         // sizing hint for the next frame: follows R upwards at once, downwards slowly (views alternate in training)
         g_last_R = R > g_last_R ? R : (int)(((long long)g_last_R * 15 + R) / 16);
     }

@@ -17,10 +17,10 @@
 
 // tuning knobs of the compositing kernels (defaults = measured best on B200, see profiles/)
 #ifndef EX_FWD_MINBLOCKS
-#define EX_FWD_MINBLOCKS 4      // 64 registers (44 B of spills) but 32 resident warps: 0.49 vs 0.53 ms at C3
+#define EX_FWD_MINBLOCKS 6      // CTAs of 128 threads (2 pixels per lane): 80 registers, 24 resident warps
 #endif
 #ifndef EX_BWD_MINBLOCKS
-#define EX_BWD_MINBLOCKS 5      // CTAs of 128 threads (PPT = 2): 96 registers, 20 resident warps; 0.926 ms vs 1.011 (4) / 0.948 (6) at C3
+#define EX_BWD_MINBLOCKS 6      // CTAs of 128 threads (2 pixels per lane, packed): 78 registers, 24 resident warps; 0.712 ms vs 0.744 (5) / 0.758 (4) at C3
 #endif
 #ifndef EX_FWD_STAGE_LDGSTS
 #define EX_FWD_STAGE_LDGSTS 1   // forward staging: 1 = per-thread 16-byte cp.async (LDGSTS), 0 = one TMA bulk copy per splat.
@@ -174,6 +174,7 @@ struct PreprocessParams {
     SplatRec* rec;
     uint8_t* clamped;
     uint32_t* flow_flag;    // device word, set to 1 when a visible Gaussian has a non-zero dir3D component
+    uint32_t* inexact_thr;  // device counter: visible Gaussians whose alpha threshold fell back to the conservative value
 };
 
 struct RenderParams {
@@ -373,7 +374,7 @@ __device__ __forceinline__ CullCtx cull_prepare(float cx, float cy, float A, flo
     const float kappa = __fdiv_rn(fm(sAC, sAC), detc);
     c.shrink = fa(1.0f, -fm(2e-5f, kappa));
     if (!(c.shrink > 0.5f)) c.ok = 0;
-    c.tq = fa(1e-3f, -thr);          // -qmin*shrink + 1e-3 < thr  <=>  qmin*shrink > 1e-3 - thr
+    c.tq = fa(2e-3f, -thr);          // -qmin*shrink + 2e-3 < thr  <=>  qmin*shrink > 2e-3 - thr   (thr = exact alpha crossing)
     return c;
 }
 
@@ -429,7 +430,7 @@ __device__ __forceinline__ void tight_rect(float cx, float cy, float A, float B,
     const float kappa = fm(fm(sAC, sAC), rdet);
     const float shrink = fa(1.0f, -fm(2.01e-5f, kappa));
     if (!(shrink > 0.5f)) return;
-    const float tq = fa(1e-3f, -thr);
+    const float tq = fa(2e-3f, -thr);
     if (!(tq > 0.f)) return;                       // nothing can pass anyway; cull_test sorts it out
     const float twoL = fm(__fdividef(fm(2.0f, tq), shrink), rdet);
     float ex = approx_sqrt(fm(twoL, C));
@@ -512,12 +513,53 @@ __device__ __forceinline__ bool block_reject(const float4& a, const float4& b, c
     const float inv = 1.0f / det;
     const float shrink = 1.0f - 8e-5f * (A * C * inv);
     if (!(shrink > 0.5f)) return false;
-    const float tq = 1e-3f - a.w;                       // NaN thr -> comparisons below are false -> keep
+    const float tq = 2e-3f - a.w;                       // NaN thr -> comparisons below are false -> keep
     const float lim = 2.0f * tq * inv / shrink * 1.0001f;
     const float dx = fmaxf(fmaxf(box.x0 - a.x, a.x - box.x1), 0.f);
     const float dy = fmaxf(fmaxf(box.y0 - a.y, a.y - box.y1), 0.f);
     return (dx * dx > lim * C) || (dy * dy > lim * A);
 }
+
+// ---- packed FP32 pairs (sm_100: fma/mul/add.rn.f32x2 -> SASS FFMA2 / FMUL2 / FADD2) ------------------------------
+// Two IEEE round-to-nearest operations per issued instruction; each half rounds exactly like the scalar
+// __fmaf_rn / __fmul_rn / __fadd_rn, so pinned arithmetic stays bit-exact.  A scalar operand is written bc(x): the
+// SASS forms take a 32-bit register (or immediate) as a broadcast operand (`R10.F32`), so bc() costs nothing.
+// The compositing kernels pair the TWO PIXELS a lane owns.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 mk2(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 bc(float s) { return mk2(s, s); }
+__device__ __forceinline__ void split2(f2 a, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ float lo2(f2 a) { float x, y; split2(a, x, y); return x; }
+__device__ __forceinline__ float hi2(f2 a) { float x, y; split2(a, x, y); return y; }
+__device__ __forceinline__ f2 fm2(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 fa2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 ff2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ float hsum2(f2 a) { float x, y; split2(a, x, y); return x + y; }
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier transaction counting -------------------
 // The compositing kernels stage each splat's 64-byte record with ONE bulk copy issued by the

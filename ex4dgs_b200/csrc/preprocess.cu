@@ -144,6 +144,43 @@ int sh_basis_fwd(int D, float dx, float dy, float dz, float* b)
     return nb;
 }
 
+// The compositing loop blends a (pixel, splat) pair iff alpha = min(0.99, opac * expf(power)) >= 1/255
+// (forward.cu:384-387).  alpha is a non-decreasing function of power, so there is ONE float thr with
+//     alpha >= 1/255  <=>  power >= thr.
+// It is found here, once per visible Gaussian, by bisection over the float bit patterns around p0 = log(1 / (255 opac))
+// (window: +-1e-6 absolute and relative - logf and expf are good to a few 1e-7), evaluating the loop's own expression
+// (libdevice expf, the same rounding of the product): 3 - 12 evaluations, more only for opacities within 1e-3 of
+// 1/255.  So the forward's skip test, the backward's membership test and the reference's alpha test agree on EVERY
+// pair, and the backward needs no exp() to know whether a pair contributed.  If the window does not bracket the
+// crossing or the two floats next to it contradict monotonicity (never observed), the conservative threshold
+// p0 - 1e-3 is stored instead and the frame's counter of such Gaussians is raised (the forward still applies the
+// alpha test itself, so images are unaffected).
+//   opac < 1/255: nothing passes (+inf);  NaN: every comparison with thr is false, the pair is kept as in the reference.
+__device__ __forceinline__ float alpha_threshold(float opac, uint32_t* inexact_counter)
+{
+    if (opac != opac) return opac;
+    if (opac < 1.0f / 255.0f) return __int_as_float(0x7f800000);
+    const float p0 = fminf(logf(1.0f / (255.0f * opac)), -0.0f);
+    if (!(p0 > -3.0e38f)) return p0;                                   // opac = +inf: alpha is always 0.99
+    // work on magnitudes m = bits(-power): m + 1 is one ulp more negative (lower alpha)
+    auto passes = [&](uint32_t m) { return !(fminf(0.99f, fm(opac, expf(-__uint_as_float(m)))) < 1.0f / 255.0f); };
+    const float mag = -p0, d = fmaf(mag, 1e-6f, 1e-6f);
+    uint32_t lo = __float_as_uint(fmaxf(mag - d, 0.0f)), hi = __float_as_uint(mag + d);
+    bool ok = passes(lo) && !passes(hi);
+    if (ok) {
+        while (hi - lo > 1u) {                                         // passes(lo) && !passes(hi)
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (passes(mid)) lo = mid; else hi = mid;
+        }
+        ok = (lo == 0u || passes(lo - 1u)) && !passes(hi + 1u);
+    }
+    if (!ok) {
+        atomicAdd(inexact_counter, 1u);
+        return p0 - 1e-3f;
+    }
+    return -__uint_as_float(lo);
+}
+
 // SEG: the SH coefficients arrive as the model's four tensors (EX4DGS_FLAG_SH_SEGMENTED).  A template
 // parameter, not a run-time test of SEG: with the test inside, the contiguous-SH instantiation
 // pays for address selects in its inner loops (measured 0.122 -> 0.130 ms forward, 0.237 -> 0.277 ms backward).
@@ -283,8 +320,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         p.clamped[idx] = clamp_bits;
 
         const float opac = fm(__ldg(p.opacities + idx), coef);
-        // skip threshold of the compositing loop: power < thr  =>  opac*exp(power) < 1/255 for sure
-        const float thr = logf(1.0f / (255.0f * opac)) - 1e-3f;
+        // skip threshold of the compositing loops: power < thr  <=>  min(0.99, opac*expf(power)) < 1/255, exactly
+        const float thr = alpha_threshold(opac, p.inexact_thr);
 
         // with EX4DGS_FLAG_TILE_CULL the rectangle is first cut down to the bounding box of the alpha >= 1/255
         // ellipse (tight_rect); the duplicate kernel then keys the instances its exact test rejects to the

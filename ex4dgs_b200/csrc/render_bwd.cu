@@ -51,39 +51,47 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v)
 // Reduce 16 per-lane value slots over the warp; afterwards lane L holds the total of slot
 // k(L) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of L (both lanes of a pair hold the same total).
 // Slots 7, 11 and 15 are unused by the caller: their exchanges are dropped or left unselected, the
-// lanes that would hold their totals end up with don't-care values.
+// lanes that would hold their totals end up with don't-care values.  The additions of neighbouring slots
+// are issued as packed pairs (FADD2).
 __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
 {
     const unsigned full = 0xffffffffu;
+    float m[8], r[8];
     bool hi = lane & 16;
 #pragma unroll
     for (int i = 0; i < 7; i++) {
         if (i == 3) {                       // slot 11 unused: the upper half-warp's result is don't-care
-            v[3] += __shfl_xor_sync(full, v[3], 16);
+            m[3] = v[3];
+            r[3] = __shfl_xor_sync(full, v[3], 16);
             continue;
         }
-        const float mine = hi ? v[i + 8] : v[i];
-        const float other = hi ? v[i] : v[i + 8];
-        v[i] = mine + __shfl_xor_sync(full, other, 16);
+        m[i] = hi ? v[i + 8] : v[i];
+        r[i] = __shfl_xor_sync(full, hi ? v[i] : v[i + 8], 16);
     }
+    split2(fa2(mk2(m[0], m[1]), mk2(r[0], r[1])), v[0], v[1]);
+    split2(fa2(mk2(m[2], m[3]), mk2(r[2], r[3])), v[2], v[3]);
+    split2(fa2(mk2(m[4], m[5]), mk2(r[4], r[5])), v[4], v[5]);
+    v[6] = m[6] + r[6];
     hi = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         if (i == 3) {                       // slots 7 / 15 unused
-            v[3] += __shfl_xor_sync(full, v[3], 8);
+            m[3] = v[3];
+            r[3] = __shfl_xor_sync(full, v[3], 8);
             continue;
         }
-        const float mine = hi ? v[i + 4] : v[i];
-        const float other = hi ? v[i] : v[i + 4];
-        v[i] = mine + __shfl_xor_sync(full, other, 8);
+        m[i] = hi ? v[i + 4] : v[i];
+        r[i] = __shfl_xor_sync(full, hi ? v[i] : v[i + 4], 8);
     }
+    split2(fa2(mk2(m[0], m[1]), mk2(r[0], r[1])), v[0], v[1]);
+    split2(fa2(mk2(m[2], m[3]), mk2(r[2], r[3])), v[2], v[3]);
     hi = lane & 4;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const float mine = hi ? v[i + 2] : v[i];
-        const float other = hi ? v[i] : v[i + 2];
-        v[i] = mine + __shfl_xor_sync(full, other, 4);
+        m[i] = hi ? v[i + 2] : v[i];
+        r[i] = __shfl_xor_sync(full, hi ? v[i] : v[i + 2], 4);
     }
+    split2(fa2(mk2(m[0], m[1]), mk2(r[0], r[1])), v[0], v[1]);
     hi = lane & 2;
     {
         const float mine = hi ? v[1] : v[0];
@@ -94,23 +102,55 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane)
     return v[0];
 }
 
-// first pixel of a lane assigns, further pixels add (keeps the PPT = 1 code free of `0 + x` adds)
-__device__ __forceinline__ void acc_to(float& dst, float x, int u)
+__device__ __forceinline__ float fast_rcp(float x)
 {
-    if (u == 0) dst = x; else dst += x;
+#if EX_BWD_FAST_RCP
+    // 1 - alpha is in [0.01, 1]: MUFU.RCP (1 ulp) instead of the 12-instruction IEEE division
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.f / x;
+#endif
 }
 
-// PPT = pixels per thread.  PPT = 1: 8 warps, each an 8x4 pixel block.  PPT = 2: 4 warps, each an
-// 8x8 block (a lane owns pixels (x, y) and (x, y + 4)): the per-lane gradient terms of the two
-// pixels are added before the warp butterfly, so one butterfly + one reduction instruction serves
-// 64 pixels instead of 32.
+// G = exp(power), alpha = min(0.99, opacity * G) of the lane's two pixels (packed).  Whether a pair CONTRIBUTED is known
+// before this is called: the record's threshold a.w is the exact crossing of the forward's alpha >= 1/255 test
+// (preprocess.cu alpha_threshold), so `power >= thr` decides membership exactly like the forward and the reference
+// (forward.cu:384-387) and exp() only supplies values.
+// EX_BWD_FAST_EXP: ex2.approx(power * log2 e) - MUFU.EX2 directly instead of libdevice's 10 instructions, relative
+// error < 1e-6 (power lies in [thr, 0], thr > -6: no denormal handling needed).
+__device__ __forceinline__ void pair_alpha2(f2 pw, float opac, bool c0, bool c1, f2& G, f2& al)
+{
+    float G0, G1, a0, a1;
+#if EX_BWD_FAST_EXP
+    float e0, e1;
+    split2(fm2(pw, bc(1.4426950408889634f)), e0, e1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G0) : "f"(e0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G1) : "f"(e1));
+#else
+    G0 = expf(lo2(pw)); G1 = expf(hi2(pw));
+#endif
+    // a pixel the splat does not contribute to runs along as a phantom with G = alpha = 0
+    G = mk2(c0 ? G0 : 0.f, c1 ? G1 : 0.f);
+    split2(fm2(bc(opac), G), a0, a1);
+    al = mk2(fminf(0.99f, a0), fminf(0.99f, a1));
+}
+
+// 4 warps per tile, each an 8x8 pixel block: a lane owns pixels (x, y) and (x, y + 4), and every per-pixel
+// quantity lives in a packed pair (f2: low half = upper pixel) processed with FFMA2 / FMUL2 / FADD2 - one issued
+// instruction for both pixels.  A pixel the splat does not contribute to runs along as a phantom with
+// G = alpha = 0: T * 1, accum_rec * 1 + 0 and every gradient term * 0 leave its state and the sums unchanged bit
+// for bit, so there are no per-pixel branches in the gradient math.  The per-lane terms of the two pixels are
+// added before the warp butterfly: one butterfly + one reduction instruction serves 64 pixels.
 // DA = false: the caller has no upstream gradient for the depth and accumulated-alpha images (NULL
 // dL_ddepth and dL_dacc - what autograd reports when the loss does not use them, as in train.py): their
 // terms are exactly zero and are dropped at compile time.  A NULL dL_dflow is read as zeros.
-template <int PPT, bool DA>
-__global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
+template <bool DA>
+__global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
 {
-    constexpr int NW = 8 / PPT;            // warps per tile
+    constexpr int PPT = 2;
+    constexpr int NW = 4;                  // warps per tile
     constexpr int SLOTS = kSub / NW;       // records each warp fetches per sub-batch
     __shared__ float4 s_rec[kRing][kSub * 3];
     __shared__ uint8_t s_list[NW][kSub];
@@ -143,7 +183,7 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
         const int pix_x = blockIdx.x * EX_TILE + (warp & 1) * 8 + (lane & 7);
-        const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * (4 * PPT) + (lane >> 3) + 4 * u;
+        const int pix_y = blockIdx.y * EX_TILE + (warp >> 1) * 8 + (lane >> 3) + 4 * u;
         const bool inside = pix_x < p.W && pix_y < p.H;
         const int pix_id = p.W * pix_y + pix_x;
         pxf[u] = (float)pix_x; pyf[u] = (float)pix_y;
@@ -198,16 +238,18 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
     }
     const bool warp_idle = warp_last == 0;
     const float bg0 = __ldg(p.bg + 0), bg1 = __ldg(p.bg + 1), bg2 = __ldg(p.bg + 2);
-    float bg_dot_dpixel[PPT], T[PPT];
-    float accum_rec0[PPT], accum_rec1[PPT], accum_rec2[PPT];
-    float last_alpha[PPT], last_c0[PPT], last_c1[PPT], last_c2[PPT];
-#pragma unroll
-    for (int u = 0; u < PPT; u++) {
-        bg_dot_dpixel[u] = bg0 * dpix0[u] + bg1 * dpix1[u] + bg2 * dpix2[u];
-        T[u] = T_final[u];
-        accum_rec0[u] = accum_rec1[u] = accum_rec2[u] = 0.f;
-        last_alpha[u] = last_c0[u] = last_c1[u] = last_c2[u] = 0.f;
-    }
+
+    // per-pixel state and constants of the lane's two pixels, packed
+    const f2 npx = mk2(-pxf[0], -pxf[1]), npy = mk2(-pyf[0], -pyf[1]);
+    const f2 dp0 = mk2(dpix0[0], dpix0[1]), dp1 = mk2(dpix1[0], dpix1[1]), dp2 = mk2(dpix2[0], dpix2[1]);
+    const f2 df0 = mk2(dflow0[0], dflow0[1]), df1 = mk2(dflow1[0], dflow1[1]), df2 = mk2(dflow2[0], dflow2[1]);
+    // -T_final * (bg . dL_dpix): factor of 1 / (1 - alpha) in the background term (backward.cu:656-659)
+    const f2 nTbg = mk2(-T_final[0] * (bg0 * dpix0[0] + bg1 * dpix1[0] + bg2 * dpix2[0]),
+                        -T_final[1] * (bg0 * dpix0[1] + bg1 * dpix1[1] + bg2 * dpix2[1]));
+    const f2 fdep = mk2(final_depth[0], final_depth[1]), ddep = mk2(dL_ddepth[0], dL_ddepth[1]);
+    f2 dacc = mk2(dL_dacc[0], dL_dacc[1]);
+    f2 T = mk2(T_final[0], T_final[1]);
+    f2 ar0 = bc(0.f), ar1 = bc(0.f), ar2 = bc(0.f);       // colour accumulated behind the current splat (accum_rec)
 
     // TMA staging: every warp fetches SLOTS records of each sub-batch (lanes 0..SLOTS-1, one 48-byte
     // bulk copy each; the dir3D word is not needed here), kAhead sub-batches ahead; thread 0 announces
@@ -256,89 +298,68 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
             __syncwarp();
         }
         // entry j of the sub-batch sits at list position q = start-1-(r*kSub+j):  q < last_contributor  <=>  j >= jthr
-        int jthr[PPT];
-#pragma unroll
-        for (int u = 0; u < PPT; u++) jthr[u] = start - r * kSub - last_contributor[u];
+        const int jthr0 = start - r * kSub - last_contributor[0], jthr1 = start - r * kSub - last_contributor[1];
         const unsigned sb = smem_u32(s);
 #pragma unroll(kUnroll)
         for (int e = 0; e < nw; e++) {
             const int j = s_list[warp][e];
             const float4 a = lds128(sb + j * 48);
             const float4 b = lds128(sb + j * 48 + 16);
-            float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
-            bool contributes[PPT];
-            bool any_c = false;
-#pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                dx[u] = fa(a.x, -pxf[u]);
-                dy[u] = fa(a.y, -pyf[u]);
-                const float power = ff(ff(dx[u], fm(dx[u], b.x), fm(fm(b.z, dy[u]), dy[u])), -0.5f, -fm(fm(b.y, dx[u]), dy[u]));
-                contributes[u] = (j >= jthr[u]) && !(power > 0.0f) && !(power < a.w);
-                G[u] = 0.f; alpha[u] = 0.f;
-                if (contributes[u]) {
-#if EX_BWD_FAST_EXP
-                    // ex2.approx(power * log2 e): 2 instructions instead of libdevice's 10; relative error < 1e-6 for
-                    // power in [-6, 0], three orders of magnitude inside the gradient budget (the FORWARD keeps expf:
-                    // its images are bit-identical to the reference's)
-                    G[u] = __expf(power);
-#else
-                    G[u] = expf(power);
-#endif
-                    alpha[u] = fminf(0.99f, fm(b.w, G[u]));
-                    contributes[u] = !(alpha[u] < 1.0f / 255.0f);
-                }
-                any_c |= contributes[u];
-            }
-            if (!__any_sync(full, any_c)) continue;
+            // power of both pixels with the forward's FMA placement (render_fwd.cu pair_power), packed
+            const f2 dx = fa2(bc(a.x), npx), dy = fa2(bc(a.y), npy);
+            const f2 pw = ff2(ff2(dx, fm2(dx, bc(b.x)), fm2(fm2(bc(b.z), dy), dy)), bc(-0.5f), fm2(fm2(bc(-b.y), dx), dy));
+            float pw0, pw1;
+            split2(pw, pw0, pw1);
+            bool c0 = (j >= jthr0) && !(pw0 > 0.0f) && !(pw0 < a.w);
+            bool c1 = (j >= jthr1) && !(pw1 > 0.0f) && !(pw1 < a.w);
+            if (!__any_sync(full, c0 | c1)) continue;
+            f2 G, al;
+            pair_alpha2(pw, b.w, c0, c1, G, al);
             const float4 c = lds128(sb + j * 48 + 32);
+            const f2 oma = ff2(al, bc(-1.0f), bc(1.0f));                // 1 - alpha (exact product: == fa(1, -alpha))
+            float om0, om1;
+            split2(oma, om0, om1);
+            const f2 inv = mk2(fast_rcp(om0), fast_rcp(om1));
+            T = fm2(T, inv);
+            const f2 w = fm2(al, T);                                    // dchannel_dcolor
+            f2 dLa;
             float v[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = 0.f;
-#pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                if (contributes[u]) {
-#if EX_BWD_FAST_RCP
-                    // 1 - alpha is in [0.01, 1]: MUFU.RCP (1 ulp) instead of the 12-instruction IEEE division
-                    float inv1ma;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.f - alpha[u]));
-#else
-                    const float inv1ma = 1.f / (1.f - alpha[u]);
-#endif
-                    T[u] = T[u] * inv1ma;
-                    const float w = alpha[u] * T[u];               // dchannel_dcolor
-                    float dL_dalpha = 0.0f;
-                    const float dep = a.z;
-                    if (DA) {
-                        if ((dep > p.min_depth) & (w > 0.0f)) {
-                            acc_to(v[2], dL_ddepth[u] * w, u);
-                            dL_dalpha += (final_depth[u] - dep) * dL_ddepth[u] * T[u];
-                        }
-                    }
-                    accum_rec0[u] = last_alpha[u] * last_c0[u] + (1.f - last_alpha[u]) * accum_rec0[u];
-                    accum_rec1[u] = last_alpha[u] * last_c1[u] + (1.f - last_alpha[u]) * accum_rec1[u];
-                    accum_rec2[u] = last_alpha[u] * last_c2[u] + (1.f - last_alpha[u]) * accum_rec2[u];
-                    last_c0[u] = c.x; last_c1[u] = c.y; last_c2[u] = c.z;
-                    dL_dalpha += (c.x - accum_rec0[u]) * dpix0[u];
-                    dL_dalpha += (c.y - accum_rec1[u]) * dpix1[u];
-                    dL_dalpha += (c.z - accum_rec2[u]) * dpix2[u];
-                    acc_to(v[8], w * dpix0[u], u); acc_to(v[9], w * dpix1[u], u); acc_to(v[10], w * dpix2[u], u);
-                    acc_to(v[12], w * dflow0[u], u); acc_to(v[13], w * dflow1[u], u); acc_to(v[14], w * dflow2[u], u);
-                    dL_dalpha *= T[u];
-                    if (DA) dL_dacc[u] *= T[u];
-                    last_alpha[u] = alpha[u];
-                    dL_dalpha += (-T_final[u] * inv1ma) * bg_dot_dpixel[u];
-                    // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
-                    const float gG = G[u] * (b.w * dL_dalpha);
-                    const float X = gG * dx[u], Y = gG * dy[u];
-                    acc_to(v[0], X * b.x + Y * b.y, u);
-                    acc_to(v[1], Y * b.z + X * b.y, u);
-                    acc_to(v[4], X * dx[u], u);
-                    acc_to(v[5], X * dy[u], u);
-                    acc_to(v[6], Y * dy[u], u);
-                    if (DA) acc_to(v[3], G[u] * dL_dalpha + G[u] * dL_dacc[u], u);
-                    else acc_to(v[3], G[u] * dL_dalpha, u);
-                }
+            // colour: dL_dalpha = sum_ch (c_ch - accum_rec_ch) dL_dpix_ch, then fold this splat into accum_rec
+            // (accum_rec <- alpha c + (1 - alpha) accum_rec, written as accum_rec + alpha (c - accum_rec))
+            const f2 t0 = ff2(ar0, bc(-1.0f), bc(c.x)), t1 = ff2(ar1, bc(-1.0f), bc(c.y)), t2 = ff2(ar2, bc(-1.0f), bc(c.z));
+            dLa = ff2(t2, dp2, ff2(t1, dp1, fm2(t0, dp0)));
+            ar0 = ff2(al, t0, ar0);
+            ar1 = ff2(al, t1, ar1);
+            ar2 = ff2(al, t2, ar2);
+            if (DA) {
+                // depth (backward.cu:604-622; its alpha term enters BEFORE the `*= T`, deviation Q3)
+                float w0, w1, T0, T1;
+                split2(w, w0, w1);
+                split2(T, T0, T1);
+                const float dep = a.z;
+                const bool d0 = (dep > p.min_depth) & (w0 > 0.0f), d1 = (dep > p.min_depth) & (w1 > 0.0f);
+                const f2 dd = fm2(fm2(fa2(fdep, bc(-dep)), ddep), T);
+                v[2] = (d0 ? dL_ddepth[0] * w0 : 0.f) + (d1 ? dL_ddepth[1] * w1 : 0.f);
+                dLa = fa2(dLa, mk2(d0 ? lo2(dd) : 0.f, d1 ? hi2(dd) : 0.f));
+                // cumulative dL_dacc *= T over the contributors (deviation Q4): phantoms must not touch it
+                dacc = fm2(dacc, mk2(c0 ? T0 : 1.0f, c1 ? T1 : 1.0f));
             }
+            dLa = fm2(dLa, T);
+            dLa = ff2(nTbg, inv, dLa);                                  // background term
+            // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
+            const f2 gG = fm2(G, fm2(bc(b.w), dLa));
+            const f2 X = fm2(gG, dx), Y = fm2(gG, dy);
+            v[0] = hsum2(ff2(Y, bc(b.y), fm2(X, bc(b.x))));
+            v[1] = hsum2(ff2(X, bc(b.y), fm2(Y, bc(b.z))));
+            v[4] = hsum2(fm2(X, dx));
+            v[5] = hsum2(fm2(X, dy));
+            v[6] = hsum2(fm2(Y, dy));
+            if (DA) v[3] = hsum2(ff2(G, dacc, fm2(G, dLa)));
+            else v[3] = hsum2(fm2(G, dLa));
+            v[8] = hsum2(fm2(w, dp0)); v[9] = hsum2(fm2(w, dp1)); v[10] = hsum2(fm2(w, dp2));
+            v[12] = hsum2(fm2(w, df0)); v[13] = hsum2(fm2(w, df1)); v[14] = hsum2(fm2(w, df2));
             const float tot = butterfly16(v, lane);
             // even lanes hold the 16 totals; 13 of them are real.  One warp-level reduction instruction:
             // 13 lanes add into the 64-byte accumulator of the splat (2 sectors).
@@ -357,6 +378,6 @@ __global__ void __launch_bounds__(256 / PPT, EX_BWD_MINBLOCKS) render_bwd_kernel
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
 {
     dim3 grid(grid_x, grid_y, 1);
-    if (p.dL_ddepth || p.dL_dacc) render_bwd_kernel<EX_BWD_PPT, true><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
-    else render_bwd_kernel<EX_BWD_PPT, false><<<grid, 256 / EX_BWD_PPT, 0, s>>>(p);
+    if (p.dL_ddepth || p.dL_dacc) render_bwd_kernel<true><<<grid, 128, 0, s>>>(p);
+    else render_bwd_kernel<false><<<grid, 128, 0, s>>>(p);
 }

@@ -38,6 +38,12 @@ def get_default_flags() -> int:
     return _DEFAULT_FLAGS
 
 
+def last_inexact_thresholds() -> int:
+    """Diagnostics of the calling thread's last forward: visible Gaussians whose exact alpha >= 1/255 threshold could not
+    be established (csrc/preprocess.cu alpha_threshold); 0 on everything observed so far."""
+    return int(_lib.load().ex4dgs_last_inexact_thresholds())
+
+
 def cpu_deep_copy_tuple(input_tuple):
     """__init__.py:18-20"""
     return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)

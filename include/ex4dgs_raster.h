@@ -363,6 +363,13 @@ unsigned long long ex4dgs_launch_count(void);
 
 int ex4dgs_abi_version(void);
 const char* ex4dgs_last_error(void);
+/* Diagnostics of the calling thread's last ex4dgs_forward: the number of visible Gaussians whose exact alpha >= 1/255
+ * threshold (the float thr with  min(0.99, opacity * expf(power)) >= 1/255  <=>  power >= thr, csrc/preprocess.cu
+ * alpha_threshold) could not be established because expf was not monotone on the nine floats around it, so that the
+ * conservative threshold was stored instead.  0 on everything observed so far; when non-zero, the backward may treat
+ * pairs of those Gaussians within 1e-3 of the limit as contributing although the forward (forward.cu:384-387) skipped
+ * them. */
+unsigned ex4dgs_last_inexact_thresholds(void);
 
 #ifdef __cplusplus
 }

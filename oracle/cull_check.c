@@ -36,7 +36,7 @@ static void tight_rect(float cx, float cy, float A, float B, float C, float thr,
     const float kappa = (sAC * sAC) * rdet;
     const float shrink = 1.0f - 2.01e-5f * kappa;
     if (!(shrink > 0.5f)) return;
-    const float tq = 1e-3f - thr;
+    const float tq = 2e-3f - thr;
     if (!(tq > 0.f)) return;
     const float twoL = ((2.0f * tq) / shrink) * rdet;
     float ex = sqrtf(twoL * C), ey = sqrtf(twoL * A);
@@ -69,7 +69,7 @@ static Ctx cull_prepare(float cx, float cy, float A, float B, float C, float thr
     const float kappa = (sAC * sAC) / detc;
     c.shrink = 1.0f - 2e-5f * kappa;
     if (!(c.shrink > 0.5f)) c.ok = 0;
-    c.tq = 1e-3f - thr;
+    c.tq = 2e-3f - thr;
     return c;
 }
 
@@ -105,6 +105,41 @@ static int contributes(float cx, float cy, float A, float B, float C, float opac
     return !(alpha < 1.0f / 255.0f);
 }
 
+/* csrc/preprocess.cu alpha_threshold(): the float thr with  min(0.99, o*expf(p)) >= 1/255  <=>  p >= thr, found by
+ * bisection over the float bit patterns around log(1/(255 o)) with the loop's own expression (here: this file's expf);
+ * conservative fallback when the window does not bracket the crossing. */
+static int alpha_passes(float opac, unsigned m)
+{
+    union { float f; unsigned u; } cv;
+    cv.u = m;
+    return !(fminf(0.99f, opac * expf(-cv.f)) < 1.0f / 255.0f);
+}
+
+static float alpha_threshold(float opac)
+{
+    if (opac != opac) return opac;
+    if (opac < 1.0f / 255.0f) return INFINITY;
+    const float p0 = fminf(logf(1.0f / (255.0f * opac)), -0.0f);
+    if (!(p0 > -3.0e38f)) return p0;
+    union { float f; unsigned u; } cv;
+    const float mag = -p0, d = fmaf(mag, 1e-6f, 1e-6f);
+    cv.f = fmaxf(mag - d, 0.0f);
+    unsigned lo = cv.u;
+    cv.f = mag + d;
+    unsigned hi = cv.u;
+    int ok = alpha_passes(opac, lo) && !alpha_passes(opac, hi);
+    if (ok) {
+        while (hi - lo > 1u) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            if (alpha_passes(opac, mid)) lo = mid; else hi = mid;
+        }
+        ok = (lo == 0u || alpha_passes(opac, lo - 1u)) && !alpha_passes(opac, hi + 1u);
+    }
+    if (!ok) return p0 - 1e-3f;
+    cv.u = lo;
+    return -cv.f;
+}
+
 /* For n splats (pixel centre cx, cy; conic A, B, C; opacity o; integer radius): counts[0] += instances of the reference
  * rectangles, [1] += instances of the tight rectangles, [2] += instances surviving the exact test, [3] += instances with
  * a contributing pixel (brute force, pad box sampled), [4] += VIOLATIONS (dropped although a pixel contributes).
@@ -118,7 +153,7 @@ long cull_check(int n, const float* cx, const float* cy, const float* A, const f
         int x0, y0, x1, y1;
         tile_rect(cx[i], cy[i], radius[i], grid_x, grid_y, &x0, &y0, &x1, &y1);
         if ((x1 - x0) * (y1 - y0) == 0) continue;
-        const float thr = logf(1.0f / (255.0f * opac[i])) - 1e-3f;
+        const float thr = alpha_threshold(opac[i]);
         int tx0 = x0, ty0 = y0, tx1 = x1, ty1 = y1;
         tight_rect(cx[i], cy[i], A[i], B[i], C[i], thr, pad, &tx0, &ty0, &tx1, &ty1);
         const Ctx c = cull_prepare(cx[i], cy[i], A[i], B[i], C[i], thr, pad);
@@ -153,8 +188,8 @@ long cull_check(int n, const float* cx, const float* cy, const float* A, const f
 /* ---- the two finer culling levels of the compositing kernels --------------------------------------------------
  * block_reject (csrc/common.cuh): a warp drops a splat for its whole 8 x bh pixel block (bh = 4 forward, 8 backward)
  * when the block's bounding box of pixel centres lies outside the alpha >= 1/255 ellipse's axis-aligned box;
- * skip threshold (render_fwd.cu / render_bwd.cu): a (pixel, splat) pair with power < thr = log(1/(255 o)) - 1e-3 is
- * skipped without evaluating exp().  Both are verified against the compositing loop's own test at every pixel. */
+ * skip threshold (render_fwd.cu / render_bwd.cu): a (pixel, splat) pair with power < thr (the exact crossing of the alpha
+ * test, alpha_threshold() of csrc/preprocess.cu restated above with this file's expf) is skipped without evaluating exp().  Both are verified against the compositing loop's own test at every pixel. */
 static int block_reject(float cx, float cy, float thr, float A, float B, float C, float x0, float x1, float y0, float y1)
 {
     const float det = A * C - B * B;
@@ -162,7 +197,7 @@ static int block_reject(float cx, float cy, float thr, float A, float B, float C
     const float inv = 1.0f / det;
     const float shrink = 1.0f - 8e-5f * (A * C * inv);
     if (!(shrink > 0.5f)) return 0;
-    const float tq = 1e-3f - thr;
+    const float tq = 2e-3f - thr;
     const float lim = 2.0f * tq * inv / shrink * 1.0001f;
     const float dx = fmaxf(fmaxf(x0 - cx, cx - x1), 0.f);
     const float dy = fmaxf(fmaxf(y0 - cy, cy - y1), 0.f);
@@ -179,7 +214,7 @@ long block_check(int n, const float* cx, const float* cy, const float* A, const 
     for (int i = 0; i < n; i++) {
         int x0, y0, x1, y1;
         tile_rect(cx[i], cy[i], radius[i], grid_x, grid_y, &x0, &y0, &x1, &y1);
-        const float thr = logf(1.0f / (255.0f * opac[i])) - 1e-3f;
+        const float thr = alpha_threshold(opac[i]);
         for (int by = y0 * TILE; by < y1 * TILE; by += bh)
             for (int bx = x0 * TILE; bx < x1 * TILE; bx += 8) {
                 const float fx0 = (float)bx + ox, fx1 = (float)(bx + 7) + ox, fy0 = (float)by + oy, fy1 = (float)(by + bh - 1) + oy;

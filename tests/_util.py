@@ -170,6 +170,8 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
     color, radii, depth, flow, acc, idxs = rast(**kw)
     out = dict(color=color, radii=radii, depth=depth, flow=flow, acc=acc, idxs=idxs)
     res = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    if kind == "ours":
+        res["inexact_thresholds"] = mod.last_inexact_thresholds()
     if intermediates and color.grad_fn is not None:
         fn = color.grad_fn
         if kind == "oracle":
@@ -182,8 +184,11 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
             g = torch.Generator().manual_seed(99)
             go["grad_depth"] = torch.randn(1, cam.H, cam.W, generator=g) * 1e-3
             go["grad_acc"] = torch.randn(1, cam.H, cam.W, generator=g) * 1e-3
-        torch.autograd.backward([color, depth, flow, acc],
-                                [go["grad_color"].to(dev), go["grad_depth"].to(dev), go["grad_flow"].to(dev), go["grad_acc"].to(dev)])
+        if grad_kind == "color_flow":   # what train.py's loss uses: depth / acc reach the backward as "no gradient"
+            torch.autograd.backward([color, flow], [go["grad_color"].to(dev), go["grad_flow"].to(dev)])
+        else:
+            torch.autograd.backward([color, depth, flow, acc],
+                                    [go["grad_color"].to(dev), go["grad_depth"].to(dev), go["grad_flow"].to(dev), go["grad_acc"].to(dev)])
         gr = dict(means3D=t["means3D"].grad, means2D=means2D.grad, dir3D=t["dir3D"].grad, opacities=t["opacities"].grad)
         if use_colors_precomp:
             gr["colors"] = extra["colors"].grad

@@ -34,3 +34,21 @@ def make_case(name: str):
         sc.sh_degree = 1
         return sc, dict(grad_kind="all")
     raise KeyError(name)
+
+
+def make_one_tile_torture(n: int = 24000, seed: int = synth.SEED + 77):
+    """>= 20k small, faint splats whose centres all fall into ONE 16x16 tile of a 48x48 image: the tile's list is
+    thousands of entries long and (almost) every entry contributes to some pixel without saturating it, so the
+    backward walks > 300 sub-batches of 64 (mbarrier ring wraps, n_contrib start logic) on a single tile."""
+    sc = synth.make_scene(P_static=n, P_dynamic=0, W=48, H=48, sigma_px=0.7, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    W, H = sc.cam.W, sc.cam.H
+    z = sc.xyz[:, 2].clone()
+    pix = torch.empty(n, 2).uniform_(16.0, 32.0, generator=g)
+    ndc = (2.0 * pix + 1.0) / torch.tensor([W, H], dtype=torch.float32) - 1.0
+    sc.xyz = torch.stack([ndc[:, 0] * sc.cam.tanfovx * z, ndc[:, 1] * sc.cam.tanfovy * z, z], dim=1).contiguous()
+    sc.xyz_disp = torch.zeros_like(sc.xyz_disp)
+    op = torch.empty(n, 1).uniform_(0.008, 0.03, generator=g)
+    sc.opacity = torch.log(op / (1.0 - op)).contiguous()
+    sc.timestamp = 0.0
+    return sc

@@ -1,0 +1,148 @@
+"""Gradient parity AT SCALE: the backward compositing kernel against the compiled, unmodified reference at the sizes the
+headline is quoted on (config 2: 500 k Gaussians, config 3: 2.0 M Gaussians, 1352x1014) and against the CPU oracle on a
+one-tile torture scene whose list is 24 000 entries long (hundreds of wraps of the staging ring).
+
+Tolerance: the north star's 1e-3 relative on every gradient tensor (|a - b| / max(|b|, floor), floor = 1 % of the tensor's
+99th-percentile magnitude, tests/_util.py).  The reference's own backward is not bit-reproducible (float atomics in
+arbitrary order: two runs of the reference on the same inputs differ by up to 7e-3 in single rotation / scale entries at
+these sizes), so each case runs the reference twice and the assertion is
+    max_rel(ours, reference run 1)  <=  1e-3 + max_rel(reference run 2, reference run 1)
+i.e. 1e-3 on top of the yardstick's own spread; both figures are printed and written to gpurun_out/parity_scale.json
+(DESIGN.md section 5 quotes them).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import _util as U
+from tests.cases import make_one_tile_torture
+from ex4dgs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-3
+OUT = os.environ.get("EX4DGS_PARITY_OUT") or \
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_scale.json")
+_cache = {}
+
+
+def _scene_and_reference(ref, cfg, grad_kind):
+    """Scene + two runs of the reference (they do not depend on our cull mode): kept for the next parametrisation."""
+    key = (cfg, grad_kind)
+    if key not in _cache:
+        _cache.clear()
+        sc = synth.make_config(cfg, pose="tilted", dir_nonzero=(grad_kind == "all"), bg=torch.tensor([0.2, 0.7, 0.4]))
+        r = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind=grad_kind, intermediates=True)
+        r2 = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind=grad_kind, intermediates=False)
+        _cache[key] = (sc, r, r2)
+    return _cache[key]
+
+
+def _record(name, rep):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    data = {}
+    if os.path.exists(OUT):
+        try:
+            data = json.load(open(OUT))
+        except Exception:
+            data = {}
+    data[name] = rep
+    json.dump(data, open(OUT, "w"), indent=1)
+
+
+def _grad_report(a, b, noise_of=None):
+    rep = {}
+    for k, g in b["grads"].items():
+        fl = U.grad_floor(g)
+        d = np.abs(np.asarray(a["grads"][k], np.float64) - g) / np.maximum(np.abs(g), fl)
+        rep[k] = dict(max_rel=float(d.max()), share_gt_1e4=float(np.mean(d > 1e-4)), floor=fl)
+        if noise_of is not None:
+            rep[k]["ref_vs_ref_max_rel"] = U.rel_err(noise_of["grads"][k], g, fl)
+    return rep
+
+
+@pytest.mark.parametrize("cull", [0, 1], ids=["exact-lists", "tile-cull"])
+@pytest.mark.parametrize("grad_kind", ["all", "color_flow"])
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_gradients_against_compiled_reference_at_scale(built, cfg, cull, grad_kind):
+    ref = U.reference_module()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    mod = U.ours_module()
+    sc, r, r2 = _scene_and_reference(ref, cfg, grad_kind)
+    old = mod.get_default_flags()
+    mod.set_default_flags(bool(cull))
+    try:
+        ours = U.run_impl(mod, sc, kind="ours", grads=True, grad_kind=grad_kind, intermediates=not cull)
+    finally:
+        mod.set_default_flags(bool(old))
+    assert ours["inexact_thresholds"] == 0
+    assert np.array_equal(ours["radii"], r["radii"])
+    assert np.array_equal(ours["idxs"], r["idxs"])
+    for k in ("color", "depth", "acc", "flow"):
+        assert np.array_equal(ours[k].view(np.uint32), r[k].view(np.uint32)), k + " not bit-identical"
+    if not cull:
+        assert np.array_equal(ours["inter"]["point_list"], r["inter"]["point_list"])
+        assert np.array_equal(ours["inter"]["n_contrib"], r["inter"]["n_contrib"])
+    rep = _grad_report(ours, r, noise_of=r2)
+    name = "%s/%s/%s" % (cfg, "tile-cull" if cull else "exact-lists", grad_kind)
+    _record(name, rep)
+    for k, v in rep.items():
+        print("%-28s %-10s max rel %.2e (reference run-to-run %.2e)  share > 1e-4: %.1e" %
+              (name, k, v["max_rel"], v["ref_vs_ref_max_rel"], v["share_gt_1e4"]))
+    for k, v in rep.items():
+        assert v["max_rel"] <= GRAD_RTOL + v["ref_vs_ref_max_rel"], (name, k, v)
+
+
+@pytest.mark.parametrize("grad_kind", ["all", "color_flow"])
+@pytest.mark.parametrize("cull", [0, 1], ids=["exact-lists", "tile-cull"])
+def test_one_tile_torture(built, cull, grad_kind):
+    """24 000 faint sub-pixel splats on one 16x16 tile: list of 24 000 entries, every pixel receives thousands of
+    contributions; 375 sub-batches of 64 through the 4-deep mbarrier ring of the backward.  Integers / lists / image
+    against the CPU oracle and, bit for bit, the compiled reference.  Gradients: every Gaussian here sums thousands of
+    terms of mixed sign, in three different orders (sequential on the CPU, atomics in the reference, butterfly + warp
+    reductions here); the two independent implementations of the SAME order-free mathematics - oracle and reference -
+    differ from each other by up to 1.5e-3 in single rotation entries, which is printed as the yardstick; the assertion
+    is 2e-3 against both."""
+    mod = U.ours_module()
+    sc = make_one_tile_torture()
+    old = mod.get_default_flags()
+    mod.set_default_flags(bool(cull))
+    try:
+        ours = U.run_impl(mod, sc, kind="ours", grads=True, grad_kind=grad_kind)
+    finally:
+        mod.set_default_flags(bool(old))
+    orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", grads=True, grad_kind=grad_kind)
+    assert np.array_equal(ours["radii"], orc["radii"])
+    assert np.array_equal(ours["idxs"], orc["idxs"])
+    if not cull:
+        assert np.array_equal(ours["inter"]["n_contrib"], orc["inter"]["n_contrib"])
+        assert np.array_equal(ours["inter"]["point_list"], orc["inter"]["point_list"])
+        assert np.array_equal(ours["inter"]["ranges"], orc["inter"]["ranges"])
+    assert int(ours["inter"]["n_contrib"].max()) >= 20000
+    for k in ("color", "depth", "acc", "flow"):
+        assert float(np.abs(ours[k] - orc[k]).max()) <= 1e-4 * max(1.0, float(np.abs(orc[k]).max())), k
+    name = "torture/%s/%s" % ("tile-cull" if cull else "exact-lists", grad_kind)
+    rep = _grad_report(ours, orc)
+    ref = U.reference_module()
+    if ref is not None:
+        r = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind=grad_kind, intermediates=False)
+        r2 = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind=grad_kind, intermediates=False)
+        for k in ("color", "depth", "acc", "flow"):
+            assert np.array_equal(ours[k].view(np.uint32), r[k].view(np.uint32)), k + " not bit-identical to the reference"
+        rep_ref = _grad_report(ours, r, noise_of=r2)
+        rep_or = _grad_report(orc, r)
+        for k in rep_ref:
+            rep_ref[k]["oracle_vs_ref_max_rel"] = rep_or[k]["max_rel"]
+        _record(name + "/vs_reference", rep_ref)
+        for k, v in rep_ref.items():
+            print("%-28s %-10s vs reference: max rel %.2e (reference run-to-run %.2e, CPU oracle vs reference %.2e)" %
+                  (name, k, v["max_rel"], v["ref_vs_ref_max_rel"], v["oracle_vs_ref_max_rel"]))
+            assert v["max_rel"] <= 2e-3, (name, k, v)
+    _record(name, rep)
+    for k, v in rep.items():
+        print("%-28s %-10s vs oracle:    max rel %.2e  share > 1e-4: %.1e" % (name, k, v["max_rel"], v["share_gt_1e4"]))
+        assert v["max_rel"] <= 2e-3, (name, k, v)
