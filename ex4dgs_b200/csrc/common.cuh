@@ -17,7 +17,7 @@
 
 // tuning knobs of the compositing kernels (defaults = measured best on B200, see profiles/)
 #ifndef EX_FWD_MINBLOCKS
-#define EX_FWD_MINBLOCKS 6      // CTAs of 128 threads (2 pixels per lane): 80 registers, 24 resident warps
+#define EX_FWD_MINBLOCKS 7      // CTAs of 128 threads (2 pixels per lane): 72 registers, 28 resident warps; 0.392 ms vs 0.407 (6) / 0.398 (8, groups of 2) at C3
 #endif
 #ifndef EX_BWD_MINBLOCKS
 #define EX_BWD_MINBLOCKS 6      // CTAs of 128 threads (2 pixels per lane, packed): 78 registers, 24 resident warps; 0.712 ms vs 0.744 (5) / 0.758 (4) at C3

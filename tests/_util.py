@@ -171,7 +171,8 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
     out = dict(color=color, radii=radii, depth=depth, flow=flow, acc=acc, idxs=idxs)
     res = {k: v.detach().cpu().numpy() for k, v in out.items()}
     if kind == "ours":
-        res["inexact_thresholds"] = mod.last_inexact_thresholds()
+        import ex4dgs_b200
+        res["inexact_thresholds"] = ex4dgs_b200.last_inexact_thresholds()
     if intermediates and color.grad_fn is not None:
         fn = color.grad_fn
         if kind == "oracle":
