@@ -160,15 +160,137 @@ def stats_tensors(Ns, Nd, dev):
         motion_xyz_ssim_error_accum=z(Nd, 1), motion_error_denom=z(Nd, 1))
 
 
+def reference_model(sc: synth.Scene, dev, cls):
+    """The reference's UNMODIFIED CGaussianModel (oracle/_ref/callers/scene/c_gaussian_model.py) built by its own
+    constructor and holding the synthetic scene in nn.Parameters of the reference's shapes."""
+    prev = torch.cuda.current_device()
+    torch.cuda.set_device(dev)          # the class calls .cuda() without a device
+    try:
+        m = cls(sh_degree=3, duration=int(sc.duration), interval=int(sc.interval), time_pad=int(sc.time_pad),
+                interp_type="cube", rot_interp_type="slerp", var_pad=sc.var_pad, kernel_size=sc.cam.kernel_size)
+    finally:
+        torch.cuda.set_device(prev)
+    P = lambda t: torch.nn.Parameter(t.detach().to(dev).float().contiguous().clone())     # noqa: E731
+    m._xyz, m._xyz_disp, m._rotation, m._scaling, m._opacity = P(sc.xyz), P(sc.xyz_disp), P(sc.rotation), P(sc.scaling), P(sc.opacity)
+    m._features_dc, m._features_rest = P(sc.features[:, :1]), P(sc.features[:, 1:])
+    m._xyz_motion, m._rotation_motion = P(sc.xyz_motion), P(sc.rotation_motion)
+    m._scaling_motion, m._opacity_motion = P(sc.scaling_motion), P(sc.opacity_motion)
+    m._opacity_duration_center, m._opacity_duration_var = P(sc.opacity_center[:, :, None]), P(sc.opacity_var[:, :, None])
+    m._features_dc_motion, m._features_rest_motion = P(sc.features_motion[:, :1]), P(sc.features_motion[:, 1:])
+    m.active_sh_degree = sc.sh_degree
+    return m
+
+
+def scene_model(sc: synth.Scene, dev):
+    """The same scene as a plain namespace with the reference's attribute names (what FusedGetters wraps)."""
+    from types import SimpleNamespace
+    P = lambda t: torch.nn.Parameter(t.detach().to(dev).float().contiguous().clone())     # noqa: E731
+    return SimpleNamespace(
+        _xyz=P(sc.xyz), _xyz_disp=P(sc.xyz_disp), _rotation=P(sc.rotation), _scaling=P(sc.scaling), _opacity=P(sc.opacity),
+        _xyz_motion=P(sc.xyz_motion), _rotation_motion=P(sc.rotation_motion), _scaling_motion=P(sc.scaling_motion),
+        _opacity_motion=P(sc.opacity_motion), _opacity_duration_center=P(sc.opacity_center[:, :, None]),
+        _opacity_duration_var=P(sc.opacity_var[:, :, None]), _features_dc=P(sc.features[:, :1]),
+        _features_rest=P(sc.features[:, 1:]), _features_dc_motion=P(sc.features_motion[:, :1]),
+        _features_rest_motion=P(sc.features_motion[:, 1:]),
+        duration=sc.duration, interval=sc.interval, time_shift=sc.time_shift, var_pad=sc.var_pad,
+        kernel_size=sc.cam.kernel_size, active_sh_degree=sc.sh_degree, max_sh_degree=3)
+
+
+def scene_inputs(sc: synth.Scene, dev, impl: str):
+    """The flat [P, .] tensors gaussian_renderer/__init__.py:62-95 hands to the rasterizer (static first, then dynamic,
+    pre-interpolated at the scene's timestamp), produced - outside every timed region - by the arm's OWN getters:
+    this repository's fused front-end for our arm, the reference's CGaussianModel getters for the reference arm."""
+    t = sc.timestamp
+    with torch.no_grad():
+        if impl == "ours":
+            from ex4dgs_b200.frontend import FusedGetters
+            g = FusedGetters(scene_model(sc, dev))
+            means, rots, scales, opac = g.get_xyz_at_t(t), g.get_rotation_at_t(t), g.get_scaling(), g.get_opacity_at_t(t)
+            shs = g.get_features().cat()
+        else:
+            cls = load_reference_model_class()
+            if cls is None:
+                raise SystemExit("reference arm: oracle/_ref/callers/scene/c_gaussian_model.py is missing (run oracle/build_ref.py)")
+            g = reference_model(sc, dev, cls)
+            means, rots, scales, opac = g.get_xyz_at_t(t), g.get_rotation_at_t(t), g.get_scaling(), g.get_opacity_at_t(t)
+            shs = g.get_features()
+    return dict(means3D=means.float().contiguous(), dir3D=torch.zeros_like(means), opacities=opac.float().contiguous(),
+                shs=shs.float().contiguous(), scales=scales.float().contiguous(), rotations=rots.float().contiguous())
+
+
+
+def kernel_source_hash():
+    """sha256/16 of the compositing kernels' sources: profiles/traffic.json records it at capture time, so that the
+    per-launch figures taken from the committed ncu capture (DRAM bytes, instruction counts) are only used for the code
+    they were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("render_fwd.cu", "render_bwd.cu", "common.cuh"):
+        with open(os.path.join(ROOT, "ex4dgs_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_reference_render():
+    """gaussian_renderer/__init__.py of the reference (installed unmodified under oracle/_ref/callers by
+    oracle/build_ref.py) - the ONE caller of the rasterizer; it imports `diff_gaussian_rasterization_df` by name."""
+    d = os.path.join(ROOT, "oracle", "_ref", "callers")
+    if not os.path.exists(os.path.join(d, "gaussian_renderer", "__init__.py")):
+        return None
+    import importlib
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    for m in ("gaussian_renderer",):
+        sys.modules.pop(m, None)
+    return importlib.import_module("gaussian_renderer")
+
+
+def make_render_api_step(frame: "Frame", impl: str, raster_mod):
+    """the frame through the UNCHANGED gaussian_renderer.render() (per-frame getters, torch.zeros_like
+    screen-space tensors, the torch.cuda.synchronize() at its end) + the same backward.  Our arm hands render() a
+    FusedGetters wrapper around the model and this repository's drop-in package; the reference arm its own
+    CGaussianModel and extension."""
+    import math
+    import types
+    sys.modules["diff_gaussian_rasterization_df"] = raster_mod if impl != "ours" else __import__("diff_gaussian_rasterization_df")
+    gr = load_reference_render()
+    if gr is None:
+        return None
+    sc, dev = frame.sc, frame.dev
+    cam = sc.cam
+    if impl == "ours":
+        from ex4dgs_b200.frontend import FusedGetters
+        pc = FusedGetters(scene_model(sc, dev))
+    else:
+        cls = load_reference_model_class()
+        if cls is None:
+            return None
+        pc = reference_model(sc, dev, cls)
+    vc = types.SimpleNamespace(FoVx=2 * math.atan(cam.tanfovx), FoVy=2 * math.atan(cam.tanfovy), image_height=cam.H,
+                               image_width=cam.W, world_view_transform=frame.view, full_proj_transform=frame.proj,
+                               camera_center=frame.campos, timestamp=sc.timestamp)
+    pipe = types.SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
+    params = [getattr(pc, n) for n in ("_xyz", "_xyz_disp", "_rotation", "_scaling", "_opacity", "_xyz_motion", "_rotation_motion",
+                                       "_scaling_motion", "_opacity_motion", "_opacity_duration_center", "_opacity_duration_var",
+                                       "_features_dc", "_features_rest", "_features_dc_motion", "_features_rest_motion")]
+
+    def step():
+        out = gr.render(vc, pc, pipe, frame.bg, near=cam.min_depth, far=cam.max_depth, timestamp=sc.timestamp)
+        torch.autograd.backward([out["render"], out["opticalflow"]], [frame.go["grad_color"], frame.go["grad_flow"]])
+        for q in params:
+            q.grad = None
+    return step
+
+
 class Frame:
     """Resident inputs of one rank + the step functions."""
 
-    def __init__(self, mod, sc: synth.Scene, dev, seed_off: int):
-        self.mod, self.sc, self.dev = mod, sc, dev
+    def __init__(self, mod, sc: synth.Scene, dev, seed_off: int, impl: str = "ours"):
+        self.mod, self.sc, self.dev, self.impl = mod, sc, dev, impl
         cam = sc.cam
-        inp = synth.flat_inputs(sc)
+        inp = scene_inputs(sc, dev, impl)
         self.P = inp["means3D"].shape[0]
-        self.t = {k: v.to(dev).requires_grad_(True) for k, v in inp.items()}
+        self.t = {k: v.detach().clone().requires_grad_(True) for k, v in inp.items()}
         self.means2D = torch.zeros(self.P, 3, device=dev, requires_grad=True)
         go = synth.grad_outputs(sc, seed_offset=7 + seed_off)
         self.go = {k: v.to(dev) for k, v in go.items()}
@@ -179,10 +301,22 @@ class Frame:
         g = torch.Generator().manual_seed(1234 + seed_off)
         self.h_gt = torch.rand(3, cam.H, cam.W, generator=g).pin_memory()
         self.h_cam = torch.cat([cam.viewmatrix.flatten(), cam.projmatrix.flatten(), cam.campos.flatten()]).pin_memory()
-        self.d_gt = torch.empty(3, cam.H, cam.W, device=dev)
+        # end-to-end legs: the ground-truth image of step i+1 is uploaded (from pinned memory, on the copy stream) while
+        # step i computes - one image per step inside the timed region, two device buffers; the loss all-reduce and its
+        # D2H run beside the next step on their own stream (ring of 4 loss words), so that no rank's compute stream waits
+        # for the slowest rank inside a step
+        self.d_gt2 = [torch.empty(3, cam.H, cam.W, device=dev) for _ in range(2)]
+        self.gt_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.gt_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.gt_step = 0
+        self.d_gt = self.d_gt2[0]
         self.d_cam = torch.empty(35, device=dev)
         self.h_loss = torch.zeros(1).pin_memory()
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self.loss_stream = torch.cuda.Stream(device=dev)
+        self.loss_ring = [torch.zeros(1, device=dev) for _ in range(4)]
+        self.loss_done = [torch.cuda.Event() for _ in range(4)]
+        self.loss_step = 0
         self.R = -1
         self.last = None
         # the L1 loss of the e2e step: utils/loss_utils.py:22-25 (torch ops) for the reference arm, this repository's
@@ -226,24 +360,59 @@ class Frame:
             self.R = int(color.grad_fn.num_rendered)
         self._zero()
 
-    def step_e2e(self, group=None):
-        # camera first (the forward needs it); the ground-truth image is only needed by the loss, so
-        # its H2D copy runs on a side stream and overlaps the forward - still inside the timed step
+    def gt_begin(self):
+        """H2D of this step's camera (main stream) and of the NEXT step's ground truth (copy stream, into the buffer the
+        previous step's loss has released); returns the device image of THIS step once its upload is awaited."""
         main = torch.cuda.current_stream(self.dev)
         self.d_cam.copy_(self.h_cam, non_blocking=True)
-        self.copy_stream.wait_stream(main)           # previous step's loss has consumed d_gt
+        i = self.gt_step
+        self.gt_step += 1
+        if i == 0:                                   # very first step: nothing was prefetched yet
+            with torch.cuda.stream(self.copy_stream):
+                self.d_gt2[0].copy_(self.h_gt, non_blocking=True)
+                self.gt_ready[0].record(self.copy_stream)
+        nxt = (i + 1) & 1
         with torch.cuda.stream(self.copy_stream):
-            self.d_gt.copy_(self.h_gt, non_blocking=True)
+            if i >= 1:
+                self.copy_stream.wait_event(self.gt_free[nxt])      # loss of step i-1 has read that buffer
+            self.d_gt2[nxt].copy_(self.h_gt, non_blocking=True)
+            self.gt_ready[nxt].record(self.copy_stream)
+        return i & 1
+
+    def gt_wait(self, buf):
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(self.gt_ready[buf])
+        self.d_gt = self.d_gt2[buf]
+        return self.d_gt
+
+    def gt_release(self, buf):
+        self.gt_free[buf].record(torch.cuda.current_stream(self.dev))
+
+    def loss_out(self, loss, group):
+        """all-reduce of the scalar loss (the ONE collective of the path) + D2H, off the compute stream"""
+        main = torch.cuda.current_stream(self.dev)
+        k = self.loss_step & 3
+        self.loss_step += 1
+        main.wait_event(self.loss_done[k])           # the ring slot's previous use (4 steps ago) is over
+        buf = self.loss_ring[k]
+        buf.copy_(loss.detach().reshape(1))
+        self.loss_stream.wait_stream(main)
+        with torch.cuda.stream(self.loss_stream):
+            if group is not None:
+                torch.distributed.all_reduce(buf, group=group)
+            self.h_loss.copy_(buf, non_blocking=True)
+            self.loss_done[k].record(self.loss_stream)
+
+    def step_e2e(self, group=None):
+        buf = self.gt_begin()
         c = self.d_cam
         rs = self.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
         color, radii, depth, flow, acc, idxs = self._raster(rs)
-        main.wait_stream(self.copy_stream)
-        loss = self.l1(color, self.d_gt) if self.l1 is not None else torch.abs((color - self.d_gt)).mean()
+        gt = self.gt_wait(buf)
+        loss = self.l1(color, gt) if self.l1 is not None else torch.abs((color - gt)).mean()
+        self.gt_release(buf)
         torch.autograd.backward([loss, flow], [None, self.go["grad_flow"]])
-        l = loss.detach().reshape(1)
-        if group is not None:
-            torch.distributed.all_reduce(l)
-        self.h_loss.copy_(l, non_blocking=True)
+        self.loss_out(loss, group)
         self._zero()
 
 
@@ -255,15 +424,10 @@ def make_train_step(frame: Frame, ref_loss, lambda_dssim=0.2):
         from ex4dgs_b200.loss import photometric_loss
 
     def step(group=None):
-        main = torch.cuda.current_stream(frame.dev)
-        frame.d_cam.copy_(frame.h_cam, non_blocking=True)
-        frame.copy_stream.wait_stream(main)
-        with torch.cuda.stream(frame.copy_stream):
-            frame.d_gt.copy_(frame.h_gt, non_blocking=True)
+        buf = frame.gt_begin()
         c = frame.d_cam
         image, radii, depth, flow, acc, idxs = frame._raster(frame.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35]))
-        main.wait_stream(frame.copy_stream)
-        gt_image = frame.d_gt
+        gt_image = frame.gt_wait(buf)
         if ref_loss is None:
             loss, Ll1, _, l1_errors, ssim_errors = photometric_loss(image, gt_image, lambda_dssim)
         else:
@@ -271,15 +435,13 @@ def make_train_step(frame: Frame, ref_loss, lambda_dssim=0.2):
             loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ref_loss.ssim(image, gt_image))
             l1_errors = (image - gt_image).abs().mean(dim=0)
             ssim_errors = ref_loss.ssim(image, gt_image, reduce=False).mean(dim=0)
+        frame.gt_release(buf)
         hook_tensor = torch.stack([acc[0], l1_errors, ssim_errors])
         flow_h = flow.register_hook(lambda grad: hook_tensor)
         loss = loss + flow.mean() * 0
         loss.backward()
         flow_h.remove()                                  # train.py:173
-        l = loss.detach().reshape(1)
-        if group is not None:
-            torch.distributed.all_reduce(l)
-        frame.h_loss.copy_(l, non_blocking=True)
+        frame.loss_out(loss, group)
         frame._zero()
     return step
 
@@ -297,8 +459,8 @@ STATIC_REG, MOTION_REG = 0.0001, 0.0001      # arguments/__init__.py:134-135 (ro
 
 def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_dssim=0.2, bookkeeping=True, ref_model_cls=None):
     """One full training iteration on the MODEL's native parameters (train.py:124-253 minus
-    densify_and_prune): per-frame getters (fused front-end kernel, row N1 / the PyTorch getters of
-    scene/c_gaussian_model.py:170-215,330-375 restated in synth.py), get_features' torch.cat, render,
+    densify_and_prune): per-frame getters (fused front-end kernel, row N1 / the getters of the reference's own
+    CGaussianModel instance, scene/c_gaussian_model.py:170-215,330-375), get_features' torch.cat, render,
     loss block (row N2 / utils/loss_utils.py), backward down to the 15 parameter tensors,
     optimizer.step() (FusedRAdam, row N4 / torch.optim.RAdam) and zero_grad(set_to_none=True).
     bookkeeping adds what train.py does around that every iteration: the static / motion regularisation terms
@@ -307,25 +469,40 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
     (ex4dgs_b200/stats.py, FusedRAdam guards) against the reference's own methods and expressions."""
     import copy
     sc, dev = frame.sc, frame.dev
-    m = copy.copy(sc)
+    Ns, Nd = sc.xyz.shape[0], sc.xyz_motion.shape[0]
+    if impl == "ours":
+        m = copy.copy(sc)
 
-    def par(t):
-        return torch.nn.Parameter(t.detach().to(dev).float().contiguous().clone())
+        def par(t):
+            return torch.nn.Parameter(t.detach().to(dev).float().contiguous().clone())
 
-    raw = ["xyz", "xyz_disp", "rotation", "scaling", "opacity", "xyz_motion", "rotation_motion", "scaling_motion",
-           "opacity_motion", "opacity_center", "opacity_var"]
-    for n in raw:
-        setattr(m, n, par(getattr(sc, n)))
-    f_dc, f_rest = par(sc.features[:, :1]), par(sc.features[:, 1:])
-    f_dc_m, f_rest_m = par(sc.features_motion[:, :1]), par(sc.features_motion[:, 1:])
-    by_name = {"xyz": m.xyz, "f_dc": f_dc, "f_rest": f_rest, "opacity": m.opacity, "scaling": m.scaling,
-               "rotation": m.rotation, "xyz_disp": m.xyz_disp, "motion_xyz": m.xyz_motion, "motion_f_dc": f_dc_m,
-               "motion_f_rest": f_rest_m, "motion_scaling": m.scaling_motion, "motion_opacity": m.opacity_motion,
-               "motion_opacity_center": m.opacity_center, "motion_opacity_var": m.opacity_var,
-               "motion_rotation": m.rotation_motion}
+        raw = ["xyz", "xyz_disp", "rotation", "scaling", "opacity", "xyz_motion", "rotation_motion", "scaling_motion",
+               "opacity_motion", "opacity_center", "opacity_var"]
+        for n in raw:
+            setattr(m, n, par(getattr(sc, n)))
+        f_dc, f_rest = par(sc.features[:, :1]), par(sc.features[:, 1:])
+        f_dc_m, f_rest_m = par(sc.features_motion[:, :1]), par(sc.features_motion[:, 1:])
+        by_name = {"xyz": m.xyz, "f_dc": f_dc, "f_rest": f_rest, "opacity": m.opacity, "scaling": m.scaling,
+                   "rotation": m.rotation, "xyz_disp": m.xyz_disp, "motion_xyz": m.xyz_motion, "motion_f_dc": f_dc_m,
+                   "motion_f_rest": f_rest_m, "motion_scaling": m.scaling_motion, "motion_opacity": m.opacity_motion,
+                   "motion_opacity_center": m.opacity_center, "motion_opacity_var": m.opacity_var,
+                   "motion_rotation": m.rotation_motion}
+    else:
+        # the reference arm runs the reference's OWN model class: its getters (get_xyz_at_t, get_opacity_at_t, get_scaling,
+        # get_rotation_at_t, get_features - what gaussian_renderer/__init__.py:62-95 calls) and its statistics methods
+        if ref_model_cls is None:
+            ref_model_cls = load_reference_model_class()
+        if ref_model_cls is None:
+            raise SystemExit("reference arm: oracle/_ref/callers/scene/c_gaussian_model.py is missing (run oracle/build_ref.py)")
+        gm = reference_model(sc, dev, ref_model_cls)
+        by_name = {"xyz": gm._xyz, "f_dc": gm._features_dc, "f_rest": gm._features_rest, "opacity": gm._opacity,
+                   "scaling": gm._scaling, "rotation": gm._rotation, "xyz_disp": gm._xyz_disp, "motion_xyz": gm._xyz_motion,
+                   "motion_f_dc": gm._features_dc_motion, "motion_f_rest": gm._features_rest_motion,
+                   "motion_scaling": gm._scaling_motion, "motion_opacity": gm._opacity_motion,
+                   "motion_opacity_center": gm._opacity_duration_center, "motion_opacity_var": gm._opacity_duration_var,
+                   "motion_rotation": gm._rotation_motion}
     groups = [{"params": [by_name[n]], "lr": lr * LR_SCALE, "name": n} for n, lr in MODEL_GROUPS]
     params = [g["params"][0] for g in groups]
-    Ns, Nd = sc.xyz.shape[0], sc.xyz_motion.shape[0]
     if impl == "ours":
         from types import SimpleNamespace
         from ex4dgs_b200 import stats as fstats
@@ -340,44 +517,34 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
         gaussians = SimpleNamespace(_xyz=m.xyz, **stats_tensors(Ns, Nd, dev))
     else:
         opt = torch.optim.RAdam(groups, lr=0.001)
-        gaussians = None
-        if bookkeeping:
-            if ref_model_cls is None:
-                raise SystemExit("reference arm: oracle/_ref/callers/scene/c_gaussian_model.py is missing (run oracle/build_ref.py)")
-            gaussians = ref_model_cls.__new__(ref_model_cls)      # __init__ would build an empty model; only the
-            for k, v in stats_tensors(Ns, Nd, dev).items():       # statistics tensors and the two tested parameters are used
-                setattr(gaussians, k, v)
-            gaussians._xyz, gaussians._xyz_motion = m.xyz, m.xyz_motion
-            gaussians._xyz_disp, gaussians._opacity_duration_var = m.xyz_disp, m.opacity_var
+        gaussians = gm
+        for k, v in stats_tensors(Ns, Nd, dev).items():
+            setattr(gaussians, k, v)
     P = Ns + Nd
     n_param = sum(p.numel() for p in params)
 
     def step(group=None):
-        main = torch.cuda.current_stream(dev)
-        frame.d_cam.copy_(frame.h_cam, non_blocking=True)
-        frame.copy_stream.wait_stream(main)
-        with torch.cuda.stream(frame.copy_stream):
-            frame.d_gt.copy_(frame.h_gt, non_blocking=True)
+        buf = frame.gt_begin()
         c = frame.d_cam
         rs = frame.settings(c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35])
         if impl == "ours":
             shs = SegmentedSH(f_dc, f_rest, f_dc_m, f_rest_m)       # the four tensors read in place, no cat
-        else:
-            # get_features (c_gaussian_model.py:337-353): cat(dc, rest) per kind, then static + dynamic
-            shs = torch.cat([torch.cat([f_dc, f_rest], dim=1), torch.cat([f_dc_m, f_rest_m], dim=1)], dim=0)
-        if impl == "ours":
             means, rots, scales, opac = interpolate_gaussians(
                 m.xyz, m.xyz_disp, m.rotation, m.scaling, m.opacity, m.xyz_motion, m.rotation_motion, m.scaling_motion,
                 m.opacity_motion, m.opacity_center, m.opacity_var, t=sc.timestamp, duration=sc.duration,
                 interval=sc.interval, time_shift=sc.time_shift, var_min=sc.var_pad / sc.interval)
         else:
-            means, rots, scales, opac = synth.model_getters(m)
+            # gaussian_renderer/__init__.py:62-95 on the reference's own class
+            means = gaussians.get_xyz_at_t(sc.timestamp, mode=0, training=True)
+            opac = gaussians.get_opacity_at_t(sc.timestamp, mode=0, training=True)
+            scales = gaussians.get_scaling(mode=0)
+            rots = gaussians.get_rotation_at_t(sc.timestamp, mode=0)
+            shs = gaussians.get_features(mode=0)
         means2D = torch.zeros(P, 3, device=dev, requires_grad=True)     # gaussian_renderer/__init__.py:28
         flow_in = torch.zeros(P, 3, device=dev, requires_grad=True)      # :66
         image, radii, depth, flow, acc, idxs = frame.mod.GaussianRasterizer(rs)(
             means3D=means, means2D=means2D, dir3D=flow_in, opacities=opac, shs=shs, scales=scales, rotations=rots)
-        main.wait_stream(frame.copy_stream)
-        gt_image = frame.d_gt
+        gt_image = frame.gt_wait(buf)
         if impl == "ours":
             loss, Ll1, _, l1_errors, ssim_errors = photometric_loss(image, gt_image, lambda_dssim)
         else:
@@ -385,6 +552,7 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
             loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ref_loss.ssim(image, gt_image))
             l1_errors = (image - gt_image).abs().mean(dim=0)
             ssim_errors = ref_loss.ssim(image, gt_image, reduce=False).mean(dim=0)
+        frame.gt_release(buf)
         hook_tensor = torch.stack([acc[0], l1_errors, ssim_errors])
         flow_h = flow.register_hook(lambda grad: hook_tensor)
         loss = loss + flow.mean() * 0
@@ -440,10 +608,7 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
             else:
                 with torch.no_grad():
                     gaussians.prune_nan_points()                  # train.py:253
-        l = loss.detach().reshape(1)
-        if group is not None:
-            torch.distributed.all_reduce(l)
-        frame.h_loss.copy_(l, non_blocking=True)
+        frame.loss_out(loss, group)
     # handles for tests/test_gpu_train_iter.py (trajectory parity of the two arms)
     step.params = dict(zip([n for n, _ in MODEL_GROUPS], params))
     step.gaussians = gaussians
@@ -482,7 +647,8 @@ def frame_stats(frame: Frame):
 def cpu_oracle_baseline(sc: synth.Scene):
     """One full fwd+bwd frame of the same workload on the CPU oracle port, all host threads."""
     from oracle import oracle as orc
-    inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
+    from oracle import getters_oracle as GO
+    inp = {k: v.numpy() for k, v in GO.flat_inputs(sc).items()}
     go = {k: v.numpy() for k, v in synth.grad_outputs(sc).items()}
     cam = sc.cam
     o = orc.Oracle()
@@ -496,6 +662,43 @@ def cpu_oracle_baseline(sc: synth.Scene):
     dt = time.time() - t0
     return {"value": 1.0 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "1 full frame (fwd+bwd) of the same workload, oracle/cpu_raster.c with OpenMP, %.1f s" % dt}
+
+
+
+def other_configs(mod, dev, K, W, cpu=True):
+    """Extra keys on BASELINE.json's other configs (parity-test cases, not the headline): config 1 on the CPU oracle port
+    (the config the reference's CPU plumbing would run), config 2 = 500 k static Gaussians forward-only, and the frame
+    size of config 5 (Technicolor 2048x1088, configs/techni/Painter.json:2) with the C3 Gaussian counts, fwd+bwd."""
+    out = {}
+
+    def run(sc, fwd_only):
+        fr = Frame(mod, sc, dev, seed_off=0, impl="ours")
+        fn = fr.step_forward if fwd_only else fr.step_device
+        for _ in range(max(W, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        st = frame_stats(fr)
+        del fr
+        torch.cuda.empty_cache()
+        return {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": K, "P": sc.P, "P_vis": st["P_vis"], "R": st["R"]}
+
+    sc2 = synth.make_config("C2")
+    out["config2_fwd_only_500k_1352x1014"] = run(sc2, True)
+    sc5 = synth.make_scene(1_500_000, 500_000, 2048, 1088)
+    out["config5_frame_2048x1088_fwd_bwd"] = run(sc5, False)
+    if cpu:
+        sc1 = synth.make_config("C1")
+        b = cpu_oracle_baseline(sc1)
+        b["sample"] = "config 1 (10 k static Gaussians, 400x400), " + b["sample"]
+        out["config1_cpu_port"] = b
+    return out
 
 
 _JSON_FD = None
@@ -541,17 +744,33 @@ def main():
                     help="--only-train-iter: include the per-iteration regularisers / statistics / NaN guards (train_iter_full)")
     ap.add_argument("--dp-grads", action="store_true",
                     help="train_iter leg under torchrun: SUM all-reduce of all gradients before the optimizer step")
+    ap.add_argument("--l2-flush", action="store_true",
+                    help="SURVEY 8d: write a 256 MB buffer (> the 126 MB L2) between the timed iterations of the device-timed leg; "
+                         "each iteration is then timed with its own pair of CUDA events and the flush is excluded")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the extra keys measured on BASELINE.json's other configs (1: CPU, 2: forward-only 500k, 5: 2048x1088)")
     ap.add_argument("--value-only", action="store_true", help="tuning aid (tools/tune.py): only the device-timed leg + stage timers")
     ap.add_argument("--tile-cull", type=int, default=int(os.environ.get("EX4DGS_TILE_CULL", "1")))
     args = ap.parse_args()
     rank, local_rank, ws = dist_env()
     K, W = args.steps, max(args.warmup, 3)
+    if ws > 1:
+        # one slice of the host cores per rank (all 8 GPUs of these boxes hang off one NUMA node): the per-frame Python
+        # work of 8 ranks otherwise migrates between cores and shows up as e2e jitter
+        try:
+            n = os.cpu_count() or 1
+            per = max(1, n // ws)
+            os.sched_setaffinity(0, set(range(local_rank * per, min(n, (local_rank + 1) * per))))
+            torch.set_num_threads(max(1, min(4, per)))
+        except Exception:
+            pass
     sc = synth.make_config(args.workload)
     cam = sc.cam
     cfg = {"workload": "%s: %d static + %d dynamic Gaussians (K=36 keyframes, pre-interpolated at t=137), %dx%d, SH degree 3, "
                        "fwd+bwd at the GaussianRasterizer boundary" % (args.workload, sc.xyz.shape[0], sc.xyz_motion.shape[0], cam.W, cam.H),
            "parallelism": "frame-parallel x%d (Gaussians replicated, one frame per GPU per step)" % ws,
-           "l2": "inputs (496 MB at C3) larger than the 126 MB L2; no explicit flush"}
+           "l2": ("256 MB written between timed iterations (--l2-flush), each iteration timed by its own event pair"
+                  if args.l2_flush else "inputs (496 MB at C3) larger than the 126 MB L2; no explicit flush (--l2-flush adds one)")}
 
     # ---------------- reference arm on the CPU (fallback when oracle/_ref is absent) ----------------
     ref_mod = None
@@ -587,7 +806,7 @@ def main():
     else:
         mod, lib = ref_mod, None
 
-    frame = Frame(mod, sc, dev, seed_off=rank)
+    frame = Frame(mod, sc, dev, seed_off=rank, impl=args.impl if args.impl == "ours" else "reference")
     if args.fwd_only:
         frame.step_device = frame.step_forward
         frame.step_e2e = lambda group=None: frame.step_forward()
@@ -598,10 +817,27 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev) if args.l2_flush else None
+
+    def timed(step_fn, steps, flush=False):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
+        if flush and flush_buf is not None:
+            evs = []
+            for _ in range(steps):
+                flush_buf.fill_(1.0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                step_fn()
+                b.record()
+                evs.append((a, b))
+            barrier()
+            t1 = time.time()
+            ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
+            if ws > 1:
+                torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+            return float(ms.item()), t0, t1
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step_fn()
@@ -654,7 +890,7 @@ def main():
     launches0 = lib.ex4dgs_launch_count() if lib else 0
     if lib and args.profile_in_timed:
         lib.ex4dgs_profile_enable(1)
-    ms_total, t0, t1 = timed(frame.step_device, K)
+    ms_total, t0, t1 = timed(frame.step_device, K, flush=args.l2_flush)
     launches = (lib.ex4dgs_launch_count() - launches0) if lib else 0
     stage_ms = None
     if lib:
@@ -676,6 +912,23 @@ def main():
     for _ in range(W):
         frame.step_e2e(group)
     ms_e2e, _, _ = timed(lambda: frame.step_e2e(group), K)
+
+    # the frame through the reference's unchanged gaussian_renderer.render()
+    render_api = None
+    if not args.fwd_only:
+        rstep = make_render_api_step(frame, "ours" if args.impl == "ours" else "reference", mod)
+        if rstep is not None:
+            Kr = max(20, K // 3)
+            for _ in range(W):
+                rstep()
+            ms_r, _, _ = timed(rstep, Kr)
+            render_api = {"value": ws * Kr / (ms_r / 1000.0), "unit": "frames/s", "ms_per_step": ms_r / Kr, "steps": Kr,
+                          "what": "fwd+bwd through the UNMODIFIED gaussian_renderer.render() of the reference (per-frame "
+                                  "getters, its torch.cuda.synchronize()), gradients down to the model parameters; "
+                                  + ("FusedGetters + this repository's drop-in package" if args.impl == "ours" else
+                                     "the reference's CGaussianModel getters + its own extension")}
+            del rstep
+            torch.cuda.empty_cache()
 
     # training-iteration leg (row N2): the same step with the reference's loss block, train.py:144-151
     train = None
@@ -753,6 +1006,8 @@ def main():
                             + ("(ex4dgs_b200.loss.l1_loss)" if args.impl == "ours" else "(utils/loss_utils.py l1_loss: torch abs/mean)")
                             + ", backward, loss (all-reduced over ranks) D2H; Gaussian parameters resident"},
             "clocks": clocks}
+    if render_api is not None:
+        line["render_api"] = render_api
     if train is not None:
         line["train_step"] = train
     if train_iter is not None:
@@ -771,25 +1026,33 @@ def main():
         t_render = stage_ms[3] / 1000.0
         achieved = alg_bytes / t_render / 1e9
         line["gpu_launches"] = int(launches)
-        line["config"].update({"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"],
+        line["scene_stats"] = {"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"],
                                "R_listed": st["R_listed"], "block_keep": st["block_keep"],
-                               "tile_cull": int(args.tile_cull), "mean_n_contrib": st["mean_n_contrib"]})
+                               "tile_cull": int(args.tile_cull), "mean_n_contrib": st["mean_n_contrib"]}
         traffic, traffic_src = None, "no ncu capture committed"
+        tj_all = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["render_fwd_kernel"]
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            tj_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj_all.get("kernel_source_sha16") != kernel_source_hash() or args.workload != "C3" or not args.tile_cull:
+                traffic_src = ("profiles/traffic.json was captured on other kernel sources / another workload (%s): not used"
+                               % tj_all.get("kernel_source_sha16"))
+                tj_all = None
+            else:
+                traffic, traffic_src = tj_all["render_fwd_kernel"]["dram_bytes_per_launch"], tj_all["render_fwd_kernel"]["source"]
         except Exception:
-            pass
+            tj_all = None
         line["roofline"] = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[3],
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                            "note": "the kernel is instruction-issue-bound (ncu: 81 % issue slots, 5 % DRAM): see issue_slots and profiles/SUMMARY.md"}
+                            "note": "the kernel is bound by instruction issue / the FP32 and ALU pipes, not by HBM (ncu: 5 % DRAM): see issue_slots and profiles/SUMMARY.md"}
         # what actually bounds the two compositing kernels: warp instructions issued (smsp__inst_executed.sum of the committed
         # ncu capture - a property of the workload, identical in every launch) over the live kernel time, against the SMs'
         # issue rate (4 schedulers x 1 warp instruction per clock x SM count x the SM clock measured under load)
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            tj = tj_all
+            if tj is None:
+                raise KeyError("no valid capture")
             props = torch.cuda.get_device_properties(dev)
             mhz = (clocks or {}).get("sm_mhz") or 1965.0
             peak_issue = props.multi_processor_count * 4 * mhz * 1e6
@@ -815,6 +1078,8 @@ def main():
                                   for n, b, ms in zip(names, stage_bytes, stage_ms) if ms > 0}
         if not args.no_cpu_baseline and ws == 1:
             line["cpu_baseline"] = cpu_oracle_baseline(sc)
+        if not args.no_extra_configs and ws == 1 and not args.fwd_only and args.workload == "C3":
+            line["other_configs"] = other_configs(mod, dev, min(K, 60), W, cpu=not args.no_cpu_baseline)
     else:
         line["impl"] = "reference"
         line["gpu_launches"] = 0

@@ -84,14 +84,25 @@ def interpolate_gaussians(xyz, xyz_disp, rotation, scaling, opacity, xyz_motion,
                                 opacity_motion, opacity_center, opacity_var, t, duration, interval, time_shift, var_min)
 
 
+_GETTER_INPUTS = ("_xyz", "_xyz_disp", "_rotation", "_scaling", "_opacity", "_xyz_motion", "_rotation_motion",
+                  "_scaling_motion", "_opacity_motion", "_opacity_duration_center", "_opacity_duration_var")
+
+
 class FusedGetters:
     """Duck-typed stand-in for the per-frame getters of CGaussianModel: wrap the model and hand the
     wrapper to the reference's unmodified render() (gaussian_renderer/__init__.py:28,62-95).  The four
     getters that render() calls for one timestamp (get_xyz_at_t twice, get_opacity_at_t,
-    get_scaling, get_rotation_at_t) are served from ONE fused kernel launch, cached per timestamp;
-    get_features returns the model's four SH tensors as a SegmentedSH (no torch.cat: render() only
-    forwards that object to the rasterizer, which reads the tensors in place and writes their gradients
-    directly).  Every other attribute is forwarded to the model.
+    get_scaling, get_rotation_at_t) are served from ONE fused kernel launch; get_features returns the model's
+    four SH tensors as a SegmentedSH (no torch.cat: render() only forwards that object to the rasterizer, which
+    reads the tensors in place and writes their gradients directly).  Every other attribute is forwarded to the model.
+
+    Cache: the result of the fused launch is kept for the getters of ONE frame.  It is dropped by get_features()
+    (the last getter render() calls) and is only reused while its key is unchanged - the timestamp, grad mode, and
+    identity, storage, shape and version counter of all eleven input tensors (so densification / reset_opacity, which
+    swap in new Parameters, and optimizer steps, which bump the versions - FusedRAdam does so explicitly -
+    invalidate it).  A wrapper may therefore be kept across iterations; a caller that drives the getters itself and
+    never calls get_features() should call new_frame() between frames when autograd is recording (a cached result
+    carries the graph of the frame it was computed in).
 
     `model` needs the reference's attribute names: _xyz, _xyz_disp, _rotation, _scaling, _opacity,
     _xyz_motion, _rotation_motion, _scaling_motion, _opacity_motion, _opacity_duration_center,
@@ -105,14 +116,18 @@ class FusedGetters:
     def __getattr__(self, name):
         return getattr(object.__getattribute__(self, "_m"), name)
 
+    def new_frame(self):
+        """Drop the cached result of the fused launch."""
+        object.__setattr__(self, "_key", None)
+        object.__setattr__(self, "_val", None)
+
     def _frame(self, t):
         m = self._m
-        key = (float(t), tuple(int(getattr(m, n)._version) for n in ("_xyz", "_xyz_motion", "_rotation_motion", "_opacity_motion")))
+        ten = [getattr(m, n) for n in _GETTER_INPUTS]
+        key = (float(t), torch.is_grad_enabled(), float(m.duration), float(m.interval), float(m.time_shift), float(m.var_pad),
+               tuple((id(x), x.data_ptr(), tuple(x.shape), int(x._version), bool(x.requires_grad)) for x in ten))
         if self._key != key:
-            val = interpolate_gaussians(m._xyz, m._xyz_disp, m._rotation, m._scaling, m._opacity, m._xyz_motion,
-                                        m._rotation_motion, m._scaling_motion, m._opacity_motion,
-                                        m._opacity_duration_center, m._opacity_duration_var, t=float(t),
-                                        duration=float(m.duration), interval=float(m.interval),
+            val = interpolate_gaussians(*ten, t=float(t), duration=float(m.duration), interval=float(m.interval),
                                         time_shift=float(m.time_shift), var_min=float(m.var_pad) / float(m.interval))
             object.__setattr__(self, "_key", key)
             object.__setattr__(self, "_val", val)
@@ -140,4 +155,5 @@ class FusedGetters:
         assert mode == 0
         from .rasterizer import SegmentedSH
         m = self._m
+        self.new_frame()          # last getter of render(): the next frame interpolates afresh
         return SegmentedSH(m._features_dc, m._features_rest, m._features_dc_motion, m._features_rest_motion)

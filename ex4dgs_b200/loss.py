@@ -21,6 +21,15 @@ import torch
 from . import _lib
 
 
+def _scalar_of(buf: torch.Tensor, i: int) -> torch.Tensor:
+    """0-dim tensor on element i of `buf` that is NOT an autograd view of it (it shares the storage through set_()):
+    the reference's training loop does `loss += ...` on the value it gets back (train.py:152-166), which autograd forbids
+    on a view created inside a custom Function ("Output 0 of ... is a view and is being modified inplace")."""
+    t = torch.empty(0, dtype=buf.dtype, device=buf.device)
+    t.set_(buf.untyped_storage(), buf.storage_offset() + i, (), ())
+    return t
+
+
 class _PhotometricLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, gt_image, lambda_dssim):
@@ -45,7 +54,7 @@ class _PhotometricLoss(torch.autograd.Function):
             raise RuntimeError("ex4dgs_loss_forward failed (%d): %s" % (rc, _lib.last_error()))
         ctx.save_for_backward(img, gt, scratch)
         ctx.lambda_dssim = float(lambda_dssim)
-        loss, ll1, ss = out3[0], out3[1], out3[2]
+        loss, ll1, ss = _scalar_of(out3, 0), _scalar_of(out3, 1), _scalar_of(out3, 2)
         ctx.mark_non_differentiable(ll1, ss, l1_err, ssim_err)
         return loss, ll1, ss, l1_err, ssim_err
 
@@ -90,7 +99,7 @@ class _L1Loss(torch.autograd.Function):
             raise RuntimeError("ex4dgs_l1_forward failed (%d): %s" % (rc, _lib.last_error()))
         ctx.save_for_backward(a, b)
         ctx.shape = network_output.shape
-        return out[0]
+        return _scalar_of(out, 0)
 
     @staticmethod
     def backward(ctx, g_loss):

@@ -111,6 +111,12 @@ class FusedRAdam(torch.optim.Optimizer):
                                                   C.c_void_p(flags_ptr) if flags_ptr else None, C.c_void_p(stream))
                 if rc < 0:
                     raise RuntimeError("ex4dgs_radam_step failed (%d): %s" % (rc, _lib.last_error()))
+                # the kernel wrote parameters and moments through raw pointers: tell autograd (and every cache keyed on
+                # Tensor._version, e.g. FusedGetters) that they changed, as torch's own optimizers do implicitly
+                for (p, g, m, v, lr, step, name) in chunk:
+                    torch.autograd.graph.increment_version(p)
+                    torch.autograd.graph.increment_version(m)
+                    torch.autograd.graph.increment_version(v)
         return loss
 
     def nan_detected(self) -> dict:

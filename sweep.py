@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--workload", default="C3")
-    ap.add_argument("--fused", type=int, default=1, help="1: fused front-end kernel, 0: PyTorch getters (synth.flat_inputs)")
+    ap.add_argument("--fused", type=int, default=1, help="1: fused front-end kernel, 0: comparison arm - the PyTorch restatement of the reference getters (oracle/getters_oracle.py)")
     ap.add_argument("--model-path", default=None, help="trained reference model directory (point_cloud/iteration_*/...)")
     ap.add_argument("--iteration", type=int, default=-1)
     ap.add_argument("--duration", type=float, default=300.0)
@@ -92,7 +92,8 @@ def main():
                                                                   interval=sc.interval, time_shift=sc.time_shift,
                                                                   var_min=sc.var_pad / sc.interval)
             else:
-                fi = synth.flat_inputs(sc_dev, t)      # PyTorch getters (synth.py restatement) on the GPU tensors
+                from oracle import getters_oracle as GO     # comparison arm only (--fused 0)
+                fi = GO.flat_inputs(sc_dev, t)      # PyTorch getters (restatement of c_gaussian_model.py) on the GPU tensors
                 means, rots, scales, opac = fi["means3D"], fi["rotations"], fi["scales"], fi["opacities"]
             return rast(means3D=means, means2D=zeros3, dir3D=zeros3, opacities=opac, shs=shs, scales=scales, rotations=rots)[0]
 

@@ -18,6 +18,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from ex4dgs_b200 import synth  # noqa: E402
+from oracle import getters_oracle as GO  # noqa: E402
 
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
@@ -145,7 +146,7 @@ def run_impl(mod, sc: synth.Scene, dev="cuda", grads: bool = True, subpixel: Opt
              grad_kind: str = "train", is_ref: bool = False, kind: Optional[str] = None) -> Dict[str, np.ndarray]:
     """One forward (+ backward) through `mod.GaussianRasterizer`; everything returned as numpy."""
     kind = kind or ("ref" if is_ref else "ours")
-    inp = synth.flat_inputs(sc)
+    inp = GO.flat_inputs(sc)
     P = inp["means3D"].shape[0]
     cam = sc.cam
     t = {k: v.detach().clone().to(dev).requires_grad_(grads) for k, v in inp.items()}

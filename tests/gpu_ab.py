@@ -21,6 +21,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import _util as U  # noqa: E402
 from ex4dgs_b200 import synth  # noqa: E402
+from oracle import getters_oracle as GO  # noqa: E402
 
 
 def compare(ours, ref, name):
@@ -54,7 +55,7 @@ def compare(ours, ref, name):
 
 
 def time_impl(mod, sc, iters=10, warmup=3, backward=True, dev="cuda"):
-    inp = {k: v.to(dev).requires_grad_(backward) for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.to(dev).requires_grad_(backward) for k, v in GO.flat_inputs(sc).items()}
     P = inp["means3D"].shape[0]
     means2D = torch.zeros(P, 3, device=dev, requires_grad=backward)
     rs = U.settings_for(mod, sc, dev)

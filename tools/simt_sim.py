@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ex4dgs_b200 import synth  # noqa: E402
+from oracle import getters_oracle as GO  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 
@@ -31,7 +32,7 @@ def main():
     lib.simulate_cursor.argtypes = [C.c_int] * 5 + [C.c_void_p] * 5
     lib.simulate_queue.argtypes = [C.c_int] * 6 + [C.c_void_p] * 5
     sc = synth.make_config(args.workload)
-    inp = {k: v.numpy() for k, v in synth.flat_inputs(sc).items()}
+    inp = {k: v.numpy() for k, v in GO.flat_inputs(sc).items()}
     cam = sc.cam
     o = orc.Oracle()
     t0 = time.time()
