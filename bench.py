@@ -617,7 +617,7 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
 
 
 def frame_stats(frame: Frame):
-    """R, P_vis and R_eff = sum_tiles min(range_len, 256*batches fetched) from the scratch buffers."""
+    """R, P_vis and R_eff = sum_tiles min(range_len, batch size * batches fetched) from the scratch buffers."""
     from ex4dgs_b200 import _lib
     t = frame.t
     color, radii, depth, flow, acc, idxs = frame._raster(frame.settings(frame.view, frame.proj, frame.campos))
@@ -637,10 +637,13 @@ def frame_stats(frame: Frame):
     word = view("tile_batches", np.uint32).astype(np.int64)
     batches, kept = word & 0xFF, word >> 8
     rl = ranges[:, 1] - ranges[:, 0]
-    r_eff = int(np.minimum(rl, 256 * batches).sum())
+    import ctypes
+    kb, kw = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.load().ex4dgs_forward_geometry(ctypes.byref(kb), ctypes.byref(kw))
+    r_eff = int(np.minimum(rl, kb.value * batches).sum())
     n_contrib = view("n_contrib", np.uint32)
     return dict(R=R, P_vis=int((radii > 0).sum().item()), R_eff=r_eff, tiles=int(ranges.shape[0]),
-                R_listed=int(rl.sum()), block_keep=float(kept.sum()) / max(1.0, 8.0 * r_eff),
+                R_listed=int(rl.sum()), block_keep=float(kept.sum()) / max(1.0, float(kw.value) * r_eff),
                 mean_n_contrib=float(n_contrib.mean()))
 
 

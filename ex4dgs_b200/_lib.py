@@ -50,6 +50,7 @@ SIGNATURES = {
     "ex4dgs_abi_version": (_I, []),
     "ex4dgs_last_error": (C.c_char_p, []),
     "ex4dgs_last_inexact_thresholds": (C.c_uint, []),
+    "ex4dgs_forward_geometry": (None, [C.POINTER(_I), C.POINTER(_I)]),
     "ex4dgs_geometry_bytes": (C.c_size_t, [_I]),
     "ex4dgs_binning_bytes": (C.c_size_t, [_I]),
     "ex4dgs_image_bytes": (C.c_size_t, [_I, _I]),

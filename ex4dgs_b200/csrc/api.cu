@@ -204,6 +204,13 @@ int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
 }
 const char* ex4dgs_last_error(void) { return g_err; }
 unsigned ex4dgs_last_inexact_thresholds(void) { return g_last_inexact; }
+void ex4dgs_forward_geometry(int* batch, int* warps)
+{
+    int b = 0, w = 0;
+    render_fwd_geometry(&b, &w);
+    if (batch) *batch = b;
+    if (warps) *warps = w;
+}
 
 size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
 size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R)).total; }
@@ -496,7 +503,7 @@ int ex4dgs_backward(
     bp.focal_y = height / (2.0f * tan_fovy);
     bp.focal_x = width / (2.0f * tan_fovx);
     bp.kernel_size = kernel_size;
-    bp.radii = radii; bp.clamped = geom.clamped; bp.gacc = geom.gacc;
+    bp.radii = radii; bp.clamped = geom.clamped; bp.gacc = geom.gacc; bp.rec = geom.rec;
     bp.W = (float)width; bp.H = (float)height;
     bp.dL_dmean2D = dL_dmean2D; bp.dL_dopacity = dL_dopacity; bp.dL_dcolor = dL_dcolor; bp.dL_dmean3D = dL_dmean3D;
     bp.dL_dcov3D = dL_dcov3D; bp.dL_dsh = dL_dsh; bp.dL_dscale = dL_dscale; bp.dL_drot = dL_drot; bp.dL_ddir = dL_ddir;

@@ -66,17 +66,22 @@ struct __align__(16) SplatRec {
 // reductions, consumed by the fused preprocess backward through gacc_load().
 //   g0 = (dL/dmean2D.x, .y, .z, dL/dopacity)   g1 = (dL/dconic.x, .y, .w, 0)
 //   g2 = (dL/dcolor r, g, b, 0)                g3 = (dL/ddir x, y, z, 0)
-// The compositing loop leaves the per-Gaussian constant factors out of its inner loop: it stores
-// g0.x / (-W/2), g0.y / (-H/2) and g1.xyz / (-1/2); gacc_load() applies them once per Gaussian.
+// The compositing loop leaves everything that is constant per Gaussian out of its inner loop: it stores
+// g0.x = S1 = sum gG dx and g0.y = S2 = sum gG dy instead of dL/dmean2D = (-W/2 (A S1 + B S2), -H/2 (C S2 + B S1))
+// (the 2x2 conic is applied here, once per Gaussian, from the record), and g1.xyz / (-1/2).
 struct __align__(16) GradAcc {
     float4 g0, g1, g2, g3;
 };
 
-__device__ __forceinline__ GradAcc gacc_load(const GradAcc* gacc, int idx, float W, float H)
+__device__ __forceinline__ GradAcc gacc_load(const GradAcc* gacc, const SplatRec* rec, int idx, float W, float H)
 {
     GradAcc g = gacc[idx];
-    g.g0.x *= -0.5f * W;
-    g.g0.y *= -0.5f * H;
+    if (g.g0.x != 0.f || g.g0.y != 0.f) {       // only Gaussians the compositing backward touched have a record
+        const float4 b = rec[idx].b;
+        const float S1 = g.g0.x, S2 = g.g0.y;
+        g.g0.x = (b.x * S1 + b.y * S2) * (-0.5f * W);
+        g.g0.y = (b.z * S2 + b.y * S1) * (-0.5f * H);
+    }
     g.g1.x *= -0.5f;
     g.g1.y *= -0.5f;
     g.g1.z *= -0.5f;
@@ -220,6 +225,7 @@ struct PreprocessBwdParams {
     const int* radii;
     const uint8_t* clamped;
     const GradAcc* gacc;
+    const SplatRec* rec; // forward records (conic for gacc_load)
     float W, H;          // image size (gacc_load)
     float* dL_dmean2D;
     float* dL_dopacity;
@@ -238,6 +244,7 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                          float min_depth, float max_depth, uint8_t* present, cudaStream_t s);
 void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, bool with_flow, cudaStream_t s);
+void render_fwd_geometry(int* batch, int* warps);     // splats staged per batch, warps per tile (statistics word of tile_batches)
 void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
 // photometric loss (loss.cu): scratch = per-block partial sums + the three SSIM derivative maps
 size_t loss_scratch_bytes(int W, int H);

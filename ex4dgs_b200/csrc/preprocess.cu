@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
 
-    const GradAcc g = gacc_load(p.gacc, idx, p.W, p.H);
+    const GradAcc g = gacc_load(p.gacc, p.rec, idx, p.W, p.H);
     // pass-through gradients (zero for Gaussians the compositing loop never touched)
     p.dL_dmean2D[3 * idx + 0] = g.g0.x; p.dL_dmean2D[3 * idx + 1] = g.g0.y; p.dL_dmean2D[3 * idx + 2] = g.g0.z;
     p.dL_dopacity[idx] = g.g0.w;
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
     const float* cam = s_cam + 32;
 
     if (idx < p.P) {
-        const GradAcc g = gacc_load(p.gacc, idx, p.W, p.H);
+        const GradAcc g = gacc_load(p.gacc, p.rec, idx, p.W, p.H);
         s_o3[0 * kBT * 3 + 3 * tid + 0] = g.g0.x; s_o3[0 * kBT * 3 + 3 * tid + 1] = g.g0.y; s_o3[0 * kBT * 3 + 3 * tid + 2] = g.g0.z;
         s_o3[1 * kBT * 3 + 3 * tid + 0] = g.g2.x; s_o3[1 * kBT * 3 + 3 * tid + 1] = g.g2.y; s_o3[1 * kBT * 3 + 3 * tid + 2] = g.g2.z;
         s_o3[2 * kBT * 3 + 3 * tid + 0] = g.g3.x; s_o3[2 * kBT * 3 + 3 * tid + 1] = g.g3.y; s_o3[2 * kBT * 3 + 3 * tid + 2] = g.g3.z;

@@ -348,11 +348,11 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
             }
             dLa = fm2(dLa, T);
             dLa = ff2(nTbg, inv, dLa);                                  // background term
-            // constant factors (-W/2, -H/2, -1/2) are applied once per Gaussian by gacc_load()
+            // what is constant per Gaussian (the 2x2 conic of dL/dmean2D, -W/2, -H/2, -1/2) is applied by gacc_load()
             const f2 gG = fm2(G, fm2(bc(b.w), dLa));
             const f2 X = fm2(gG, dx), Y = fm2(gG, dy);
-            v[0] = hsum2(ff2(Y, bc(b.y), fm2(X, bc(b.x))));
-            v[1] = hsum2(ff2(X, bc(b.y), fm2(Y, bc(b.z))));
+            v[0] = hsum2(X);
+            v[1] = hsum2(Y);
             v[4] = hsum2(fm2(X, dx));
             v[5] = hsum2(fm2(X, dy));
             v[6] = hsum2(fm2(Y, dy));

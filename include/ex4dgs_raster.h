@@ -370,6 +370,11 @@ const char* ex4dgs_last_error(void);
  * pairs of those Gaussians within 1e-3 of the limit as contributing although the forward (forward.cu:384-387) skipped
  * them. */
 unsigned ex4dgs_last_inexact_thresholds(void);
+/* Work decomposition of the forward compositing kernel, needed to read the per-tile statistics word `tile_batches`
+ * (ex4dgs_describe_buffers): low 8 bits = batches of *batch splats the tile fetched before all its pixels were done
+ * (R_eff of SURVEY.md 8d = sum over tiles of min(range length, batch * batches)), high 24 bits = (warp, splat) pairs
+ * that survived the per-warp block test, out of *warps warps per tile. */
+void ex4dgs_forward_geometry(int* batch, int* warps);
 
 #ifdef __cplusplus
 }
