@@ -425,7 +425,13 @@ int ex4dgs_forward(
     rp.point_list = bin.point_list;
     rp.rec = geom.rec;
     prof.mark();
-    launch_render_fwd(rp, grid_x, grid_y, flow32 != 0, s);
+    {
+        CUtensorMap rec_map;
+        const bool have_map = P > 0 && render_fwd_uses_gather() && make_record_tensor_map(&rec_map, geom.rec, P);
+        if (P > 0 && render_fwd_uses_gather() && !have_map)
+            return fail(EX4DGS_ERR_CUDA, "cuTensorMapEncodeTiled is not available (forward built with TMA gather staging)");
+        launch_render_fwd(rp, have_map ? &rec_map : nullptr, grid_x, grid_y, flow32 != 0, s);
+    }
     g_launches += 1;
     STAGE(debug, s, "render");
     prof.mark();
@@ -482,7 +488,13 @@ int ex4dgs_backward(
     rp.out_depth = const_cast<float*>(acc_depth); rp.out_acc = const_cast<float*>(acc);
     rp.dL_dpix = dL_dpix; rp.dL_ddepth = dL_ddepth; rp.dL_dflow = dL_dflow; rp.dL_dacc = dL_dacc;
     rp.gacc = geom.gacc;
-    if (R > 0) { launch_render_bwd(rp, grid_x, grid_y, s); g_launches += 1; }
+    if (R > 0) {
+        CUtensorMap rec_map;
+        if (!make_record_tensor_map(&rec_map, geom.rec, P) && EX_BWD_STAGE_GATHER4)
+            return fail(EX4DGS_ERR_CUDA, "cuTensorMapEncodeTiled is not available (the backward stages its records with TMA gathers)");
+        launch_render_bwd(rp, &rec_map, grid_x, grid_y, s);
+        g_launches += 1;
+    }
     STAGE(debug, s, "render backward");
     prof.mark();
 

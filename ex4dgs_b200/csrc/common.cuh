@@ -7,6 +7,7 @@
 // "pinned arithmetic"; reference sources: cuda_rasterizer/forward.cu:74-124,128-162,165-269,
 // auxiliary.h:41-87,267-294).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -26,6 +27,10 @@
 #define EX_FWD_STAGE_LDGSTS 1   // forward staging: 1 = per-thread 16-byte cp.async (LDGSTS), 0 = one TMA bulk copy per splat.
                                 // A bulk copy takes uniform registers, so 32 per-lane copies become a 32-trip loop of 9
                                 // instructions (7 % of the kernel's issue slots, ncu r1i); measured 0.422 vs 0.439 ms at C3.
+#endif
+#ifndef EX_BWD_STAGE_GATHER4
+#define EX_BWD_STAGE_GATHER4 1  // backward staging: 1 = TMA tile::gather4 (UTMALDG.2D.GATHER4: FOUR 64-byte records per instruction, row
+                                // indices = Gaussian ids, over a [P,16] float tensor map of the record array), 0 = one 48-byte bulk copy per record
 #endif
 #ifndef EX_BWD_FAST_RCP
 #define EX_BWD_FAST_RCP 1       // T /= (1 - alpha) with MUFU.RCP: 1.011 vs 1.075 ms at C3, gradients within the 1e-3 budget
@@ -243,9 +248,12 @@ void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t s);
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* view, const float* proj,
                          float min_depth, float max_depth, uint8_t* present, cudaStream_t s);
-void launch_render_fwd(const RenderParams& p, int grid_x, int grid_y, bool with_flow, cudaStream_t s);
+void launch_render_fwd(const RenderParams& p, const CUtensorMap* rec_map, int grid_x, int grid_y, bool with_flow, cudaStream_t s);
+bool render_fwd_uses_gather();    // compiled with EX_FWD_STAGE=2: needs the record tensor map
 void render_fwd_geometry(int* batch, int* warps);     // splats staged per batch, warps per tile (statistics word of tile_batches)
-void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s);
+void launch_render_bwd(const RenderParams& p, const CUtensorMap* rec_map, int grid_x, int grid_y, cudaStream_t s);
+// [P,16] float32 tensor map over the record array (box {16,1}) for the TMA gathers; false when the driver entry point is missing
+bool make_record_tensor_map(CUtensorMap* out, const SplatRec* rec, int P);
 // photometric loss (loss.cu): scratch = per-block partial sums + the three SSIM derivative maps
 size_t loss_scratch_bytes(int W, int H);
 cudaError_t launch_loss_forward(int W, int H, const float* img, const float* gt, float lambda, char* scratch,
@@ -618,6 +626,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// TMA gather: rows i0..i3 (all 16 floats = 64 bytes each) of the 2-D tensor `tmap` ([P,16] float32, box {16,1}) land densely at
+// smem_dst (128-byte aligned): 256 bytes per instruction, completion counted on `bar` (probed in tools/tma_gather4_probe.cu)
+__device__ __forceinline__ void tma_gather4_g2s(void* smem_dst, const CUtensorMap* tmap, int i0, int i1, int i2, int i3,
+                                                unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(0), "r"(i0), "r"(i1), "r"(i2), "r"(i3), "r"(smem_u32(bar)) : "memory");
 }
 
 // global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned)

@@ -23,6 +23,7 @@
 //  * NULL upstream gradients for depth / acc (autograd: "not used by the loss") select an instantiation
 //    without those terms.
 #include "common.cuh"
+#include <string.h>
 
 namespace {
 
@@ -146,13 +147,21 @@ __device__ __forceinline__ void pair_alpha2(f2 pw, float opac, bool c0, bool c1,
 // DA = false: the caller has no upstream gradient for the depth and accumulated-alpha images (NULL
 // dL_ddepth and dL_dacc - what autograd reports when the loss does not use them, as in train.py): their
 // terms are exactly zero and are dropped at compile time.  A NULL dL_dflow is read as zeros.
+#ifdef EX_BWD_HIST
+__device__ unsigned long long g_bwd_hist[66];     // [0..32]: entries by number of lanes with a contributing pixel; [33..65]: by number of contributing pixels / 2
+#endif
+
 template <bool DA>
-__global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p)
+__global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const __grid_constant__ RenderParams p,
+                                                                            const __grid_constant__ CUtensorMap rec_map)
 {
     constexpr int PPT = 2;
     constexpr int NW = 4;                  // warps per tile
     constexpr int SLOTS = kSub / NW;       // records each warp fetches per sub-batch
-    __shared__ float4 s_rec[kRing][kSub * 3];
+    constexpr int RS = EX_BWD_STAGE_GATHER4 ? 4 : 3;      // float4 words per staged record (the gather moves whole 64-byte rows)
+    constexpr unsigned RB = RS * 16;                       // bytes per staged record
+    static_assert(!EX_BWD_STAGE_GATHER4 || (SLOTS % 4 == 0), "a warp's slots are gathered four at a time");
+    __shared__ __align__(128) float4 s_rec[kRing][kSub * RS];
     __shared__ uint8_t s_list[NW][kSub];
     __shared__ int s_start;
     __shared__ __align__(8) unsigned long long s_full[kRing];     // records of a sub-batch have landed (TMA byte count)
@@ -251,9 +260,10 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
     f2 T = mk2(T_final[0], T_final[1]);
     f2 ar0 = bc(0.f), ar1 = bc(0.f), ar2 = bc(0.f);       // colour accumulated behind the current splat (accum_rec)
 
-    // TMA staging: every warp fetches SLOTS records of each sub-batch (lanes 0..SLOTS-1, one 48-byte
-    // bulk copy each; the dir3D word is not needed here), kAhead sub-batches ahead; thread 0 announces
-    // the byte count of the whole sub-batch to the buffer's `full` barrier.  No block-wide barrier in
+    // TMA staging: every warp fetches SLOTS records of each sub-batch, kAhead sub-batches ahead; thread 0 announces the byte
+    // count of the whole sub-batch to the buffer's `full` barrier.  EX_BWD_STAGE_GATHER4: lanes 0..SLOTS/4-1 issue ONE
+    // tile::gather4 each (four 64-byte records per instruction, row index = Gaussian id; slots beyond the list re-fetch
+    // record 0 and are never read); otherwise lanes 0..SLOTS-1 issue one 48-byte bulk copy each.  No block-wide barrier in
     // the loop: a warp only waits for the records (full) and, before refilling a buffer, for the
     // slowest warp to have left it (empty) - with kRing buffers the warps of a tile may drift
     // kRing - kAhead sub-batches apart, which absorbs the imbalance between the pixel blocks.
@@ -264,8 +274,22 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
     };
     auto stage = [&](int r, int id) {
         const int buf = r % kRing;
-        if (tid == 0) mbar_arrive_expect_tx(&s_full[buf], (unsigned)(min(kSub, start - r * kSub) * 48));
-        if (id >= 0) tma_bulk_g2s(&s_rec[buf][slot * 3], p.rec + id, 48, &s_full[buf]);
+        const int cnt_r = min(kSub, start - r * kSub);
+#if EX_BWD_STAGE_GATHER4
+        if (tid == 0) {
+            int groups = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) groups += (max(0, min(SLOTS, cnt_r - w * SLOTS)) + 3) >> 2;
+            mbar_arrive_expect_tx(&s_full[buf], (unsigned)(groups * 256));
+        }
+        const int i0 = __shfl_sync(full, id, (4 * lane) & 31), i1 = __shfl_sync(full, id, (4 * lane + 1) & 31);
+        const int i2 = __shfl_sync(full, id, (4 * lane + 2) & 31), i3 = __shfl_sync(full, id, (4 * lane + 3) & 31);
+        if (lane < SLOTS / 4 && i0 >= 0)
+            tma_gather4_g2s(&s_rec[buf][(warp * SLOTS + 4 * lane) * RS], &rec_map, i0, max(i1, 0), max(i2, 0), max(i3, 0), &s_full[buf]);
+#else
+        if (tid == 0) mbar_arrive_expect_tx(&s_full[buf], (unsigned)(cnt_r * 48));
+        if (id >= 0) tma_bulk_g2s(&s_rec[buf][slot * RS], p.rec + id, 48, &s_full[buf]);
+#endif
     };
 #pragma unroll
     for (int r = 0; r < kAhead; r++)
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
                 const int jj = g + lane;
                 bool keep = false;
                 // entry jj sits at list position q = start-1-(r*kSub+jj); only q < warp_last can matter
-                if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !EX_BLOCK_TEST(s[jj * 3], s[jj * 3 + 1], box);
+                if (jj < cnt && (start - 1 - (r * kSub + jj)) < warp_last) keep = !EX_BLOCK_TEST(s[jj * RS], s[jj * RS + 1], box);
                 const unsigned m = __ballot_sync(full, keep);
                 if (keep) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)jj;
                 nw += __popc(m);
@@ -303,8 +327,8 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 #pragma unroll(kUnroll)
         for (int e = 0; e < nw; e++) {
             const int j = s_list[warp][e];
-            const float4 a = lds128(sb + j * 48);
-            const float4 b = lds128(sb + j * 48 + 16);
+            const float4 a = lds128(sb + j * RB);
+            const float4 b = lds128(sb + j * RB + 16);
             // power of both pixels with the forward's FMA placement (render_fwd.cu pair_power), packed
             const f2 dx = fa2(bc(a.x), npx), dy = fa2(bc(a.y), npy);
             const f2 pw = ff2(ff2(dx, fm2(dx, bc(b.x)), fm2(fm2(bc(b.z), dy), dy)), bc(-0.5f), fm2(fm2(bc(-b.y), dx), dy));
@@ -313,9 +337,16 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
             bool c0 = (j >= jthr0) && !(pw0 > 0.0f) && !(pw0 < a.w);
             bool c1 = (j >= jthr1) && !(pw1 > 0.0f) && !(pw1 < a.w);
             if (!__any_sync(full, c0 | c1)) continue;
+#ifdef EX_BWD_HIST
+            {
+                const unsigned m = __ballot_sync(full, c0 | c1);
+                const int npix = __popc(__ballot_sync(full, c0)) + __popc(__ballot_sync(full, c1));
+                if (lane == 0) { atomicAdd(&g_bwd_hist[__popc(m)], 1ull); atomicAdd(&g_bwd_hist[33 + npix / 2], 1ull); }
+            }
+#endif
             f2 G, al;
             pair_alpha2(pw, b.w, c0, c1, G, al);
-            const float4 c = lds128(sb + j * 48 + 32);
+            const float4 c = lds128(sb + j * RB + 32);
             const f2 oma = ff2(al, bc(-1.0f), bc(1.0f));                // 1 - alpha (exact product: == fa(1, -alpha))
             float om0, om1;
             split2(oma, om0, om1);
@@ -375,9 +406,44 @@ __global__ void __launch_bounds__(128, EX_BWD_MINBLOCKS) render_bwd_kernel(const
 
 }  // namespace
 
-void launch_render_bwd(const RenderParams& p, int grid_x, int grid_y, cudaStream_t s)
+#ifdef EX_BWD_HIST
+extern "C" void ex4dgs_debug_bwd_hist(unsigned long long* out)
+{
+    cudaMemcpyFromSymbol(out, g_bwd_hist, sizeof(g_bwd_hist));
+    unsigned long long z[66] = {0};
+    cudaMemcpyToSymbol(g_bwd_hist, z, sizeof(z));
+}
+#endif
+
+void launch_render_bwd(const RenderParams& p, const CUtensorMap* rec_map, int grid_x, int grid_y, cudaStream_t s)
 {
     dim3 grid(grid_x, grid_y, 1);
-    if (p.dL_ddepth || p.dL_dacc) render_bwd_kernel<true><<<grid, 128, 0, s>>>(p);
-    else render_bwd_kernel<false><<<grid, 128, 0, s>>>(p);
+    if (p.dL_ddepth || p.dL_dacc) render_bwd_kernel<true><<<grid, 128, 0, s>>>(p, *rec_map);
+    else render_bwd_kernel<false><<<grid, 128, 0, s>>>(p, *rec_map);
+}
+
+bool make_record_tensor_map(CUtensorMap* out, const SplatRec* rec, int P)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;      // resolved once through the runtime: the library does not link libcuda
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    memset(out, 0, sizeof(*out));
+    if (!enc || P <= 0) return false;
+    const cuuint64_t dims[2] = {16, (cuuint64_t)P};
+    const cuuint64_t strides[1] = {sizeof(SplatRec)};
+    const cuuint32_t box[2] = {16, 1}, estr[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<SplatRec*>(rec), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
