@@ -9,6 +9,14 @@
 //             (cov3D), :372-423 (preprocessCUDA) including the deviations listed in SURVEY.md A.3
 //             (Q1: mip-coef gradient dropped, Q2: cov2D->mean term overwritten, Q6: no quaternion
 //             normalisation).
+//
+// Provenance note: the kernel structure here is this repository's own (fused K10 + K11, shared-memory staged coalesced
+// I/O, zero-fill folded in, exact alpha threshold), but the closed-form derivative EXPRESSIONS of the backward
+// (bwd_conic_to_cov3d, bwd_mean2d_to_mean3d, bwd_cov3d_to_scale_rot, bwd_dir_to_mean) and the real-SH basis / derivative
+// tables restate backward.cu:225-251, :403-410, :342-366, auxiliary.h:235-245 and forward.cu:30-59 / backward.cu:47-123 term
+// for term with renamed identifiers: the order of operations is part of the 1e-3 gradient-parity contract, the SH basis
+// is fixed mathematics, and a derivative has one closed form.  They live in ONE set of __device__ functions used by both
+// backward kernels.
 #include "common.cuh"
 #include <math.h>
 #include <stdio.h>
@@ -379,6 +387,120 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
     present[idx] = out ? 0 : 1;
 }
 
+__device__ __forceinline__ void sh_basis_and_grad(int D, float x, float y, float z, int k,
+                                                  float& b, float& bx, float& by, float& bz)
+{
+    // value and d/d(x,y,z) of real SH basis k (forward.cu:30-59, backward.cu:47-123), k < (D+1)^2
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    bx = by = bz = 0.f;
+    switch (k) {
+    case 0: b = kC0; break;
+    case 1: b = -kC1 * y; by = -kC1; break;
+    case 2: b = kC1 * z; bz = kC1; break;
+    case 3: b = -kC1 * x; bx = -kC1; break;
+    case 4: b = kC2[0] * xy; bx = kC2[0] * y; by = kC2[0] * x; break;
+    case 5: b = kC2[1] * yz; by = kC2[1] * z; bz = kC2[1] * y; break;
+    case 6: b = kC2[2] * (2.f * zz - xx - yy); bx = kC2[2] * 2.f * -x; by = kC2[2] * 2.f * -y; bz = kC2[2] * 2.f * 2.f * z; break;
+    case 7: b = kC2[3] * xz; bx = kC2[3] * z; bz = kC2[3] * x; break;
+    case 8: b = kC2[4] * (xx - yy); bx = kC2[4] * 2.f * x; by = kC2[4] * 2.f * -y; break;
+    case 9: b = kC3[0] * y * (3.f * xx - yy); bx = kC3[0] * 3.f * 2.f * xy; by = kC3[0] * 3.f * (xx - yy); break;
+    case 10: b = kC3[1] * xy * z; bx = kC3[1] * yz; by = kC3[1] * xz; bz = kC3[1] * xy; break;
+    case 11: b = kC3[2] * y * (4.f * zz - xx - yy); bx = kC3[2] * -2.f * xy; by = kC3[2] * (-3.f * yy + 4.f * zz - xx); bz = kC3[2] * 4.f * 2.f * yz; break;
+    case 12: b = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = kC3[3] * -3.f * 2.f * xz; by = kC3[3] * -3.f * 2.f * yz; bz = kC3[3] * 3.f * (2.f * zz - xx - yy); break;
+    case 13: b = kC3[4] * x * (4.f * zz - xx - yy); bx = kC3[4] * (-3.f * xx + 4.f * zz - yy); by = kC3[4] * -2.f * xy; bz = kC3[4] * 4.f * 2.f * xz; break;
+    case 14: b = kC3[5] * z * (xx - yy); bx = kC3[5] * 2.f * xz; by = kC3[5] * -2.f * yz; bz = kC3[5] * (xx - yy); break;
+    default: b = kC3[6] * x * (xx - 3.f * yy); bx = kC3[6] * 3.f * (xx - yy); by = kC3[6] * -3.f * 2.f * xy; break;
+    }
+}
+
+// ---- shared pieces of the two backward kernels (closed-form derivatives; the expressions follow backward.cu:225-251,
+// :403-410, :342-366 and auxiliary.h:235-245 term for term - a derivative has one form - including the reference's
+// deviations from the true gradient) ---------------------------------------------------------------
+
+// conic gradient -> cov2D -> cov3D (backward.cu:144-257).  The cov2D -> mean term (backward.cu:259-299) is overwritten by
+// the assignment at backward.cu:414 in the reference, so it is not computed (A.3-Q2); the mip-coefficient gradient is
+// dropped as in the reference (A.3-Q1).
+__device__ __forceinline__ void bwd_conic_to_cov3d(const PreprocessBwdParams& p, const float* view, float mx, float my, float mz,
+                                                   const float* cov3D, float dcx, float dcy, float dcz, float* dcov)
+{
+    const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
+    const float a = cv.a + p.kernel_size, b = cv.b, c = cv.c + p.kernel_size;
+    const float denom = a * c - b * b;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    if (denom2inv != 0) {
+        const float dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
+        const float dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
+        const float dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+        const float* T0 = cv.T0; const float* T1 = cv.T1;
+        dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
+        dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
+        dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
+        dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
+        dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
+        dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
+    }
+}
+
+// mean2D -> mean3D through the projection (backward.cu:396-414; an assignment, not an accumulation)
+__device__ __forceinline__ void bwd_mean2d_to_mean3d(const float* pr, float mx, float my, float mz, float gx, float gy, float gz,
+                                                     float* dmean)
+{
+    const float hw = pr[3] * mx + pr[7] * my + pr[11] * mz + pr[15];
+    const float m_w = 1.0f / (hw + 0.0000001f);
+    const float mul1 = (pr[0] * mx + pr[4] * my + pr[8] * mz + pr[12]) * m_w * m_w;
+    const float mul2 = (pr[1] * mx + pr[5] * my + pr[9] * mz + pr[13]) * m_w * m_w;
+    const float mul3 = (pr[2] * mx + pr[6] * my + pr[10] * mz + pr[14]) * m_w * m_w;
+    dmean[0] = (pr[0] * m_w - pr[3] * mul1) * gx + (pr[1] * m_w - pr[3] * mul2) * gy + (pr[2] * m_w - pr[3] * mul3) * gz;
+    dmean[1] = (pr[4] * m_w - pr[7] * mul1) * gx + (pr[5] * m_w - pr[7] * mul2) * gy + (pr[6] * m_w - pr[7] * mul3) * gz;
+    dmean[2] = (pr[8] * m_w - pr[11] * mul1) * gx + (pr[9] * m_w - pr[11] * mul2) * gy + (pr[10] * m_w - pr[11] * mul3) * gz;
+}
+
+// gradient of the SH view direction through dir = o / |o| (auxiliary.h:235-245), added to dmean
+__device__ __forceinline__ void bwd_dir_to_mean(float ox, float oy, float oz, float ddx, float ddy, float ddz, float* dmean)
+{
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+    dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+    dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+}
+
+// cov3D -> scale / rotation (backward.cu:304-367), no quaternion-normalisation Jacobian (A.3-Q6)
+__device__ __forceinline__ void bwd_cov3d_to_scale_rot(float4 q, float sx, float sy, float sz, float mod, const float* dcov,
+                                                       float* dscale, float4& drot)
+{
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    // R[c][r] column-major as in the forward
+    const float R[3][3] = {
+        {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+        {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+        {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+    const float s[3] = {mod * sx, mod * sy, mod * sz};
+    // M[c][r] = s_r R[c][r];  dL_dSigma symmetric with halved off-diagonals
+    const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                            {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                            {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+    // dL_dM = 2 M dL_dSigma : dL_dM[c][r] = 2 sum_k M[k][r] dS[c][k]
+    float dM[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++)
+            dM[c][rr] = 2.0f * (s[rr] * R[0][rr] * dS[c][0] + s[rr] * R[1][rr] * dS[c][1] + s[rr] * R[2][rr] * dS[c][2]);
+    // dL_dscale_a = sum_b R[b][a] dM[b][a]
+#pragma unroll
+    for (int a = 0; a < 3; a++) dscale[a] = R[0][a] * dM[0][a] + R[1][a] * dM[1][a] + R[2][a] * dM[2][a];
+    float Mt[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) Mt[a][b2] = dM[b2][a] * s[a];
+    drot.x = 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
+    drot.y = 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r * (Mt[1][2] - Mt[2][1]) - 4 * x * (Mt[2][2] + Mt[1][1]);
+    drot.z = 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) - 4 * y * (Mt[2][2] + Mt[0][0]);
+    drot.w = 2 * r * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) - 4 * z * (Mt[1][1] + Mt[0][0]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused backward of the per-Gaussian steps (backward.cu computeCov2DCUDA + preprocessCUDA in one
 // pass, zero-fill of invisible Gaussians folded in).
@@ -422,41 +544,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
             sx = __ldg(p.scales + 3 * idx); sy = __ldg(p.scales + 3 * idx + 1); sz = __ldg(p.scales + 3 * idx + 2);
             cov3d_from_scale_rot(sx, sy, sz, p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
         }
-        // ---- conic -> cov2D -> cov3D (backward.cu:144-257)
-        {
-            const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
-            const float a = cv.a + p.kernel_size, b = cv.b, c = cv.c + p.kernel_size;
-            const float dcx = g.g1.x, dcy = g.g1.y, dcz = g.g1.z;
-            const float denom = a * c - b * b;
-            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-            if (denom2inv != 0) {
-                const float dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
-                const float dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
-                const float dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
-                const float* T0 = cv.T0; const float* T1 = cv.T1;
-                dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
-                dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
-                dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
-                dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
-                dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
-                dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
-            }
-            // the cov2D -> mean term (backward.cu:259-299) is overwritten by the assignment at
-            // backward.cu:414 in the reference, so it is not computed.
-        }
-        // ---- mean2D -> mean3D through the projection (backward.cu:396-414)
-        {
-            const float* pr = s_cam + 16;
-            const float hw = pr[3] * mx + pr[7] * my + pr[11] * mz + pr[15];
-            const float m_w = 1.0f / (hw + 0.0000001f);
-            const float mul1 = (pr[0] * mx + pr[4] * my + pr[8] * mz + pr[12]) * m_w * m_w;
-            const float mul2 = (pr[1] * mx + pr[5] * my + pr[9] * mz + pr[13]) * m_w * m_w;
-            const float mul3 = (pr[2] * mx + pr[6] * my + pr[10] * mz + pr[14]) * m_w * m_w;
-            const float gx = g.g0.x, gy = g.g0.y, gz = g.g0.z;
-            dmean[0] = (pr[0] * m_w - pr[3] * mul1) * gx + (pr[1] * m_w - pr[3] * mul2) * gy + (pr[2] * m_w - pr[3] * mul3) * gz;
-            dmean[1] = (pr[4] * m_w - pr[7] * mul1) * gx + (pr[5] * m_w - pr[7] * mul2) * gy + (pr[6] * m_w - pr[7] * mul3) * gz;
-            dmean[2] = (pr[8] * m_w - pr[11] * mul1) * gx + (pr[9] * m_w - pr[11] * mul2) * gy + (pr[10] * m_w - pr[11] * mul3) * gz;
-        }
+        bwd_conic_to_cov3d(p, view, mx, my, mz, cov3D, g.g1.x, g.g1.y, g.g1.z, dcov);
+        bwd_mean2d_to_mean3d(s_cam + 16, mx, my, mz, g.g0.x, g.g0.y, g.g0.z, dmean);
         // ---- SH backward (backward.cu:20-139)
         if (p.shs != nullptr) {
             const float ox = mx - cam[0], oy = my - cam[1], oz = mz - cam[2];
@@ -465,44 +554,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
             const uint8_t cl = p.clamped[idx];
             float dRGB[3] = {(cl & 1) ? 0.f : g.g2.x, (cl & 2) ? 0.f : g.g2.y, (cl & 4) ? 0.f : g.g2.z};
             const float* sh = p.shs + (size_t)idx * p.M * 3;
-            float b[16];
-            float dbx[16], dby[16], dbz[16];      // d basis_k / d(x,y,z)
+            const int nb = (p.D + 1) * (p.D + 1);
+            float b[16], dbx[16], dby[16], dbz[16];      // basis_k and d basis_k / d(x,y,z)
 #pragma unroll
-            for (int k = 0; k < 16; k++) { b[k] = 0.f; dbx[k] = 0.f; dby[k] = 0.f; dbz[k] = 0.f; }
-            int nb = 1;
-            b[0] = kC0;
-            if (p.D > 0) {
-                nb = 4;
-                b[1] = -kC1 * y; b[2] = kC1 * z; b[3] = -kC1 * x;
-                dby[1] = -kC1; dbz[2] = kC1; dbx[3] = -kC1;
-                if (p.D > 1) {
-                    nb = 9;
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.f * zz - xx - yy);
-                    b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy);
-                    dbx[4] = kC2[0] * y; dby[4] = kC2[0] * x;
-                    dby[5] = kC2[1] * z; dbz[5] = kC2[1] * y;
-                    dbx[6] = kC2[2] * 2.f * -x; dby[6] = kC2[2] * 2.f * -y; dbz[6] = kC2[2] * 2.f * 2.f * z;
-                    dbx[7] = kC2[3] * z; dbz[7] = kC2[3] * x;
-                    dbx[8] = kC2[4] * 2.f * x; dby[8] = kC2[4] * 2.f * -y;
-                    if (p.D > 2) {
-                        nb = 16;
-                        b[9] = kC3[0] * y * (3.f * xx - yy);
-                        b[10] = kC3[1] * xy * z;
-                        b[11] = kC3[2] * y * (4.f * zz - xx - yy);
-                        b[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                        b[13] = kC3[4] * x * (4.f * zz - xx - yy);
-                        b[14] = kC3[5] * z * (xx - yy);
-                        b[15] = kC3[6] * x * (xx - 3.f * yy);
-                        dbx[9] = kC3[0] * 3.f * 2.f * xy;          dby[9] = kC3[0] * 3.f * (xx - yy);
-                        dbx[10] = kC3[1] * yz;                     dby[10] = kC3[1] * xz;          dbz[10] = kC3[1] * xy;
-                        dbx[11] = kC3[2] * -2.f * xy;              dby[11] = kC3[2] * (-3.f * yy + 4.f * zz - xx); dbz[11] = kC3[2] * 4.f * 2.f * yz;
-                        dbx[12] = kC3[3] * -3.f * 2.f * xz;        dby[12] = kC3[3] * -3.f * 2.f * yz; dbz[12] = kC3[3] * 3.f * (2.f * zz - xx - yy);
-                        dbx[13] = kC3[4] * (-3.f * xx + 4.f * zz - yy); dby[13] = kC3[4] * -2.f * xy; dbz[13] = kC3[4] * 4.f * 2.f * xz;
-                        dbx[14] = kC3[5] * 2.f * xz;               dby[14] = kC3[5] * -2.f * yz;   dbz[14] = kC3[5] * (xx - yy);
-                        dbx[15] = kC3[6] * 3.f * (xx - yy);        dby[15] = kC3[6] * -3.f * 2.f * xy;
-                    }
-                }
+            for (int k = 0; k < 16; k++) {
+                b[k] = dbx[k] = dby[k] = dbz[k] = 0.f;
+                if (k < nb) sh_basis_and_grad(p.D, x, y, z, k, b[k], dbx[k], dby[k], dbz[k]);
             }
             float ddir[3] = {0.f, 0.f, 0.f};
             if (p.M == 16) {
@@ -540,47 +597,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
                     }
                 }
             }
-            // through dir = o/|o|  (auxiliary.h:235-245)
-            const float sum2 = ox * ox + oy * oy + oz * oz;
-            const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-            dmean[0] += ((+sum2 - ox * ox) * ddir[0] - oy * ox * ddir[1] - oz * ox * ddir[2]) * invsum32;
-            dmean[1] += (-ox * oy * ddir[0] + (sum2 - oy * oy) * ddir[1] - oz * oy * ddir[2]) * invsum32;
-            dmean[2] += (-ox * oz * ddir[0] - oy * oz * ddir[1] + (sum2 - oz * oz) * ddir[2]) * invsum32;
+            bwd_dir_to_mean(ox, oy, oz, ddir[0], ddir[1], ddir[2], dmean);
         }
-        // ---- cov3D -> scale / rotation (backward.cu:304-367), no normalisation Jacobian (A.3-Q6)
         if (p.scales != nullptr) {
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            // R[c][r] column-major as in the forward
-            const float R[3][3] = {
-                {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-            const float s[3] = {p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
-            // M[c][r] = s_r R[c][r];  dL_dSigma symmetric with halved off-diagonals
-            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            // dL_dM = 2 M dL_dSigma : dL_dM[c][r] = 2 sum_k M[k][r] dS[c][k]
-            float dM[3][3];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++)
-                    dM[c][rr] = 2.0f * (s[rr] * R[0][rr] * dS[c][0] + s[rr] * R[1][rr] * dS[c][1] + s[rr] * R[2][rr] * dS[c][2]);
-            // dL_dMt[a][b] = dL_dM[b][a];  Rt[a][b] = R[b][a]
-            // dL_dscale_a = dot(Rt[a], dL_dMt[a]) = sum_b R[b][a] dM[b][a]
-#pragma unroll
-            for (int a = 0; a < 3; a++) dscale[a] = R[0][a] * dM[0][a] + R[1][a] * dM[1][a] + R[2][a] * dM[2][a];
-            // dL_dMt[a] *= s_a
-            float Mt[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-                for (int b2 = 0; b2 < 3; b2++) Mt[a][b2] = dM[b2][a] * s[a];
-            drot[0] = 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
-            drot[1] = 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r * (Mt[1][2] - Mt[2][1]) - 4 * x * (Mt[2][2] + Mt[1][1]);
-            drot[2] = 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) - 4 * y * (Mt[2][2] + Mt[0][0]);
-            drot[3] = 2 * r * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) - 4 * z * (Mt[1][1] + Mt[0][0]);
+            float4 dr;
+            bwd_cov3d_to_scale_rot(q, sx, sy, sz, p.scale_modifier, dcov, dscale, dr);
+            drot[0] = dr.x; drot[1] = dr.y; drot[2] = dr.z; drot[3] = dr.w;
         }
     } else if (p.dL_dsh != nullptr) {
         if (dsh4 != nullptr) {
@@ -613,32 +635,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 constexpr int kBT = 128;        // threads = Gaussians per CTA
 constexpr int kRow = 49;        // padded SH row (floats)
-
-__device__ __forceinline__ void sh_basis_and_grad(int D, float x, float y, float z, int k,
-                                                  float& b, float& bx, float& by, float& bz)
-{
-    // value and d/d(x,y,z) of real SH basis k (forward.cu:30-59, backward.cu:47-123), k < (D+1)^2
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    bx = by = bz = 0.f;
-    switch (k) {
-    case 0: b = kC0; break;
-    case 1: b = -kC1 * y; by = -kC1; break;
-    case 2: b = kC1 * z; bz = kC1; break;
-    case 3: b = -kC1 * x; bx = -kC1; break;
-    case 4: b = kC2[0] * xy; bx = kC2[0] * y; by = kC2[0] * x; break;
-    case 5: b = kC2[1] * yz; by = kC2[1] * z; bz = kC2[1] * y; break;
-    case 6: b = kC2[2] * (2.f * zz - xx - yy); bx = kC2[2] * 2.f * -x; by = kC2[2] * 2.f * -y; bz = kC2[2] * 2.f * 2.f * z; break;
-    case 7: b = kC2[3] * xz; bx = kC2[3] * z; bz = kC2[3] * x; break;
-    case 8: b = kC2[4] * (xx - yy); bx = kC2[4] * 2.f * x; by = kC2[4] * 2.f * -y; break;
-    case 9: b = kC3[0] * y * (3.f * xx - yy); bx = kC3[0] * 3.f * 2.f * xy; by = kC3[0] * 3.f * (xx - yy); break;
-    case 10: b = kC3[1] * xy * z; bx = kC3[1] * yz; by = kC3[1] * xz; bz = kC3[1] * xy; break;
-    case 11: b = kC3[2] * y * (4.f * zz - xx - yy); bx = kC3[2] * -2.f * xy; by = kC3[2] * (-3.f * yy + 4.f * zz - xx); bz = kC3[2] * 4.f * 2.f * yz; break;
-    case 12: b = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = kC3[3] * -3.f * 2.f * xz; by = kC3[3] * -3.f * 2.f * yz; bz = kC3[3] * 3.f * (2.f * zz - xx - yy); break;
-    case 13: b = kC3[4] * x * (4.f * zz - xx - yy); bx = kC3[4] * (-3.f * xx + 4.f * zz - yy); by = kC3[4] * -2.f * xy; bz = kC3[4] * 4.f * 2.f * xz; break;
-    case 14: b = kC3[5] * z * (xx - yy); bx = kC3[5] * 2.f * xz; by = kC3[5] * -2.f * yz; bz = kC3[5] * (xx - yy); break;
-    default: b = kC3[6] * x * (xx - 3.f * yy); bx = kC3[6] * 3.f * (xx - yy); by = kC3[6] * -3.f * 2.f * xy; break;
-    }
-}
 
 template <bool SEG>
 __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __grid_constant__ PreprocessBwdParams p)
@@ -735,36 +731,8 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
                 sx = __ldg(p.scales + 3 * idx); sy = __ldg(p.scales + 3 * idx + 1); sz = __ldg(p.scales + 3 * idx + 2);
                 cov3d_from_scale_rot(sx, sy, sz, p.scale_modifier, q.x, q.y, q.z, q.w, cov3D);
             }
-            {   // conic -> cov2D -> cov3D (backward.cu:144-257)
-                const Cov2D cv = cov2d_project(mx, my, mz, view, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D);
-                const float a = cv.a + p.kernel_size, b = cv.b, c = cv.c + p.kernel_size;
-                const float dcx = g.g1.x, dcy = g.g1.y, dcz = g.g1.z;
-                const float denom = a * c - b * b;
-                const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-                if (denom2inv != 0) {
-                    const float dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
-                    const float dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
-                    const float dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
-                    const float* T0 = cv.T0; const float* T1 = cv.T1;
-                    dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
-                    dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
-                    dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
-                    dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
-                    dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
-                    dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
-                }
-            }
-            {   // mean2D -> mean3D (backward.cu:396-414)
-                const float hw = pr[3] * mx + pr[7] * my + pr[11] * mz + pr[15];
-                const float m_w = 1.0f / (hw + 0.0000001f);
-                const float mul1 = (pr[0] * mx + pr[4] * my + pr[8] * mz + pr[12]) * m_w * m_w;
-                const float mul2 = (pr[1] * mx + pr[5] * my + pr[9] * mz + pr[13]) * m_w * m_w;
-                const float mul3 = (pr[2] * mx + pr[6] * my + pr[10] * mz + pr[14]) * m_w * m_w;
-                const float gx = g.g0.x, gy = g.g0.y, gz = g.g0.z;
-                dmean[0] = (pr[0] * m_w - pr[3] * mul1) * gx + (pr[1] * m_w - pr[3] * mul2) * gy + (pr[2] * m_w - pr[3] * mul3) * gz;
-                dmean[1] = (pr[4] * m_w - pr[7] * mul1) * gx + (pr[5] * m_w - pr[7] * mul2) * gy + (pr[6] * m_w - pr[7] * mul3) * gz;
-                dmean[2] = (pr[8] * m_w - pr[11] * mul1) * gx + (pr[9] * m_w - pr[11] * mul2) * gy + (pr[10] * m_w - pr[11] * mul3) * gz;
-            }
+            bwd_conic_to_cov3d(p, view, mx, my, mz, cov3D, g.g1.x, g.g1.y, g.g1.z, dcov);
+            bwd_mean2d_to_mean3d(pr, mx, my, mz, g.g0.x, g.g0.y, g.g0.z, dmean);
             if (has_sh) {   // SH backward in place on the staged row (backward.cu:20-139)
                 const float ox = mx - cam[0], oy = my - cam[1], oz = mz - cam[2];
                 const float len = sqrtf(ox * ox + oy * oy + oz * oz);
@@ -787,40 +755,9 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
                         rk[3 * k] = 0.f; rk[3 * k + 1] = 0.f; rk[3 * k + 2] = 0.f;
                     }
                 }
-                const float sum2 = ox * ox + oy * oy + oz * oz;
-                const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-                dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
-                dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
-                dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+                bwd_dir_to_mean(ox, oy, oz, ddx, ddy, ddz, dmean);
             }
-            if (p.scales != nullptr) {   // cov3D -> scale / rotation (backward.cu:304-367)
-                const float r = q.x, x = q.y, y = q.z, z = q.w;
-                const float R[3][3] = {
-                    {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-                const float s[3] = {p.scale_modifier * sx, p.scale_modifier * sy, p.scale_modifier * sz};
-                const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                        {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                        {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-                float dM[3][3];
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++)
-                        dM[c][rr] = 2.0f * (s[rr] * R[0][rr] * dS[c][0] + s[rr] * R[1][rr] * dS[c][1] + s[rr] * R[2][rr] * dS[c][2]);
-#pragma unroll
-                for (int a = 0; a < 3; a++) dscale[a] = R[0][a] * dM[0][a] + R[1][a] * dM[1][a] + R[2][a] * dM[2][a];
-                float Mt[3][3];
-#pragma unroll
-                for (int a = 0; a < 3; a++)
-#pragma unroll
-                    for (int b2 = 0; b2 < 3; b2++) Mt[a][b2] = dM[b2][a] * s[a];
-                drot.x = 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
-                drot.y = 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r * (Mt[1][2] - Mt[2][1]) - 4 * x * (Mt[2][2] + Mt[1][1]);
-                drot.z = 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) - 4 * y * (Mt[2][2] + Mt[0][0]);
-                drot.w = 2 * r * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) - 4 * z * (Mt[1][1] + Mt[0][0]);
-            }
+            if (p.scales != nullptr) bwd_cov3d_to_scale_rot(q, sx, sy, sz, p.scale_modifier, dcov, dscale, drot);
         } else if (has_sh) {
 #pragma unroll
             for (int k = 0; k < 48; k++) ((k < 3) ? row0 : row)[k] = 0.f;

@@ -9,7 +9,7 @@
  *
  * Parity status: the reference ships no tests or golden vectors; this oracle is
  * pinned instead against outputs of the compiled, unmodified reference itself, generated on a
- * B200 by oracle/make_golden.py and committed under tests/golden/ (see tests/test_oracle_golden.py).
+ * B200 by oracle/make_golden.py and committed under tests/golden/ (see tests/test_oracle.py).
  *
  * Arithmetic: compiled with -ffp-contract=off.  Where the result decides an integer output
  * (depth key, radius, tile rectangle, alpha thresholds) the float operations are written out with

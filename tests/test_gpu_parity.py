@@ -525,3 +525,35 @@ def test_tile_cull_is_output_exact_on_adversarial_scenes(built, seed):
         noise, err = off_share(a2["grads"][k], ga), off_share(b["grads"][k], ga)
         print("%-10s share of entries off by > 1e-3: cull-vs-exact %.2e   exact-vs-exact %.2e" % (k, err, noise))
         assert err <= max(1e-4, 3.0 * noise), (k, err, noise)
+
+
+def test_nine_coefficient_sh_rows_against_oracle(built, cull):
+    """shs given as [P,9,3] (degree-2 rows, M = 9): the forward reads rows of M coefficients and the backward takes the
+    generic per-Gaussian kernel (preprocess_bwd_kernel; the staged kernel handles the 16-coefficient layout).  Both share
+    their derivative blocks with the staged kernel (bwd_* functions of csrc/preprocess.cu)."""
+    mod, orc = U.ours_module(), U.oracle_module()
+    sc = synth.make_scene(900, 300, 112, 80, sigma_px=3.0, seed=synth.SEED + 41, pose="tilted")
+    sc.sh_degree = 2
+    go = synth.grad_outputs(sc)
+
+    def run(m, dev):
+        inp = {k: v.to(dev) for k, v in GO.flat_inputs(sc).items()}
+        inp["shs"] = inp["shs"][:, :9].contiguous()
+        t = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+        P = t["means3D"].shape[0]
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        out = m.GaussianRasterizer(U.settings_for(m, sc, dev))(means3D=t["means3D"], means2D=m2, dir3D=t["dir3D"], opacities=t["opacities"],
+                                                             shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+        torch.autograd.backward([out[0], out[2], out[3], out[4]], [go[k].to(dev) for k in ("grad_color", "grad_depth", "grad_flow", "grad_acc")])
+        res = {k: v.grad.detach().cpu().numpy() for k, v in t.items()}
+        res["means2D"] = m2.grad.detach().cpu().numpy()
+        return out[0].detach().cpu().numpy(), out[1].cpu().numpy(), res
+
+    ca, ra, ga = run(mod, "cuda")
+    cb, rb, gb = run(orc, "cpu")
+    assert np.array_equal(ra, rb)
+    assert float(np.abs(ca - cb).max()) <= RGB_TOL
+    assert ga["shs"].shape == (1200, 9, 3)
+    for k, g in gb.items():
+        e = U.rel_err(ga[k], g, U.grad_floor(g))
+        assert e <= GRAD_RTOL, (k, e)
