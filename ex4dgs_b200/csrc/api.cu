@@ -23,6 +23,8 @@ thread_local unsigned g_last_inexact = 0;   // Gaussians of the last forward who
 struct Readback {
     uint32_t* host = nullptr;
     int device = -1;
+    cudaEvent_t ev = nullptr;
+    // (re)creates the pinned words and the event when the calling thread has moved to another device
     uint32_t* get()
     {
         int dev = 0;
@@ -30,21 +32,17 @@ struct Readback {
         if (host == nullptr || dev != device) {
             if (host) cudaFreeHost(host);
             host = nullptr;
+            ev = nullptr;        // an event of the previous device stays with that device (never destroyed: the context may be gone)
             if (cudaHostAlloc(reinterpret_cast<void**>(&host), 64, cudaHostAllocDefault) != cudaSuccess) host = nullptr;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; cudaGetLastError(); }
             device = dev;
         }
         return host;
     }
     // event recorded right after the read-back copies: the host waits for it instead of the whole stream, so
     // that work queued behind the copies (the speculative duplicate kernel) runs while the host wakes up
-    cudaEvent_t event()
-    {
-        if (!ev_ok) ev_ok = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
-        return ev_ok ? ev : nullptr;
-    }
+    cudaEvent_t event() { return ev; }
     ~Readback() { if (host) cudaFreeHost(host); }
-    cudaEvent_t ev = nullptr;
-    bool ev_ok = false;
 };
 thread_local Readback g_readback;
 // Measurement state is process-wide: autograd runs the backward on its own thread.
@@ -395,6 +393,8 @@ int ex4dgs_forward(
         }
         if (rb_ev) CK(cudaEventSynchronize(rb_ev));
         else CK(cudaStreamSynchronize(s));
+        if (rb[0] > 0x7fffffffu)
+            return fail(EX4DGS_ERR_UNSUPPORTED, "%u (Gaussian, tile) instances: more than 2^31-1 is not supported (num_rendered is an int, as in the reference)", rb[0]);
         R = (int)rb[0];
         flow32 = rb[1];
         g_last_inexact = rb[2];

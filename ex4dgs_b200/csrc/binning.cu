@@ -177,9 +177,12 @@ uint32_t higher_msb(uint32_t n)
 // they sit on the critical path right after the forward's host synchronisation.
 size_t binning_stage1_temp_bytes(int P)
 {
-    static thread_local int last_p = -1;
+    static thread_local int last_p = -1, last_dev = -1;
     static thread_local size_t last_bytes = 0;
-    if (P == last_p) return last_bytes;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (P == last_p && dev == last_dev) return last_bytes;
+    last_dev = dev;
     size_t a = 0, b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
@@ -194,9 +197,13 @@ size_t binning_stage2_temp_bytes(int R)
 {
     // temp size grows monotonically with the item count: query once per 1M-item bucket
     static thread_local long long last_bucket = -1;
+    static thread_local int last_dev = -1;
     static thread_local size_t last_bytes = 0;
     const long long bucket = ((long long)(R > 0 ? R : 1) + 0xFFFFF) >> 20;
-    if (bucket == last_bucket) return last_bytes;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bucket == last_bucket && dev == last_dev) return last_bytes;
+    last_dev = dev;
     const long long n = bucket << 20;
     size_t a = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint16_t*)nullptr, (uint16_t*)nullptr,
