@@ -704,6 +704,117 @@ def other_configs(mod, dev, K, W, cpu=True):
     return out
 
 
+
+def config4_sweep(sc: synth.Scene, dev, rank: int, ws: int, frames: int = 300):
+    """BASELINE.json config 4 in synthetic form, driver-visible: the render.py sweep (render.py:64-96) - `frames` frames,
+    one timestamp each, forward only - sharded frame i -> rank i mod N.  The model goes through the reference's on-disk
+    format on the way: rank 0 writes the scene as point_cloud.ply + dynamic_point_cloud.ply (ex4dgs_b200/model_io.py,
+    byte-compatible with CGaussianModel.save_ply), every rank loads the two files, wraps the loaded arrays in FusedGetters
+    and renders its share through GaussianRasterizer (fused front-end kernel + rasterizer forward per frame)."""
+    import shutil
+    import tempfile
+    from ex4dgs_b200 import model_io, parallel
+    from ex4dgs_b200.frontend import FusedGetters
+    import ex4dgs_b200 as m
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    d = os.path.join(base, "ex4dgs_b200_bench_model_%s" % os.environ.get("MASTER_PORT", "single"))
+    path = os.path.join(d, "point_cloud.ply")
+    t_io = time.time()
+    if rank == 0:
+        os.makedirs(d, exist_ok=True)
+        ga = model_io.GaussianArrays(
+            _xyz=sc.xyz, _features_dc=sc.features[:, :1], _features_rest=sc.features[:, 1:], _opacity=sc.opacity,
+            _scaling=sc.scaling, _rotation=sc.rotation, _xyz_disp=sc.xyz_disp, _xyz_motion=sc.xyz_motion,
+            _features_dc_motion=sc.features_motion[:, :1], _features_rest_motion=sc.features_motion[:, 1:],
+            _scaling_motion=sc.scaling_motion, _opacity_motion=sc.opacity_motion,
+            _opacity_duration_center=sc.opacity_center[:, :, None], _opacity_duration_var=sc.opacity_var[:, :, None],
+            _rotation_motion=sc.rotation_motion, duration=sc.duration, interval=sc.interval, time_pad=sc.time_pad,
+            time_shift=sc.time_shift, var_pad=sc.var_pad, kernel_size=sc.cam.kernel_size)
+        model_io.save_model(ga, path)
+    if ws > 1:
+        torch.distributed.barrier()
+    ga = model_io.load_model(path, 3, duration=sc.duration, interval=sc.interval, time_pad=sc.time_pad, var_pad=sc.var_pad,
+                             kernel_size=sc.cam.kernel_size, device=dev, check_keyframes=False)
+    nbytes = os.path.getsize(path) + os.path.getsize(path.replace("point_cloud.ply", "dynamic_point_cloud.ply"))
+    t_io = time.time() - t_io
+    if ws > 1:
+        torch.distributed.barrier()
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+    cam = sc.cam
+    pc = FusedGetters(ga)
+    rs = m.GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, kernel_size=cam.kernel_size,
+        subpixel_offset=torch.zeros(cam.H, cam.W, 2, device=dev), bg=sc.bg.to(dev), scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev), sh_degree=sc.sh_degree,
+        campos=cam.campos.to(dev), prefiltered=False, min_depth=cam.min_depth, max_depth=cam.max_depth, debug=False)
+    rast = m.GaussianRasterizer(rs)
+    zeros3 = torch.zeros(ga.num_static + ga.num_dynamic, 3, device=dev)
+    timestamps = [float(i % 300) for i in range(frames)]
+    mine = parallel.shard_frames(len(timestamps), rank, ws)
+
+    def frame(t):
+        with torch.no_grad():
+            # the order render() calls them in (gaussian_renderer/__init__.py:62-95): get_features() ends the frame
+            return rast(means3D=pc.get_xyz_at_t(t), means2D=zeros3, dir3D=zeros3, opacities=pc.get_opacity_at_t(t),
+                        scales=pc.get_scaling(), rotations=pc.get_rotation_at_t(t), shs=pc.get_features())[0]
+
+    for t in timestamps[:3]:
+        frame(t)
+    torch.cuda.synchronize()
+    if ws > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = torch.zeros((), device=dev, dtype=torch.float64)
+    for i in mine:
+        checksum += frame(timestamps[i]).double().sum()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if ws > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(checksum)
+    return {"value": len(timestamps) / (ms.item() / 1e3), "unit": "frames/s", "frames": len(timestamps), "ms_total": ms.item(),
+            "n_gpus": ws, "model_files_bytes": int(nbytes), "model_io_s": round(t_io, 2), "checksum": checksum.item(),
+            "what": "render.py-style sweep: 300 timestamps, forward only, frame i -> rank i mod N; model written to and loaded "
+                    "from the reference's two-file PLY format; per frame: fused front-end kernel (SegmentedSH, no torch.cat) "
+                    "+ rasterizer forward"}
+
+
+
+def config5_train_step(mod, dev, rank, ws, group, K, W):
+    """BASELINE.json config 5 in synthetic form, driver-visible at every N: the training step of train.py:139-172 (H2D camera
+    + ground truth, render, 0.8 L1 + 0.2 (1 - SSIM) + the l1_accum hook tensor, backward, loss all-reduce + D2H) at the
+    Technicolor frame size 2048x1088 (configs/techni/Painter.json:2), ONE camera per rank per step - 8 cameras per step,
+    data-parallel, loss all-reduce only, when launched on 8 GPUs.  Gaussian counts of C3 (BASELINE.json fixes only those)."""
+    sc5 = synth.make_scene(1_500_000, 500_000, 2048, 1088)
+    fr = Frame(mod, sc5, dev, seed_off=rank, impl="ours")
+    step = make_train_step(fr, None)
+    for _ in range(max(W, 3)):
+        step(group)
+    torch.cuda.synchronize()
+    if ws > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step(group)
+    e1.record()
+    torch.cuda.synchronize()
+    if ws > 1:
+        torch.distributed.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if ws > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    out = {"value": ws * K / (ms.item() / 1e3), "unit": "cameras/s", "ms_per_step": ms.item() / K, "steps": K, "n_gpus": ws,
+           "cameras_per_step": ws, "image": "2048x1088", "P": sc5.P,
+           "what": "train.py step (render + photometric loss + backward + loss all-reduce), one camera per rank per step"}
+    del step, fr
+    torch.cuda.empty_cache()
+    return out
+
+
 _JSON_FD = None
 
 
@@ -992,6 +1103,11 @@ def main():
                                  if args.impl == "ours" else
                                  "PyTorch getters + get_features torch.cat + utils/loss_utils.py + torch.optim.RAdam (foreach)")}
 
+    sweep4 = train5 = None
+    if args.impl == "ours" and not args.fwd_only and not args.no_extra_configs and args.workload == "C3":
+        sweep4 = config4_sweep(sc, dev, rank, ws)
+        train5 = config5_train_step(mod, dev, rank, ws, group, min(K, 60), W)
+
     value = ws * K / (ms_total / 1000.0)
     e2e_value = ws * K / (ms_e2e / 1000.0)
     if rank != 0:
@@ -1011,6 +1127,10 @@ def main():
             "clocks": clocks}
     if render_api is not None:
         line["render_api"] = render_api
+    if sweep4 is not None:
+        line["config4_render_sweep"] = sweep4
+    if train5 is not None:
+        line["config5_train_step_2048x1088"] = train5
     if train is not None:
         line["train_step"] = train
     if train_iter is not None:
