@@ -454,6 +454,7 @@ MODEL_GROUPS = [("xyz", 1.6e-4), ("f_dc", 2.5e-3), ("f_rest", 2.5e-3 / 20), ("op
 LR_SCALE = 1e-3     # keeps the synthetic scene stationary over the timed steps; RAdam's work is lr-independent
 
 
+DP_OVERLAP = int(os.environ.get("EX4DGS_DP_OVERLAP", "1"))    # --dp-grads: 1 = all-reduce overlapped with the bucketed RAdam step
 STATIC_REG, MOTION_REG = 0.0001, 0.0001      # arguments/__init__.py:134-135 (rot_reg = 0.0: its branch never runs)
 
 
@@ -587,18 +588,19 @@ def make_model_step(frame: Frame, impl: str, ref_loss, dp_grads: bool, lambda_ds
                     if gaussians._opacity_duration_var.shape[0] != 0:
                         if not gaussians._opacity_duration_var.grad is None:
                             gaussians._opacity_duration_var.grad = gaussians._opacity_duration_var.grad.nan_to_num()
-        scale = 1.0
-        if dp_grads and group is not None:
-            if impl == "ours":
-                scale = allreduce_gradients(params, group)
+        if impl == "ours":
+            if dp_grads and group is not None and DP_OVERLAP:
+                opt.step(allreduce_group=group)        # reductions queued up front, the step kernel follows them bucket by bucket
+            elif dp_grads and group is not None:
+                opt.step(grad_scale=allreduce_gradients(params, group))
             else:
+                opt.step()
+        else:
+            if dp_grads and group is not None:
                 ws = torch.distributed.get_world_size(group)
                 for p in params:
                     torch.distributed.all_reduce(p.grad, group=group)
                     p.grad /= ws
-        if impl == "ours":
-            opt.step(grad_scale=scale)
-        else:
             opt.step()
         opt.zero_grad(set_to_none=True)
         if bookkeeping:
@@ -1096,7 +1098,7 @@ def main():
             model_step(group)
         ms_iter, _, _ = timed(lambda: model_step(group), Kt)
         train_iter = {"value": ws * Kt / (ms_iter / 1000.0), "unit": "iterations/s", "ms_per_step": ms_iter / Kt, "steps": Kt,
-                      "parameters": n_param, "lr_scale": LR_SCALE, "gradient_allreduce": bool(args.dp_grads and ws > 1),
+                      "parameters": n_param, "lr_scale": LR_SCALE, "gradient_allreduce": bool(args.dp_grads and ws > 1), "gradient_allreduce_overlapped": bool(DP_OVERLAP),
                       "what": "train.py iteration without densification on the 15 native parameter tensors: per-frame getters, "
                               "get_features, render, loss block, backward to the parameters, RAdam step, zero_grad; "
                               + ("fused front-end + segmented SH input (no torch.cat) + fused loss + FusedRAdam (one kernel each)"

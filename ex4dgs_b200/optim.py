@@ -50,7 +50,12 @@ class FusedRAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
+    def step(self, closure=None, grad_scale: float = 1.0, allreduce_group=None, buckets: int = 6):
+        """allreduce_group: data-parallel training - SUM all-reduce every gradient over that process group and step with the
+        mean gradient, OVERLAPPED: all reductions are queued on the communication stream up front (in parameter order) and
+        the step kernel is launched per bucket of tensors (`buckets` of roughly equal bytes) as soon as that bucket's
+        reductions have completed, so the HBM-bound update of bucket k runs beside the NVLink-bound reduction of bucket
+        k+1 (the un-overlapped form is allreduce_gradients() followed by step(grad_scale=...))."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -78,11 +83,35 @@ class FusedRAdam(torch.optim.Optimizer):
                 g = p.grad if (p.grad.dtype == torch.float32 and p.grad.is_contiguous()) else p.grad.float().contiguous()
                 batches.setdefault((float(beta1), float(beta2), float(group["eps"]), p.device), []).append(
                     (p, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), int(st["step"].item()), group.get("name")))
+        works = {}
+        if allreduce_group is not None and dist.is_available() and dist.is_initialized():
+            for items in batches.values():
+                for it in items:
+                    works[id(it[0])] = dist.all_reduce(it[1], op=dist.ReduceOp.SUM, group=allreduce_group, async_op=True)
+            grad_scale = grad_scale / dist.get_world_size(allreduce_group)
         slot = {}
         for (beta1, beta2, eps, dev), items in batches.items():
             stream = torch.cuda.current_stream(dev).cuda_stream
-            for i in range(0, len(items), 32):
-                chunk = items[i:i + 32]
+            # launch units: at most 32 tensors each; with an overlapped all-reduce, buckets of ~equal bytes in issue order
+            if works:
+                total = sum(it[0].numel() for it in items)
+                target = max(1, total // max(1, buckets))
+                units, cur, acc = [], [], 0
+                for it in items:
+                    cur.append(it)
+                    acc += it[0].numel()
+                    if acc >= target or len(cur) == 32:
+                        units.append(cur)
+                        cur, acc = [], 0
+                if cur:
+                    units.append(cur)
+            else:
+                units = [items[i:i + 32] for i in range(0, len(items), 32)]
+            for chunk in units:
+                for it in chunk:
+                    w = works.get(id(it[0]))
+                    if w is not None:
+                        w.wait()              # the CURRENT stream waits for this tensor's reduction, the host does not
                 arr = (_lib.RAdamTensor * len(chunk))()
                 check = sanitize = 0
                 for j, (a, (p, g, m, v, lr, step, name)) in enumerate(zip(arr, chunk)):

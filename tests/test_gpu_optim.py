@@ -132,3 +132,36 @@ def test_fused_radam_nan_guards():
     assert torch.isnan(po[names.index("motion_xyz")][17, 4, 1])
     ours.clear_nan()
     assert ours.nan_detected() == {"xyz": False, "motion_xyz": False}
+
+
+def test_overlapped_allreduce_step_equals_plain_step(built):
+    """FusedRAdam.step(allreduce_group=...) - reductions queued up front, the step kernel launched per bucket - on a
+    one-rank NCCL group must give exactly the plain step (sum over one rank, mean = the gradient itself)."""
+    import torch.distributed as dist
+    from ex4dgs_b200.optim import FusedRAdam
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        g = torch.Generator().manual_seed(9)
+        shapes = [(1000, 3), (1000, 1, 3), (1000, 15, 3), (1000, 1), (700, 36, 3), (700, 36, 4), (5,), (700, 2)]
+        def make():
+            ps = [torch.nn.Parameter(torch.randn(*s, generator=torch.Generator().manual_seed(i)).cuda()) for i, s in enumerate(shapes)]
+            return ps, FusedRAdam([{"params": [p], "lr": 1e-2 * (i + 1), "name": "g%d" % i} for i, p in enumerate(ps)])
+        pa, oa = make()
+        pb, ob = make()
+        for it in range(7):
+            for x, y in zip(pa, pb):
+                gr = torch.randn(x.shape, generator=g).cuda()
+                x.grad, y.grad = gr.clone(), gr.clone()
+            oa.step()
+            ob.step(allreduce_group=dist.group.WORLD, buckets=3)
+        torch.cuda.synchronize()
+        for x, y in zip(pa, pb):
+            assert torch.equal(x, y)
+            assert torch.equal(oa.state[x]["exp_avg_sq"], ob.state[y]["exp_avg_sq"])
+    finally:
+        if created:
+            dist.destroy_process_group()
