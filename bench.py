@@ -644,7 +644,13 @@ def frame_stats(frame: Frame):
     _lib.load().ex4dgs_forward_geometry(ctypes.byref(kb), ctypes.byref(kw))
     r_eff = int(np.minimum(rl, kb.value * batches).sum())
     n_contrib = view("n_contrib", np.uint32)
-    return dict(R=R, P_vis=int((radii > 0).sum().item()), R_eff=r_eff, tiles=int(ranges.shape[0]),
+    # SURVEY 8d's literal definition (256-splat batches): sum_tiles min(range_len, 256 * ceil(max_pix n_contrib / 256))
+    gx, gy = (cam.W + 15) // 16, (cam.H + 15) // 16
+    nc = np.zeros((gy * 16, gx * 16), np.int64)
+    nc[:cam.H, :cam.W] = n_contrib.reshape(cam.H, cam.W)
+    tile_max = nc.reshape(gy, 16, gx, 16).max(axis=(1, 3)).reshape(-1)
+    r_eff_256 = int(np.minimum(rl, 256 * ((tile_max + 255) // 256)).sum())
+    return dict(R=R, P_vis=int((radii > 0).sum().item()), R_eff=r_eff, R_eff_256=r_eff_256, tiles=int(ranges.shape[0]),
                 R_listed=int(rl.sum()), block_keep=float(kept.sum()) / max(1.0, float(kw.value) * r_eff),
                 mean_n_contrib=float(n_contrib.mean()))
 
@@ -1151,7 +1157,7 @@ def main():
         t_render = stage_ms[3] / 1000.0
         achieved = alg_bytes / t_render / 1e9
         line["gpu_launches"] = int(launches)
-        line["scene_stats"] = {"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"],
+        line["scene_stats"] = {"P": frame.P, "P_vis": st["P_vis"], "R": st["R"], "R_eff": st["R_eff"], "R_eff_256": st["R_eff_256"],
                                "R_listed": st["R_listed"], "block_keep": st["block_keep"],
                                "tile_cull": int(args.tile_cull), "mean_n_contrib": st["mean_n_contrib"]}
         traffic, traffic_src = None, "no ncu capture committed"
@@ -1169,6 +1175,9 @@ def main():
         line["roofline"] = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[3],
+                            "R_eff": "instances in the 128-splat batches the tiles actually fetch (scene_stats.R_eff); with SURVEY 8d's "
+                                     "literal 256-splat granularity (scene_stats.R_eff_256) the fraction is frac_at_256",
+                            "frac_at_256": (56 * st["R_eff_256"] + 52 * cam.W * cam.H + 8 * st["tiles"]) / t_render / 1e9 / peak,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                             "note": "the kernel is bound by instruction issue / the FP32 and ALU pipes, not by HBM (ncu: 5 % DRAM): see issue_slots and profiles/SUMMARY.md"}
         # what actually bounds the two compositing kernels: warp instructions issued (smsp__inst_executed.sum of the committed
