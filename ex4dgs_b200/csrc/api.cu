@@ -16,6 +16,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_last_R = 0;     // sizing hint only (previous frame of this thread)
+thread_local bool g_last_flow = false;   // did the last frame of this thread have flow (non-zero dir3D)? (which compositing instantiation to queue before the flag is read)
+thread_local int g_last_cap = 0;   // capacity of the binning buffer of this thread's last forward (ex4dgs_describe_buffers)
 thread_local unsigned g_last_inexact = 0;   // Gaussians of the last forward whose alpha threshold fell back (preprocess.cu)
 
 // Pinned landing pad of the forward's one read-back (R and the flow flag), one per host thread and
@@ -34,6 +36,7 @@ struct Readback {
             host = nullptr;
             ev = nullptr;        // an event of the previous device stays with that device (never destroyed: the context may be gone)
             if (cudaHostAlloc(reinterpret_cast<void**>(&host), 64, cudaHostAllocDefault) != cudaSuccess) host = nullptr;
+            if (host) memset(host, 0, 64);
             if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; cudaGetLastError(); }
             device = dev;
         }
@@ -117,11 +120,11 @@ GeometryState carve_geometry(void* base, int P, size_t temp_bytes)
     Carver c(base);
     const size_t n = (size_t)P;
     g.key_in = c.take<uint32_t>(n);
-    g.val_in = c.take<uint32_t>(n);
-    g.key_sorted = c.take<uint32_t>(n);
+    g.key_a = c.take<uint32_t>(n);
+    g.val_a = c.take<uint32_t>(n);
+    g.key_b = c.take<uint32_t>(n);
     g.order = c.take<uint32_t>(n);
     g.tiles_touched = c.take<uint32_t>(n);
-    g.offsets = c.take<uint32_t>(n);
     g.rec = c.take<SplatRec>(n);
     g.clamped = c.take<uint8_t>(n);
     g.gacc = c.take<GradAcc>(n);
@@ -132,26 +135,20 @@ GeometryState carve_geometry(void* base, int P, size_t temp_bytes)
     return g;
 }
 
-// Layout of the binning buffer.  The two SORTED arrays - what the compositing kernels, the backward and the tests
-// read - sit at the front at offsets that depend on R alone (point_list at 0); the two UNSORTED arrays, which only
-// live between the duplicate kernel and the sort, sit behind the space the sorted arrays would need at full capacity.
-// So a buffer sized for a guess `cap` >= R can be filled by the duplicate kernel before R is known on the host, and
-// everything read later is found from R.  With cap == R this is simply four consecutive arrays.
-BinningState carve_binning(void* base, int R, int cap, size_t temp_bytes)
+// Layout of the binning buffer: two sets of (ids, tiles) of `cap` entries each (BinningState), then the look-back
+// words of the tile sort.  The sorted id list (point_list, all the backward needs) is at offset 0 whatever `cap` is,
+// so a buffer sized for a guess cap >= R can be filled and sorted before R is known on the host.
+BinningState carve_binning(void* base, int cap, size_t status_bytes)
 {
     BinningState b;
-    const size_t n = (size_t)(R > 0 ? R : 0), m = (size_t)(cap > R ? cap : (R > 0 ? R : 0));
+    const size_t m = (size_t)(cap > 0 ? cap : 0);
     Carver c(base);
-    b.point_list = c.take<uint32_t>(n);
-    b.tile_sorted = c.take<uint16_t>(n);
-    Carver d(base);
-    d.take<uint32_t>(m);
-    d.take<uint16_t>(m);
-    b.val_unsorted = d.take<uint32_t>(m);
-    b.tile_unsorted = d.take<uint16_t>(m);
-    b.temp = d.take<char>(temp_bytes);
-    b.temp_bytes = temp_bytes;
-    b.total = d.off + 256;
+    b.val[0] = c.take<uint32_t>(m);
+    b.tile[0] = c.take<uint16_t>(m);
+    b.val[1] = c.take<uint32_t>(m);
+    b.tile[1] = c.take<uint16_t>(m);
+    b.status = reinterpret_cast<uint32_t*>(c.take<char>(status_bytes));
+    b.total = c.off + 256;
     return b;
 }
 
@@ -210,30 +207,28 @@ void ex4dgs_forward_geometry(int* batch, int* warps)
     if (warps) *warps = w;
 }
 
-size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1)).total; }
-size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R)).total; }
+size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_geometry_scratch_bytes(P > 0 ? P : 1)).total; }
+size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, binning_status_bytes(R)).total; }
 size_t ex4dgs_image_bytes(int width, int height) { return carve_image(nullptr, width, height).total; }
 
 int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_desc* out, int max)
 {
-    const GeometryState g = carve_geometry(nullptr, P, binning_stage1_temp_bytes(P > 0 ? P : 1));
-    const BinningState b = carve_binning(nullptr, R, R, binning_stage2_temp_bytes(R));
+    // the binning buffer is laid out from its capacity: the one of the calling thread's last forward when that covers R
+    const int cap = g_last_cap >= R ? g_last_cap : R;
+    const GeometryState g = carve_geometry(nullptr, P, binning_geometry_scratch_bytes(P > 0 ? P : 1));
+    const BinningState b = carve_binning(nullptr, cap, binning_status_bytes(cap));
     const ImageState im = carve_image(nullptr, width, height);
     const size_t n = (size_t)P, r = (size_t)(R > 0 ? R : 0), px = (size_t)width * height;
     const size_t tiles = (size_t)((width + EX_TILE - 1) / EX_TILE) * ((height + EX_TILE - 1) / EX_TILE);
     const ex4dgs_array_desc all[] = {
         {"depth_key", 0, (size_t)g.key_in, 4, n},
-        {"depth_key_sorted", 0, (size_t)g.key_sorted, 4, n},
         {"order", 0, (size_t)g.order, 4, n},
         {"tiles_touched", 0, (size_t)g.tiles_touched, 4, n},
-        {"offsets", 0, (size_t)g.offsets, 4, n},
         {"rec", 0, (size_t)g.rec, sizeof(SplatRec), n},
         {"clamped", 0, (size_t)g.clamped, 1, n},
         {"gacc", 0, (size_t)g.gacc, sizeof(GradAcc), n},
-        {"tile_unsorted", 1, (size_t)b.tile_unsorted, 2, r},
-        {"val_unsorted", 1, (size_t)b.val_unsorted, 4, r},
-        {"tile_sorted", 1, (size_t)b.tile_sorted, 2, r},
-        {"point_list", 1, (size_t)b.point_list, 4, r},
+        {"tile_sorted", 1, (size_t)b.tile[0], 2, r},
+        {"point_list", 1, (size_t)b.val[0], 4, r},
         {"final_T", 2, (size_t)im.final_T, 4, px},
         {"n_contrib", 2, (size_t)im.n_contrib, 4, px},
         {"ranges", 2, (size_t)im.ranges, 8, tiles},
@@ -312,9 +307,8 @@ int ex4dgs_forward(
     rp.final_T = img.final_T; rp.n_contrib = img.n_contrib; rp.tile_batches = img.tile_batches; rp.ranges = img.ranges;
     rp.out_color = out_color; rp.out_depth = out_depth; rp.out_acc = out_acc; rp.out_flow = out_flow; rp.out_idx = out_idx;
 
-    int R = 0, spec_R = 0;
+    int R = 0;
     uint32_t flow32 = 0;      // read back with R: does any visible Gaussian carry a non-zero dir3D?
-    void* spec_base = nullptr;
     GeometryState geom;
     memset(&geom, 0, sizeof(geom));
     BinningState bin;
@@ -326,115 +320,143 @@ int ex4dgs_forward(
     pp.view = viewmatrix; pp.proj = projmatrix; pp.cam = cam_pos;
     rp.bg = background;
 
-    if (P > 0) {
-        const size_t temp1 = binning_stage1_temp_bytes(P);
-        const size_t geom_bytes = carve_geometry(nullptr, P, temp1).total;
-        void* geom_base = geometryBuffer(geometry_user, geom_bytes);
-        if (!geom_base) return fail(EX4DGS_ERR_ALLOC, "geometryBuffer(%zu) returned NULL", geom_bytes);
-        geom = carve_geometry(align256(geom_base), P, temp1);
-
-        pp.P = P; pp.D = D; pp.M = M;
-        pp.means3D = means3D; pp.dir3D = dir3D; pp.scales = scales; pp.rotations = rotations;
-        pp.opacities = opacities; pp.shs = shs; pp.cov3D_precomp = cov3D_precomp; pp.colors_precomp = colors_precomp;
-        if ((flags & EX4DGS_FLAG_SH_SEGMENTED) && shs != nullptr) {
-            const int rc = read_segments(shs, P, M, &pp.seg, "forward");
-            if (rc < 0) return rc;
-            pp.shs = nullptr;
-        }
-        pp.scale_modifier = scale_modifier;
-        pp.W = width; pp.H = height;
-        pp.tan_fovx = tan_fovx; pp.tan_fovy = tan_fovy;
-        pp.focal_y = height / (2.0f * tan_fovy);
-        pp.focal_x = width / (2.0f * tan_fovx);
-        pp.kernel_size = kernel_size;
-        pp.min_depth = min_depth; pp.max_depth = max_depth;
-        pp.grid_x = grid_x; pp.grid_y = grid_y;
-        pp.prefiltered = prefiltered; pp.flags = flags;
-        pp.radii = radii; pp.key_in = geom.key_in; pp.val_in = geom.val_in; pp.tiles_touched = geom.tiles_touched;
-        pp.rec = geom.rec; pp.clamped = geom.clamped;
-        pp.pad_ptr = reinterpret_cast<const float*>(geom.meta);
-        pp.flow_flag = geom.meta + 1;
-        pp.inexact_thr = geom.meta + 2;
-        CK(cudaMemsetAsync(geom.meta, 0, 3 * sizeof(uint32_t), s));     // [0] max |subpixel offset| bits, [1] flow flag, [2] inexact thresholds
-        if (flags & EX4DGS_FLAG_TILE_CULL)
-            CK(launch_subpixel_absmax(subpixel_offset, (size_t)width * height * 2, geom.meta, s));
-        prof.mark();
-        launch_preprocess_fwd(pp, s);
-        g_launches += 1;
-        STAGE(debug, s, "preprocess");
-        prof.mark();
-
-        CK(binning_stage1(geom, P, s));
-        STAGE(debug, s, "depth sort + scan");
-        // the one blocking read-back of the pipeline (rasterizer_impl.cu:299)
-        prof.mark();
-        uint32_t* rb = g_readback.get();
-        if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
-        CK(cudaMemcpyAsync(rb, geom.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(rb + 1, geom.meta + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        cudaEvent_t rb_ev = g_readback.event();
-        if (rb_ev) CK(cudaEventRecord(rb_ev, s));
-        // While the GPU is still busy with preprocess / sort / scan, ask the caller for a binning buffer sized
-        // from the previous frames of this thread (+25 %) and queue the duplicate kernel into it (its grid
-        // depends on P only; entries beyond the guessed capacity are dropped): the allocator callback (a trip
-        // into Python), the host's wake-up after the wait and the launches of the sort then overlap device work
-        // instead of leaving the GPU idle between the scan and the duplicate kernel.
-        if (g_last_R > 0 && rb_ev) {
-            const long long guess = (long long)g_last_R + g_last_R / 4 + 65536;
-            if (guess < 0x7fffffffLL) {
-                spec_R = (int)guess;
-                const size_t spec_temp = binning_stage2_temp_bytes(spec_R);
-                const size_t spec_bytes = carve_binning(nullptr, spec_R, spec_R, spec_temp).total;
-                spec_base = binningBuffer(binning_user, spec_bytes);
-                if (!spec_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", spec_bytes);
-                const BinningState sb = carve_binning(align256(spec_base), 0, spec_R, spec_temp);
-                CK(binning_duplicate(geom, sb, radii, P, spec_R, grid_x, grid_y, flags, s));
-            }
-        }
-        if (rb_ev) CK(cudaEventSynchronize(rb_ev));
-        else CK(cudaStreamSynchronize(s));
-        if (rb[0] > 0x7fffffffu)
-            return fail(EX4DGS_ERR_UNSUPPORTED, "%u (Gaussian, tile) instances: more than 2^31-1 is not supported (num_rendered is an int, as in the reference)", rb[0]);
-        R = (int)rb[0];
-        flow32 = rb[1];
-        g_last_inexact = rb[2];
-        // sizing hint for the next frame: follows R upwards at once, downwards slowly (views alternate in training)
-        g_last_R = R > g_last_R ? R : (int)(((long long)g_last_R * 15 + R) / 16);
-    }
-
-    const bool spec_hit = spec_base != nullptr && R <= spec_R;
-    const int cap = spec_hit ? spec_R : R;
-    const size_t temp2 = binning_stage2_temp_bytes(cap);
-    void* bin_base = spec_base;
-    if (!spec_hit) {
-        const size_t bin_bytes = carve_binning(nullptr, R, R, temp2).total;
-        bin_base = binningBuffer(binning_user, bin_bytes);
-        if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
-    }
-    bin = carve_binning(align256(bin_base), R, cap, temp2);     // sorted arrays are laid out from R alone
-
-    if (P > 0) {
-        if (!spec_hit) CK(binning_duplicate(geom, bin, radii, P, R, grid_x, grid_y, flags, s));   // no guess, or it was too small
-        CK(binning_sort_ranges(bin, img, R, grid_x, grid_y, flags, s));
-        g_launches += (R > 0) ? 2 : 0;
-    } else {
-        CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
-    }
-    STAGE(debug, s, "duplicate + tile sort + ranges");
-
-    rp.point_list = bin.point_list;
-    rp.rec = geom.rec;
-    prof.mark();
-    {
+    // compositing of the sorted lists in `bin` (everything else of rp is set)
+    auto render = [&](bool with_flow) -> int {
+        rp.point_list = bin.val[0];
+        rp.rec = geom.rec;
         CUtensorMap rec_map;
         const bool have_map = P > 0 && render_fwd_uses_gather() && make_record_tensor_map(&rec_map, geom.rec, P);
         if (P > 0 && render_fwd_uses_gather() && !have_map)
             return fail(EX4DGS_ERR_CUDA, "cuTensorMapEncodeTiled is not available (forward built with TMA gather staging)");
-        launch_render_fwd(rp, have_map ? &rec_map : nullptr, grid_x, grid_y, flow32 != 0, s);
+        launch_render_fwd(rp, have_map ? &rec_map : nullptr, grid_x, grid_y, with_flow, s);
+        g_launches += 1;
+        return EX4DGS_OK;
+    };
+
+    if (P <= 0) {
+        void* bin_base = binningBuffer(binning_user, carve_binning(nullptr, 0, binning_status_bytes(0)).total);
+        if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer returned NULL");
+        CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
+        prof.mark();
+        const int rc = render(false);
+        if (rc < 0) return rc;
+        STAGE(debug, s, "render");
+        prof.mark();
+        prof.done();
+        g_last_cap = 0;
+        return 0;
     }
-    g_launches += 1;
-    STAGE(debug, s, "render");
+
+    const size_t scratch = binning_geometry_scratch_bytes(P);
+    const size_t geom_bytes = carve_geometry(nullptr, P, scratch).total;
+    void* geom_base = geometryBuffer(geometry_user, geom_bytes);
+    if (!geom_base) return fail(EX4DGS_ERR_ALLOC, "geometryBuffer(%zu) returned NULL", geom_bytes);
+    geom = carve_geometry(align256(geom_base), P, scratch);
+
+    pp.P = P; pp.D = D; pp.M = M;
+    pp.means3D = means3D; pp.dir3D = dir3D; pp.scales = scales; pp.rotations = rotations;
+    pp.opacities = opacities; pp.shs = shs; pp.cov3D_precomp = cov3D_precomp; pp.colors_precomp = colors_precomp;
+    if ((flags & EX4DGS_FLAG_SH_SEGMENTED) && shs != nullptr) {
+        const int rc = read_segments(shs, P, M, &pp.seg, "forward");
+        if (rc < 0) return rc;
+        pp.shs = nullptr;
+    }
+    pp.scale_modifier = scale_modifier;
+    pp.W = width; pp.H = height;
+    pp.tan_fovx = tan_fovx; pp.tan_fovy = tan_fovy;
+    pp.focal_y = height / (2.0f * tan_fovy);
+    pp.focal_x = width / (2.0f * tan_fovx);
+    pp.kernel_size = kernel_size;
+    pp.min_depth = min_depth; pp.max_depth = max_depth;
+    pp.grid_x = grid_x; pp.grid_y = grid_y;
+    pp.prefiltered = prefiltered; pp.flags = flags;
+    pp.radii = radii; pp.key_in = geom.key_in; pp.tiles_touched = geom.tiles_touched;
+    pp.rec = geom.rec; pp.clamped = geom.clamped;
+    pp.pad_ptr = reinterpret_cast<const float*>(geom.meta + EX_META_PAD);
+    pp.flow_flag = geom.meta + EX_META_FLOW;
+    pp.inexact_thr = geom.meta + EX_META_INEXACT;
+    // device scalars, digit histograms and look-back words: one clear (the sort scratch directly follows meta)
+    CK(cudaMemsetAsync(geom.meta, 0, (size_t)(geom.temp - reinterpret_cast<char*>(geom.meta)) + binning_geometry_zero_bytes(P), s));
+    if (flags & EX4DGS_FLAG_TILE_CULL)
+        CK(launch_subpixel_absmax(subpixel_offset, (size_t)width * height * 2, geom.meta + EX_META_PAD, s));
     prof.mark();
+    launch_preprocess_fwd(pp, s);
+    g_launches += 1;
+    STAGE(debug, s, "preprocess");
+    prof.mark();
+
+    CK(binning_depth_order(geom, P, s));
+    g_launches += 6;
+    STAGE(debug, s, "depth sort");
+    prof.mark();
+
+    // R is on the device now; the host reads it (rasterizer_impl.cu:299) but waits for it only after everything is queued
+    uint32_t* rb = g_readback.get();
+    if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
+    cudaEvent_t rb_ev = g_readback.event();
+    CK(cudaMemcpyAsync(rb, geom.meta + EX_META_FLOW, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (rb_ev) CK(cudaEventRecord(rb_ev, s));
+
+    // Nothing below waits for the instance count R before it is launched: the binning buffer is asked for with a
+    // capacity guessed from the previous frames of this thread (largest recent R + 25 %), the duplicate kernel drops
+    // what does not fit, the tile sort and the ranges kernel read min(R, capacity) from the device.  The host waits
+    // for R only after the compositing kernel is queued - the GPU never idles.  If the guess was too small (or there
+    // is none: first frame) the instance stages run (once more) into a buffer of exactly R entries.
+    bool marked = false;
+    int cap = 0;
+    if (g_last_R > 0) {
+        const long long guess = (long long)g_last_R + g_last_R / 4 + 65536;
+        cap = (int)(guess < 0x3fffffffLL ? guess : 0x3fffffffLL);
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (attempt == 1) CK(binning_reset_instances(geom, P, s));
+        if (cap > 0 || attempt == 1) {
+            const size_t status_bytes = binning_status_bytes(cap);
+            const size_t bin_bytes = carve_binning(nullptr, cap, status_bytes).total;
+            void* bin_base = binningBuffer(binning_user, bin_bytes);
+            if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
+            bin = carve_binning(align256(bin_base), cap, status_bytes);
+        }
+        if (cap > 0) {
+            CK(binning_duplicate(geom, bin, radii, P, cap, grid_x, grid_y, flags, s));
+            g_launches += 1;
+        }
+        if (cap > 0 || attempt == 1) {
+            CK(binning_sort_ranges(geom, bin, img, P, cap, grid_x, grid_y, flags, s));
+            g_launches += cap > 0 ? 4 : 0;
+            STAGE(debug, s, "duplicate + tile sort + ranges");
+            if (!marked) prof.mark();
+            // the flow flag is known on the host only after the wait: the first attempt carries the flow accumulators
+            // whenever a previous frame of this thread did
+            const int rc = render(attempt == 0 ? g_last_flow : flow32 != 0);
+            if (rc < 0) return rc;
+            STAGE(debug, s, "render");
+            if (!marked) prof.mark();
+            marked = true;
+        }
+        if (attempt == 1) break;
+        if (rb_ev) CK(cudaEventSynchronize(rb_ev));
+        else CK(cudaStreamSynchronize(s));
+        if (rb[8] != 0) {
+            rb[8] = 0;
+            return fail(EX4DGS_ERR_CUDA, "binning: a look-back of the previous forward's tile sort did not complete");
+        }
+        flow32 = rb[EX_META_FLOW - EX_META_FLOW];
+        g_last_inexact = rb[EX_META_INEXACT - EX_META_FLOW];
+        const uint32_t total = rb[EX_META_TOTAL - EX_META_FLOW];
+        if (rb[EX_META_ERROR - EX_META_FLOW] != 0 || total > 0x3fffffffu)
+            return fail(EX4DGS_ERR_UNSUPPORTED, "binning: a look-back did not complete or there are more than 2^30-1 (Gaussian, tile) instances (read %u)", total);
+        R = (int)total;
+        // sizing hint for the next frame: follows R upwards at once, downwards slowly (views alternate in training)
+        g_last_R = R > g_last_R ? R : (int)(((long long)g_last_R * 15 + R) / 16);
+        const bool flow_ok = (flow32 != 0) == g_last_flow || g_last_flow;     // carrying unused flow accumulators is harmless
+        g_last_flow = flow32 != 0;
+        if (cap > 0 && R <= cap && flow_ok) break;
+        cap = R;
+    }
+    g_last_cap = cap;
+    // look-back failures of the tile passes (queued behind the read-back above) are reported by the next forward
+    CK(cudaMemcpyAsync(rb + 8, geom.meta + EX_META_ERROR, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     prof.done();
     return R;
 }
@@ -468,7 +490,7 @@ int ex4dgs_backward(
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
     // the CUB temp areas are the last sub-arrays and are not used by the backward
     const GeometryState geom = carve_geometry(align256(geom_buffer), P, 0);
-    const BinningState bin = carve_binning(align256(binning_buffer), R, R, 0);
+    const BinningState bin = carve_binning(align256(binning_buffer), 0, 0);      // the sorted id list is at offset 0
     const ImageState img = carve_image(align256(image_buffer), width, height);
 
     PreprocessBwdParams bp;
@@ -479,7 +501,7 @@ int ex4dgs_backward(
 
     RenderParams rp;
     memset(&rp, 0, sizeof(rp));
-    rp.ranges = img.ranges; rp.point_list = bin.point_list; rp.rec = geom.rec;
+    rp.ranges = img.ranges; rp.point_list = bin.val[0]; rp.rec = geom.rec;
     rp.W = width; rp.H = height; rp.grid_x = grid_x;
     rp.subpixel_offset = reinterpret_cast<const float2*>(subpixel_offset);
     rp.bg = background;

@@ -1,24 +1,288 @@
-// Tile binning for sm_100a: depth ordering of Gaussians, duplication into (tile, id) instances,
-// stable tile sort and per-tile ranges.
+// Tile binning for sm_100a: depth ordering of the visible Gaussians, duplication into (tile, id)
+// instances, stable tile sort and per-tile ranges - every item count stays on the device.
 //
 // Behavioural spec: rasterizer_impl.cu:72-140 (duplicateWithKeys, identifyTileRanges) and
 // :293-336 (scan, 64-bit key radix sort over bits [0, 32+bit), ranges).  The reference sorts R
 // 64-bit keys (tile << 32 | depth bits).  Here the same permutation is produced with two stable
 // sorts on much less data (SURVEY.md section 7 "Sort traffic"):
-//   1. stable sort of the P Gaussians by their 32 depth bits          -> order by (depth, id)
+//   1. stable sort of the VISIBLE Gaussians by their 32 depth bits      -> order by (depth, id)
 //   2. emit the (tile, id) instances in that order, stable sort by the `bit`-bit tile id only
 //      (uint16 keys) -> (tile, depth, id), which is exactly the order of the reference's stable
 //      LSD sort with its emission order (= Gaussian index) as tie-break.
-// Both sorts are cub::DeviceRadixSort as the north star prescribes.
+//
+// Both sorts are the one-sweep LSD radix sort below (8-bit digits, one kernel per digit: rank the
+// tile's keys with warp match, publish the tile's digit counts, chained look-back over the previous
+// tiles, scatter through shared memory).  It does what cub::DeviceRadixSort does, with three
+// differences that the pipeline needs: the item count is read from DEVICE memory (the number of
+// visible Gaussians / of instances is produced by the kernel in front, the host never waits for it
+// before launching), the first depth pass drops the culled Gaussians on the fly (P keys in, P_vis
+// pairs out: the later passes and the duplicate kernel only see visible ones), and the values of the
+// first pass are the indices themselves (no iota array).  The prefix sum of `tiles_touched` in depth
+// order (rasterizer_impl.cu:295 InclusiveSum) is fused into the duplicate kernel with the same
+// look-back, which also leaves the instance count R on the device.
 #include "common.cuh"
-#include <cub/cub.cuh>
+#include <type_traits>
 
 namespace {
 
-struct TilesInOrder {
-    const uint32_t* tiles_touched;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles_touched[id]; }
-};
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kBins = 256;                       // 8-bit digits
+#ifndef EX_SORT_ITEMS_DEPTH
+#define EX_SORT_ITEMS_DEPTH 16                   // keys per thread and tile: 4096 (depth, id) pairs per tile
+#endif
+#ifndef EX_SORT_ITEMS_TILE
+#define EX_SORT_ITEMS_TILE 16                    // 4096 (tile, id) pairs per tile
+#endif
+#ifndef EX_SORT_MINBLOCKS
+#define EX_SORT_MINBLOCKS 3                      // resident CTAs per SM the pass kernel is compiled for (register cap 85)
+#endif
+#ifndef EX_SORT_WINDOW
+#define EX_SORT_WINDOW 8                         // status words a look-back step loads at once
+#endif
+constexpr uint32_t kFlagAgg = 1u << 30;          // status word = 2 flag bits | 30-bit count
+constexpr uint32_t kFlagPrefix = 2u << 30;
+constexpr uint32_t kFlagMask = 3u << 30;
+constexpr uint32_t kValMask = ~kFlagMask;
+constexpr int kSpinLimit = 1 << 22;              // a look-back that never completes raises meta[kMetaError] instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- digit histograms of all passes in one read of the keys -------------------------------------
+// DROP: keys equal to EX_INVISIBLE_KEY are not counted; *n_valid receives the number of counted keys.
+template <typename KeyT, int NPASS, bool DROP>
+__global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ count_ptr,
+                                                         uint32_t cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ n_valid)
+{
+    constexpr int KPV = 16 / (int)sizeof(KeyT);          // keys per 128-bit load
+    __shared__ uint32_t sh[NPASS][kBins];
+    for (int i = threadIdx.x; i < NPASS * kBins; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n = count_ptr ? min(__ldg(count_ptr), cap) : cap;
+    const uint32_t nvec = n / KPV;                       // full vectors; the tail is counted by one thread per key
+    uint32_t mine = 0;
+    auto count = [&](uint32_t k) {
+        if (DROP && k == (uint32_t)(KeyT)EX_INVISIBLE_KEY) return;
+        mine++;
+#pragma unroll
+        for (int p = 0; p < NPASS; p++) atomicAdd(&sh[p][(k >> (8 * p)) & 255u], 1u);
+    };
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(keys) + v);
+        if (sizeof(KeyT) == 4) {
+            count(q.x); count(q.y); count(q.z); count(q.w);
+        } else {
+            count(q.x & 0xffff); count(q.x >> 16); count(q.y & 0xffff); count(q.y >> 16);
+            count(q.z & 0xffff); count(q.z >> 16); count(q.w & 0xffff); count(q.w >> 16);
+        }
+    }
+    if (blockIdx.x == 0 && nvec * KPV + threadIdx.x < n) count((uint32_t)keys[nvec * KPV + threadIdx.x]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * kBins; i += blockDim.x) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+    if (DROP) {
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_valid, mine);
+    }
+}
+
+// ---- one digit pass ---------------------------------------------------------------------------------
+// Stable: a tile is taken in ticket order (the ticket is the tile index, so every earlier tile is already
+// running when a tile starts waiting for it), items of a tile are ranked in (warp, round, lane) order, which
+// is their index order (index = tile base + warp * 32 * ITEMS + round * 32 + lane).
+// Ranking inside a warp: the lanes OR their lane bit into a per-(warp, digit) mask in shared memory - the result does
+// not depend on the order in which the hardware serialises conflicting lanes - and read the mask of their digit back:
+// lanes with the same digit, 12 instructions per key.  (MATCH.ANY resolves one group of equal values per iteration:
+// ~200 cycles on 32 distinct digits, 30 us of an 86 us tile pass; nine ballots + bit logic cost 45 instructions.)
+// FIRST: the values are the indices, keys equal to EX_INVISIBLE_KEY are dropped (`hist` does not count them).
+// !WRITE_KEYS (last pass of a sort whose keys are not needed afterwards): side_out[g] = side_src[value] rides along.
+template <typename KeyT, int ITEMS, bool FIRST, bool WRITE_KEYS>
+__global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_kernel(
+    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ count_ptr, uint32_t cap, int shift,
+    const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket_ctr,
+    uint32_t* __restrict__ err, const uint32_t* __restrict__ side_src, uint32_t* __restrict__ side_out)
+{
+    constexpr int TILE = kSortThreads * ITEMS;
+    constexpr int kMaskWords = 2 * kSortWarps * kBins;
+    __shared__ uint32_t s_cnt[kSortWarps][kBins];     // per-warp digit counts, then the warp's first local position per digit
+    __shared__ uint32_t s_delta[kBins];               // (global position) - (position in the sorted tile) of a digit's items
+    __shared__ KeyT s_key[TILE];                      // the tile in sorted order
+    __shared__ uint32_t s_raw[TILE > kMaskWords ? TILE : kMaskWords];   // lane masks while ranking, then the values in sorted order
+    __shared__ uint32_t s_part[2][kSortWarps];
+    __shared__ uint32_t s_ticket;
+    uint32_t* const s_val = s_raw;
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
+    for (int i = tid; i < kSortWarps * kBins; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
+    for (int i = tid; i < kMaskWords; i += kSortThreads) s_raw[i] = 0;
+    const uint32_t ghist = __ldg(hist + tid);                              // items of digit `tid` in the whole array
+    const uint32_t n = count_ptr ? min(__ldg(count_ptr), cap) : cap;
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    if ((uint64_t)ticket * TILE >= n) return;
+    const uint32_t tile_base = ticket * TILE;
+    const uint32_t warp_base = tile_base + warp * (32 * ITEMS) + lane;
+    const bool all_valid = !FIRST && (uint64_t)tile_base + TILE <= n;
+
+    uint32_t key[ITEMS], pos[ITEMS];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t idx = warp_base + i * 32;
+        bool ok = all_valid || idx < n;
+        key[i] = ok ? (uint32_t)__ldg(keys_in + idx) : 0u;
+        if (FIRST) ok = ok && key[i] != EX_INVISIBLE_KEY;
+        valid |= (ok ? 1u : 0u) << i;
+    }
+    // rank inside the warp (two mask arrays, alternating: the clear of round i cannot meet the ORs of round i + 1)
+    const uint32_t lane_bit = 1u << lane, lt = lane_bit - 1u;
+    auto rank_rounds = [&](auto all_c) {
+        constexpr bool ALL = decltype(all_c)::value;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const bool ok = ALL || ((valid >> i) & 1u);
+            const uint32_t d = (key[i] >> shift) & 255u;
+            uint32_t* const mask = s_raw + ((i & 1) * kSortWarps + warp) * kBins + d;
+            if (ok) atomicOr(mask, lane_bit);
+            __syncwarp();
+            const uint32_t peers = ok ? *mask : 0u;
+            const uint32_t before = s_cnt[warp][d];
+            __syncwarp();
+            if (ok && (peers & lt) == 0u) {                 // the lowest lane of the group
+                s_cnt[warp][d] = before + __popc(peers);
+                *mask = 0u;
+            }
+            pos[i] = before + __popc(peers & lt);
+        }
+    };
+    if (all_valid) rank_rounds(std::true_type{}); else rank_rounds(std::false_type{});
+    __syncthreads();
+    // thread `tid` owns digit `tid`: exclusive offsets of the warps, the tile's count
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) {
+        const uint32_t c = s_cnt[w][tid];
+        s_cnt[w][tid] = cnt;
+        cnt += c;
+    }
+    // publish as early as possible: the tiles behind wait for this
+    uint32_t* const my_status = status + (size_t)ticket * kBins + tid;
+    st_status(my_status, (ticket == 0 ? kFlagPrefix : kFlagAgg) | cnt);
+    // exclusive scans over the digits: position of the digit inside the sorted tile / inside the whole output
+    uint32_t ia = cnt, ib = ghist;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ta = __shfl_up_sync(full, ia, d), tb = __shfl_up_sync(full, ib, d);
+        if (lane >= d) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_part[0][warp] = ia; s_part[1][warp] = ib; }
+    __syncthreads();
+    uint32_t wa = 0, wb = 0, n_tile = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) {
+        const uint32_t a = s_part[0][w], b = s_part[1][w];
+        if (w < warp) { wa += a; wb += b; }
+        n_tile += a;
+    }
+    const uint32_t tile_start = wa + ia - cnt;      // first position of digit `tid` in the sorted tile
+    const uint32_t glob_start = wb + ib - ghist;    // first position of digit `tid` in the output
+    // chained look-back: items of digit `tid` in all earlier tiles
+    // (kWindow independent loads in flight per step)
+    uint32_t prefix = 0;
+    if (ticket != 0) {
+        constexpr int kWindow = EX_SORT_WINDOW;
+        int t = (int)ticket - 1, spins = 0;
+        bool done = false;
+        while (!done) {
+            uint32_t v[kWindow];
+#pragma unroll
+            for (int k = 0; k < kWindow; k++) v[k] = t - k >= 0 ? ld_status(status + (size_t)(t - k) * kBins + tid) : kFlagPrefix;
+#pragma unroll
+            for (int k = 0; k < kWindow; k++) {
+                if (!done) {
+                    const uint32_t f = v[k] & kFlagMask;
+                    if (f == 0) {                    // not published yet: read again from here
+                        if (++spins > kSpinLimit) { atomicOr(err, 1u); done = true; }
+                        break;
+                    }
+                    prefix += v[k] & kValMask;
+                    --t;
+                    if (f == kFlagPrefix) done = true;
+                }
+            }
+        }
+        st_status(my_status, kFlagPrefix | ((prefix + cnt) & kValMask));
+    }
+    s_delta[tid] = glob_start + prefix - tile_start;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++) s_cnt[w][tid] += tile_start;
+    __syncthreads();
+    // scatter into the sorted tile (the values are fetched only now: fewer live registers while ranking) ...
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        if ((valid >> i) & 1u) {
+            const uint32_t idx = warp_base + i * 32;
+            const uint32_t d = (key[i] >> shift) & 255u;
+            const uint32_t lp = s_cnt[warp][d] + pos[i];
+            s_key[lp] = (KeyT)key[i];
+            s_val[lp] = FIRST ? idx : __ldg(vals_in + idx);
+        }
+    }
+    __syncthreads();
+    // ... and from there to the output: consecutive threads write consecutive addresses within a digit
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t p = i * kSortThreads + tid;
+        if (p < n_tile) {
+            const KeyT k = s_key[p];
+            const uint32_t g = s_delta[((uint32_t)k >> shift) & 255u] + p;
+            if (WRITE_KEYS) keys_out[g] = k;
+            const uint32_t v = s_val[p];
+            vals_out[g] = v;
+            if (!WRITE_KEYS && side_src) side_out[g] = __ldg(side_src + v);     // last depth pass: tiles_touched in depth order
+        }
+    }
+}
+
+// Sums of tiles_touched (in depth order) over 32 / 256 / 16384 consecutive Gaussians and their total R: with them a
+// warp of the duplicate kernel finds its first output position from < 100 words (rasterizer_impl.cu:295 runs an
+// inclusive scan over all P Gaussians).
+__global__ void __launch_bounds__(256) touched_sums_kernel(const uint32_t* __restrict__ n_vis_ptr, const uint32_t* __restrict__ touched_in_order,
+                                                           uint32_t* __restrict__ warp_sum, uint32_t* __restrict__ block_sum,
+                                                           uint32_t* __restrict__ super_sum, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_w[8];
+    const uint32_t n_vis = __ldg(n_vis_ptr);
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (blockIdx.x * 256u >= n_vis) return;
+    const uint32_t w = __reduce_add_sync(0xffffffffu, j < n_vis ? touched_in_order[j] : 0u);
+    if ((threadIdx.x & 31) == 0) {
+        warp_sum[j >> 5] = w;
+        s_w[threadIdx.x >> 5] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) b += s_w[k];
+        block_sum[blockIdx.x] = b;
+        atomicAdd(super_sum + (blockIdx.x >> 6), b);
+        atomicAdd(total, b);
+    }
+}
 
 constexpr int kDupThreads = 256;
 
@@ -29,9 +293,13 @@ constexpr int kDupThreads = 256;
 // writes 2- and 4-byte items at 32 unrelated addresses per instruction).  With exact-output
 // culling the surviving items are compacted with a ballot; their order, and therefore the
 // offsets of the scan, are preserved.
-__global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uint32_t* __restrict__ order,
-                                                                const uint32_t* __restrict__ key_sorted,
-                                                                const uint32_t* __restrict__ offsets,
+// The warp's first output position is the number of items of all earlier Gaussians, summed from the three levels of
+// touched_sums_kernel; warps are independent (no barrier, no chain).  The rectangle is recomputed from the stored
+// record with the same inline functions on the same floats as in the preprocess kernel (its area IS tiles_touched).
+__global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* __restrict__ n_vis_ptr, const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ touched_in_order,
+                                                                const uint32_t* __restrict__ warp_sum, const uint32_t* __restrict__ block_sum,
+                                                                const uint32_t* __restrict__ super_sum,
                                                                 const SplatRec* __restrict__ rec, const int* __restrict__ radii,
                                                                 int grid_x, int grid_y, unsigned flags, const float* __restrict__ pad_ptr,
                                                                 uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out, uint32_t cap)
@@ -39,33 +307,24 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
     __shared__ CullCtx s_ctx[kDupThreads / 32][32];
     __shared__ int s_prefix[kDupThreads / 32][32];
     const unsigned full = 0xffffffffu;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_vis = __ldg(n_vis_ptr);
+    if ((j & ~31u) >= n_vis) return;
     const bool cull = (flags & 1u) != 0;
     const float pad = cull ? __ldg(pad_ptr) : 0.f;
-    const int jw = (j & ~31);
-    if (jw >= P) return;
-    // the warp's output window starts at wbase: offsets are an inclusive scan in this order
-    const uint32_t wbase = (jw == 0) ? 0u : offsets[jw - 1];
-    if (offsets[min(jw + 31, P - 1)] == wbase) return;       // nothing to emit
+    const bool have = j < n_vis;
 
-    CullCtx c;
-    c.ok = 0; c.w = 0; c.x0 = c.y0 = 0; c.id = 0;
-    int area = 0;
-    if (j < P && key_sorted[j] != EX_INVISIBLE_KEY) {
-        const uint32_t id = order[j];
-        const float4 a = rec[id].a;
-        int x0, y0, x1, y1;
-        tile_rect(a.x, a.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
-        if (cull) {
-            const float4 b = rec[id].b;
-            tight_rect(a.x, a.y, b.x, b.y, b.z, a.w, pad, x0, y0, x1, y1);     // the rectangle preprocess counted
-            c = cull_prepare(a.x, a.y, b.x, b.y, b.z, a.w, x0, y0, x1 - x0, id, pad);
-        } else {
-            c.x0 = x0; c.y0 = y0; c.w = x1 - x0; c.id = id;
-        }
-        area = (x1 - x0) * (y1 - y0);
-    }
+    const int area = have ? (int)touched_in_order[j] : 0;
+    const uint32_t id = have ? order[j] : 0u;
+    // first output position of the warp
+    const uint32_t wg = j >> 5, b = wg >> 3, sb = b >> 6;
+    uint32_t part = 0;
+    for (uint32_t k = lane; k < sb; k += 32) part += super_sum[k];
+    for (uint32_t k = sb * 64 + lane; k < b; k += 32) part += block_sum[k];
+    if ((uint32_t)lane < (wg & 7u)) part += warp_sum[b * 8 + lane];
+    const uint32_t wbase = __reduce_add_sync(full, part);
+
     int incl = area;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -73,6 +332,22 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
         if (lane >= d) incl += t;
     }
     const int total = __shfl_sync(full, incl, 31);
+    if (total == 0) return;
+
+    CullCtx c;
+    c.ok = 0; c.w = 0; c.x0 = c.y0 = 0; c.id = 0;
+    if (have) {
+        const float4 a = rec[id].a;
+        int x0, y0, x1, y1;
+        tile_rect(a.x, a.y, radii[id], grid_x, grid_y, x0, y0, x1, y1);
+        if (cull) {
+            const float4 bb = rec[id].b;
+            tight_rect(a.x, a.y, bb.x, bb.y, bb.z, a.w, pad, x0, y0, x1, y1);     // the rectangle preprocess counted
+            c = cull_prepare(a.x, a.y, bb.x, bb.y, bb.z, a.w, x0, y0, x1 - x0, id, pad);
+        } else {
+            c.x0 = x0; c.y0 = y0; c.w = x1 - x0; c.id = id;
+        }
+    }
     s_prefix[warp][lane] = incl - area;
     s_ctx[warp][lane] = c;
     __syncwarp();
@@ -80,29 +355,31 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(int P, const uin
         const int item = base + lane;
         bool keep = false;
         uint16_t tile = 0;
-        uint32_t id = 0;
+        uint32_t idv = 0;
         if (item < total) {
             const int src = expand_owner(s_prefix[warp], item);
             const int local = item - s_prefix[warp][src];
             const int w = s_ctx[warp][src].w;
             const int ty = s_ctx[warp][src].y0 + local / w, tx = s_ctx[warp][src].x0 + local % w;
-            id = s_ctx[warp][src].id;
+            idv = s_ctx[warp][src].id;
             tile = (uint16_t)(ty * grid_x + tx);
             keep = !(cull && cull_test(s_ctx[warp][src], tx, ty, pad));
         }
-        // culled instances keep their slot (the scan counted the full rectangle) but are keyed to
+        // culled instances keep their slot (the count is the full rectangle) but are keyed to
         // the dump tile 0xFFFF, which the stable tile sort moves behind every real tile
-        if (item < total && wbase + item < cap) {      // cap: capacity of a speculatively sized buffer (api.cu)
+        if (item < total && wbase + item < cap) {      // cap: capacity of the buffer, sized before R is known (api.cu)
             tile_out[wbase + item] = keep ? tile : (uint16_t)0xFFFF;
-            val_out[wbase + item] = id;
+            val_out[wbase + item] = idv;
         }
     }
 }
 
 // ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
 // eight 16-bit keys per thread from one 128-bit load.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges, uint32_t dump)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ total_ptr, uint32_t cap, const uint16_t* __restrict__ tiles,
+                                                          uint2* __restrict__ ranges, uint32_t dump)
 {
+    const int L = (int)min(__ldg(total_ptr), cap);
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = g * 8;
     if (base >= L) return;
@@ -173,45 +450,53 @@ uint32_t higher_msb(uint32_t n)
 
 }  // namespace
 
-// The CUB size queries touch the driver (device attributes, function attributes): memoised, because
-// they sit on the critical path right after the forward's host synchronisation.
-size_t binning_stage1_temp_bytes(int P)
-{
-    static thread_local int last_p = -1, last_dev = -1;
-    static thread_local size_t last_bytes = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (P == last_p && dev == last_dev) return last_bytes;
-    last_dev = dev;
-    size_t a = 0, b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
-    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint32_t*> it(nullptr, TilesInOrder{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
-    last_p = P;
-    last_bytes = (a > b ? a : b) + 256;
-    return last_bytes;
-}
+// ---- host side -------------------------------------------------------------------------------------
+// Scratch words behind GeometryState::meta.  Zeroed together with it at the start of every forward:
+//   hist[6][256]                     digit histograms: 4 depth passes, 2 tile passes
+//   super_sum[ceil(P / 16384)]       sums of tiles_touched (depth order) over 16384 Gaussians
+//   depth_status[4][tiles][256]      look-back words of the depth passes
+// not zeroed (fully written before they are read):
+//   block_sum[ceil(P / 256)], warp_sum[ceil(P / 32)]
+namespace {
+constexpr int kDepthPasses = 4;
+constexpr int kDepthTile = kSortThreads * EX_SORT_ITEMS_DEPTH;
+constexpr int kTileTile = kSortThreads * EX_SORT_ITEMS_TILE;
 
-size_t binning_stage2_temp_bytes(int R)
+struct SortScratch {
+    uint32_t *hist, *super_sum, *depth_status, *block_sum, *warp_sum;
+    size_t depth_tiles, zero_words, words;
+};
+SortScratch sort_scratch(char* base, int P)
 {
-    // temp size grows monotonically with the item count: query once per 1M-item bucket
-    static thread_local long long last_bucket = -1;
-    static thread_local int last_dev = -1;
-    static thread_local size_t last_bytes = 0;
-    const long long bucket = ((long long)(R > 0 ? R : 1) + 0xFFFFF) >> 20;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (bucket == last_bucket && dev == last_dev) return last_bytes;
-    last_dev = dev;
-    const long long n = bucket << 20;
-    size_t a = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint16_t*)nullptr, (uint16_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n < 0x7fffffffLL ? n : 0x7fffffffLL));
-    last_bucket = bucket;
-    last_bytes = a + 256;
-    return last_bytes;
+    SortScratch sc;
+    const size_t n = (size_t)(P > 0 ? P : 0);
+    auto up = [](size_t v) { return (v + 63) & ~size_t(63); };
+    uint32_t* w = reinterpret_cast<uint32_t*>(base);
+    sc.depth_tiles = (n + kDepthTile - 1) / kDepthTile;
+    sc.hist = w;
+    sc.super_sum = sc.hist + 6 * kBins;
+    sc.depth_status = sc.super_sum + up((n + 16383) / 16384 + 1);
+    sc.block_sum = sc.depth_status + (size_t)kDepthPasses * sc.depth_tiles * kBins;
+    sc.zero_words = (size_t)(sc.block_sum - w);
+    sc.warp_sum = sc.block_sum + up((n + 255) / 256);
+    sc.words = (size_t)(sc.warp_sum - w) + up((n + 31) / 32);
+    return sc;
 }
+int tile_sort_passes(int grid_x, int grid_y, unsigned flags)
+{
+    const int bit = (int)higher_msb((uint32_t)(grid_x * grid_y));
+    return ((flags & 1u) != 0 || bit > 8) ? 2 : 1;        // with culling the dump tile 0xFFFF needs all 16 bits
+}
+}  // namespace
+
+size_t binning_geometry_scratch_bytes(int P) { return sort_scratch(nullptr, P).words * sizeof(uint32_t) + 256; }
+size_t binning_geometry_zero_bytes(int P) { return sort_scratch(nullptr, P).zero_words * sizeof(uint32_t); }
+size_t binning_status_bytes(int cap)
+{
+    const size_t tiles = ((size_t)(cap > 0 ? cap : 0) + kTileTile - 1) / kTileTile;
+    return 2 * tiles * kBins * sizeof(uint32_t) + 256;
+}
+int binning_duplicate_set(int grid_x, int grid_y, unsigned flags) { return tile_sort_passes(grid_x, grid_y, flags) & 1; }
 
 // `out` must have been zeroed by the caller
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s)
@@ -220,39 +505,85 @@ cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint3
     return cudaGetLastError();
 }
 
-cudaError_t binning_stage1(const GeometryState& g, int P, cudaStream_t s)
+// depth order of the visible Gaussians: g.order[0 .. N_vis), N_vis in meta[EX_META_NVIS]; tiles_touched in that order
+// (g.key_b) with its partial sums, the instance count R in meta[EX_META_TOTAL]
+cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s)
 {
-    size_t tb = g.temp_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(g.temp, tb, g.key_in, g.key_sorted, g.val_in, g.order, P, 0, 32, s);
-    if (e != cudaSuccess) return e;
-    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint32_t*> it(g.order, TilesInOrder{g.tiles_touched});
-    tb = g.temp_bytes;
-    return cub::DeviceScan::InclusiveSum(g.temp, tb, it, g.offsets, P, s);
-}
-
-cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, const int* radii, int P, int cap,
-                              int grid_x, int grid_y, unsigned flags, cudaStream_t s)
-{
-    if (P <= 0 || cap <= 0) return cudaSuccess;
-    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
-        P, g.order, g.key_sorted, g.offsets, g.rec, radii, grid_x, grid_y, flags,
-        reinterpret_cast<const float*>(g.meta), b.tile_unsorted, b.val_unsorted, (uint32_t)cap);
+    if (P <= 0) return cudaSuccess;
+    const SortScratch sc = sort_scratch(g.temp, P);
+    uint32_t* const n_vis = g.meta + EX_META_NVIS;
+    uint32_t* const err = g.meta + EX_META_ERROR;
+    radix_hist_kernel<uint32_t, kDepthPasses, true><<<148 * 3, 512, 0, s>>>(g.key_in, nullptr, (uint32_t)P, sc.hist, n_vis);
+    const int grid = (int)sc.depth_tiles;
+    // ping-pong between (key_a, val_a) and (key_b, order): the last pass leaves the ids in `order`, writes no keys and
+    // gathers tiles_touched into key_b (depth order) for the duplicate kernel's scan
+    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, true, true><<<grid, kSortThreads, 0, s>>>(
+        g.key_in, nullptr, g.key_a, g.val_a, nullptr, (uint32_t)P, 0, sc.hist, sc.depth_status, g.meta + EX_META_TICKETS + 0, err, nullptr, nullptr);
+    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, true><<<grid, kSortThreads, 0, s>>>(
+        g.key_a, g.val_a, g.key_b, g.order, n_vis, (uint32_t)P, 8, sc.hist + kBins, sc.depth_status + sc.depth_tiles * kBins,
+        g.meta + EX_META_TICKETS + 1, err, nullptr, nullptr);
+    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, true><<<grid, kSortThreads, 0, s>>>(
+        g.key_b, g.order, g.key_a, g.val_a, n_vis, (uint32_t)P, 16, sc.hist + 2 * kBins, sc.depth_status + 2 * sc.depth_tiles * kBins,
+        g.meta + EX_META_TICKETS + 2, err, nullptr, nullptr);
+    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, false><<<grid, kSortThreads, 0, s>>>(
+        g.key_a, g.val_a, nullptr, g.order, n_vis, (uint32_t)P, 24, sc.hist + 3 * kBins, sc.depth_status + 3 * sc.depth_tiles * kBins,
+        g.meta + EX_META_TICKETS + 3, err, g.tiles_touched, g.key_b);
+    touched_sums_kernel<<<(P + 255) / 256, 256, 0, s>>>(n_vis, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.meta + EX_META_TOTAL);
     return cudaGetLastError();
 }
 
-cudaError_t binning_sort_ranges(const BinningState& b, const ImageState& img, int R, int grid_x, int grid_y,
-                                unsigned flags, cudaStream_t s)
+// before a second duplicate / tile sort of the same frame (the first buffer was too small): clear what the tile sort accumulates
+cudaError_t binning_reset_instances(const GeometryState& g, int P, cudaStream_t s)
+{
+    const SortScratch sc = sort_scratch(g.temp, P);
+    cudaError_t e = cudaMemsetAsync(g.meta + EX_META_TICKETS + 5, 0, 2 * sizeof(uint32_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc.hist + 4 * kBins, 0, 2 * kBins * sizeof(uint32_t), s);
+    return e;
+}
+
+// emit the (tile, id) pairs in depth order into set `binning_duplicate_set()` of the buffer; entries at positions
+// >= cap are dropped (the buffer is sized before the count is known on the host)
+cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, const int* radii, int P, int cap,
+                              int grid_x, int grid_y, unsigned flags, cudaStream_t s)
+{
+    if (P <= 0) return cudaSuccess;
+    const SortScratch sc = sort_scratch(g.temp, P);
+    const int set = binning_duplicate_set(grid_x, grid_y, flags);
+    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
+        g.meta + EX_META_NVIS, g.order, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.rec, radii, grid_x, grid_y, flags,
+        reinterpret_cast<const float*>(g.meta), b.tile[set], b.val[set], (uint32_t)(cap > 0 ? cap : 0));
+    return cudaGetLastError();
+}
+
+// stable sort of the min(R, cap) pairs by tile into set 0 (point_list, tile_sorted), per-tile ranges
+cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, const ImageState& img, int P, int cap,
+                                int grid_x, int grid_y, unsigned flags, cudaStream_t s)
 {
     const int tiles = grid_x * grid_y;
     cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, s);
-    if (e != cudaSuccess || R <= 0) return e;
-    size_t tb = b.temp_bytes;
-    const int bit = (int)higher_msb((uint32_t)tiles);
-    const bool cull = (flags & 1u) != 0;
-    e = cub::DeviceRadixSort::SortPairs(b.temp, tb, b.tile_unsorted, b.tile_sorted, b.val_unsorted, b.point_list,
-                                        R, 0, (cull || bit > 16) ? 16 : bit, s);
+    if (e != cudaSuccess || cap <= 0 || P <= 0) return e;
+    e = cudaMemsetAsync(b.status, 0, binning_status_bytes(cap) - 256, s);
     if (e != cudaSuccess) return e;
-    const int groups = (R + 7) / 8;
-    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(R, b.tile_sorted, img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu);
+    const SortScratch sc = sort_scratch(g.temp, P);
+    const uint32_t* const total = g.meta + EX_META_TOTAL;
+    uint32_t* const err = g.meta + EX_META_ERROR;
+    const bool cull = (flags & 1u) != 0;
+    const int passes = tile_sort_passes(grid_x, grid_y, flags);
+    const int src = passes & 1;
+    const int grid = (cap + kTileTile - 1) / kTileTile;
+    const size_t st = (size_t)grid * kBins;
+    if (passes == 2) {
+        radix_hist_kernel<uint16_t, 2, false><<<148 * 3, 512, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
+        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
+            b.tile[0], b.val[0], b.tile[1], b.val[1], total, (uint32_t)cap, 0, sc.hist + 4 * kBins, b.status, g.meta + EX_META_TICKETS + 5, err, nullptr, nullptr);
+        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
+            b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 8, sc.hist + 5 * kBins, b.status + st, g.meta + EX_META_TICKETS + 6, err, nullptr, nullptr);
+    } else {
+        radix_hist_kernel<uint16_t, 1, false><<<148 * 3, 512, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
+        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
+            b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 0, sc.hist + 4 * kBins, b.status, g.meta + EX_META_TICKETS + 5, err, nullptr, nullptr);
+    }
+    const int groups = (cap + 7) / 8;
+    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(total, (uint32_t)cap, b.tile[0], img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu);
     return cudaGetLastError();
 }

@@ -107,29 +107,38 @@ struct Carver {
     }
 };
 
+// device scalars in GeometryState::meta (zeroed at the start of every forward)
+#define EX_META_PAD 0        // bits of max |subpixel offset| (exact tile culling)
+#define EX_META_FLOW 1       // does any visible Gaussian carry a non-zero dir3D?
+#define EX_META_INEXACT 2    // alpha thresholds that fell back to the conservative value (preprocess.cu)
+#define EX_META_NVIS 3       // visible Gaussians (depth histogram kernel)
+#define EX_META_TOTAL 4      // R: (Gaussian, tile) instances (touched_sums_kernel)
+#define EX_META_ERROR 5      // bit 0: a look-back did not complete
+#define EX_META_TICKETS 8    // [0..3] depth passes, [5..6] tile passes
+
 struct GeometryState {
     uint32_t* key_in;         // [P] depth bits, EX_INVISIBLE_KEY when culled
-    uint32_t* val_in;         // [P] iota
-    uint32_t* key_sorted;     // [P]
-    uint32_t* order;          // [P] Gaussian ids by (depth, id)
+    uint32_t* key_a;          // [P] ping-pong arrays of the depth sort (only the first N_vis entries are used)
+    uint32_t* val_a;          // [P]
+    uint32_t* key_b;          // [P]
+    uint32_t* order;          // [P] ids of the visible Gaussians by (depth, id): N_vis entries
     uint32_t* tiles_touched;  // [P]
-    uint32_t* offsets;        // [P] inclusive scan of tiles_touched in `order`
     SplatRec* rec;            // [P]
     uint8_t* clamped;         // [P] bit c = colour channel c was clamped (forward.cu:67-69)
     GradAcc* gacc;            // [P]
-    uint32_t* meta;           // [64] misc device scalars
-    char* temp;               // cub temp storage
+    uint32_t* meta;           // [64] device scalars (EX_META_*), directly followed by ...
+    char* temp;               // ... the sort scratch (binning.cu: histograms, look-back words)
     size_t temp_bytes;
     size_t total;
 };
 
+// Two sets of (tile, id) arrays of `cap` entries each.  Set 0 sits at the front of the buffer (point_list at
+// offset 0) and holds the sorted lists at the end; the duplicate kernel writes set 0 when the tile sort has two
+// passes (0 -> 1 -> 0) and set 1 when it has one.
 struct BinningState {
-    uint16_t* tile_unsorted;  // [R]
-    uint32_t* val_unsorted;   // [R]
-    uint16_t* tile_sorted;    // [R]
-    uint32_t* point_list;     // [R] Gaussian ids, by (tile, depth, id): == reference point_list
-    char* temp;
-    size_t temp_bytes;
+    uint16_t* tile[2];        // [cap]; tile[0] = sorted tile ids at the end
+    uint32_t* val[2];         // [cap]; val[0] = point_list: Gaussian ids by (tile, depth, id) == reference point_list
+    uint32_t* status;         // look-back words of the tile passes
     size_t total;
 };
 
@@ -142,7 +151,7 @@ struct ImageState {
 };
 
 GeometryState carve_geometry(void* base, int P, size_t temp_bytes);
-BinningState carve_binning(void* base, int R, int cap, size_t temp_bytes);
+BinningState carve_binning(void* base, int cap, size_t status_bytes);
 ImageState carve_image(void* base, int width, int height);
 
 // ---- kernel parameter blocks ---------------------------------------------------------------------
@@ -179,7 +188,6 @@ struct PreprocessParams {
     const float* pad_ptr;   // max |subpixel offset| (device scalar), read when EX4DGS_FLAG_TILE_CULL
     int* radii;
     uint32_t* key_in;
-    uint32_t* val_in;
     uint32_t* tiles_touched;
     SplatRec* rec;
     uint8_t* clamped;
@@ -323,17 +331,22 @@ int regularizer_blocks();
 cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s);
 
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
-size_t binning_stage1_temp_bytes(int P);
-size_t binning_stage2_temp_bytes(int R);
-// sort Gaussians by depth bits, scan tiles_touched in that order; returns cudaError
-cudaError_t binning_stage1(const GeometryState& g, int P, cudaStream_t s);
-// emit (tile, id) pairs in depth order (entries at positions >= cap are dropped: speculative launch before the
+size_t binning_geometry_scratch_bytes(int P);      // sort scratch behind GeometryState::meta ...
+size_t binning_geometry_zero_bytes(int P);         // ... and how much of it has to be zero at the start of a forward
+size_t binning_status_bytes(int cap);              // look-back words of the tile passes for a buffer of `cap` instances
+int binning_duplicate_set(int grid_x, int grid_y, unsigned flags);
+// depth order of the visible Gaussians -> g.order, their number -> meta[EX_META_NVIS], the instance count R ->
+// meta[EX_META_TOTAL]; returns cudaError
+cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s);
+// emit the (tile, id) pairs in depth order (entries at positions >= cap are dropped: the buffer is sized before the
 // instance count is known on the host) ...
 cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, const int* radii, int P, int cap,
                               int grid_x, int grid_y, unsigned flags, cudaStream_t s);
-// ... stable-sort the R pairs by tile, find per-tile ranges
-cudaError_t binning_sort_ranges(const BinningState& b, const ImageState& img, int R, int grid_x, int grid_y,
-                                unsigned flags, cudaStream_t s);
+// ... stable-sort the min(R, cap) pairs by tile, find the per-tile ranges
+cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, const ImageState& img, int P, int cap,
+                                int grid_x, int grid_y, unsigned flags, cudaStream_t s);
+// clear what duplicate / tile sort accumulate, for a second run within one frame
+cudaError_t binning_reset_instances(const GeometryState& g, int P, cudaStream_t s);
 
 // ---- tile rectangle (auxiliary.h:46-56), shared by preprocess and the duplicate kernel -----------------
 __device__ __forceinline__ void tile_rect(float px, float py, int radius, int grid_x, int grid_y,

@@ -366,7 +366,6 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     p.radii[idx] = radius_out;
     p.tiles_touched[idx] = tiles;
     p.key_in[idx] = tiles ? key : EX_INVISIBLE_KEY;
-    p.val_in[idx] = (uint32_t)idx;
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
