@@ -15,6 +15,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 FLAG_TILE_CULL = 1
 FLAG_SH_SEGMENTED = 2
+FLAG_NO_HOST_WAIT = 4
 
 _F = C.c_float
 _P = C.c_void_p
@@ -51,6 +52,7 @@ SIGNATURES = {
     "ex4dgs_last_error": (C.c_char_p, []),
     "ex4dgs_last_inexact_thresholds": (C.c_uint, []),
     "ex4dgs_forward_geometry": (None, [C.POINTER(_I), C.POINTER(_I)]),
+    "ex4dgs_set_capacity_hint": (None, [_I]),
     "ex4dgs_geometry_bytes": (C.c_size_t, [_I]),
     "ex4dgs_binning_bytes": (C.c_size_t, [_I]),
     "ex4dgs_image_bytes": (C.c_size_t, [_I, _I]),

@@ -198,6 +198,7 @@ int ex4dgs_profile_read(double* ms, int* frames_fwd, int* frames_bwd)
     return EX4DGS_OK;
 }
 const char* ex4dgs_last_error(void) { return g_err; }
+void ex4dgs_set_capacity_hint(int instances) { g_last_R = instances > 0 ? instances : 0; }
 unsigned ex4dgs_last_inexact_thresholds(void) { return g_last_inexact; }
 void ex4dgs_forward_geometry(int* batch, int* warps)
 {
@@ -227,6 +228,7 @@ int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_de
         {"rec", 0, (size_t)g.rec, sizeof(SplatRec), n},
         {"clamped", 0, (size_t)g.clamped, 1, n},
         {"gacc", 0, (size_t)g.gacc, sizeof(GradAcc), n},
+        {"meta", 0, (size_t)g.meta, 4, 64},
         {"tile_sorted", 1, (size_t)b.tile[0], 2, r},
         {"point_list", 1, (size_t)b.val[0], 4, r},
         {"final_T", 2, (size_t)im.final_T, 4, px},
@@ -390,12 +392,17 @@ int ex4dgs_forward(
     STAGE(debug, s, "depth sort");
     prof.mark();
 
+    const bool no_wait = (flags & EX4DGS_FLAG_NO_HOST_WAIT) != 0;
+    if (no_wait && g_last_R <= 0)
+        return fail(EX4DGS_ERR_INVALID, "EX4DGS_FLAG_NO_HOST_WAIT needs a capacity hint (ex4dgs_set_capacity_hint, or an earlier forward of this thread)");
     // R is on the device now; the host reads it (rasterizer_impl.cu:299) but waits for it only after everything is queued
-    uint32_t* rb = g_readback.get();
-    if (!rb) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
-    cudaEvent_t rb_ev = g_readback.event();
-    CK(cudaMemcpyAsync(rb, geom.meta + EX_META_FLOW, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (rb_ev) CK(cudaEventRecord(rb_ev, s));
+    uint32_t* rb = no_wait ? nullptr : g_readback.get();
+    if (!rb && !no_wait) return fail(EX4DGS_ERR_ALLOC, "cudaHostAlloc of the read-back words failed");
+    cudaEvent_t rb_ev = no_wait ? nullptr : g_readback.event();
+    if (!no_wait) {
+        CK(cudaMemcpyAsync(rb, geom.meta + EX_META_FLOW, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (rb_ev) CK(cudaEventRecord(rb_ev, s));
+    }
 
     // Nothing below waits for the instance count R before it is launched: the binning buffer is asked for with a
     // capacity guessed from the previous frames of this thread (largest recent R + 25 %), the duplicate kernel drops
@@ -428,16 +435,20 @@ int ex4dgs_forward(
             if (!marked) prof.mark();
             // the flow flag is known on the host only after the wait: the first attempt carries the flow accumulators
             // whenever a previous frame of this thread did
-            const int rc = render(attempt == 0 ? g_last_flow : flow32 != 0);
+            const int rc = render(no_wait ? true : (attempt == 0 ? g_last_flow : flow32 != 0));
             if (rc < 0) return rc;
             STAGE(debug, s, "render");
             if (!marked) prof.mark();
             marked = true;
         }
         if (attempt == 1) break;
+        if (no_wait) {            // nothing is read back: the capacity stands in for R (truncation is flagged on the device)
+            R = cap;
+            break;
+        }
         if (rb_ev) CK(cudaEventSynchronize(rb_ev));
         else CK(cudaStreamSynchronize(s));
-        if (rb[8] != 0) {
+        if (rb[8] & 1u) {
             rb[8] = 0;
             return fail(EX4DGS_ERR_CUDA, "binning: a look-back of the previous forward's tile sort did not complete");
         }
@@ -456,7 +467,7 @@ int ex4dgs_forward(
     }
     g_last_cap = cap;
     // look-back failures of the tile passes (queued behind the read-back above) are reported by the next forward
-    CK(cudaMemcpyAsync(rb + 8, geom.meta + EX_META_ERROR, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (!no_wait) CK(cudaMemcpyAsync(rb + 8, geom.meta + EX_META_ERROR, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     prof.done();
     return R;
 }

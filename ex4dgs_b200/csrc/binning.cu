@@ -377,10 +377,12 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* 
 // ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
 // eight 16-bit keys per thread from one 128-bit load.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ total_ptr, uint32_t cap, const uint16_t* __restrict__ tiles,
-                                                          uint2* __restrict__ ranges, uint32_t dump)
+                                                          uint2* __restrict__ ranges, uint32_t dump, uint32_t* __restrict__ err)
 {
-    const int L = (int)min(__ldg(total_ptr), cap);
+    const uint32_t total = __ldg(total_ptr);
+    const int L = (int)min(total, cap);
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0 && total > cap) atomicOr(err, 2u);      // the lists are truncated (EX4DGS_FLAG_NO_HOST_WAIT: nobody else notices)
     const int base = g * 8;
     if (base >= L) return;
     uint16_t t[8];
@@ -584,6 +586,6 @@ cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, c
             b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 0, sc.hist + 4 * kBins, b.status, g.meta + EX_META_TICKETS + 5, err, nullptr, nullptr);
     }
     const int groups = (cap + 7) / 8;
-    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(total, (uint32_t)cap, b.tile[0], img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu);
+    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(total, (uint32_t)cap, b.tile[0], img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu, err);
     return cudaGetLastError();
 }

@@ -113,7 +113,7 @@ struct Carver {
 #define EX_META_INEXACT 2    // alpha thresholds that fell back to the conservative value (preprocess.cu)
 #define EX_META_NVIS 3       // visible Gaussians (depth histogram kernel)
 #define EX_META_TOTAL 4      // R: (Gaussian, tile) instances (touched_sums_kernel)
-#define EX_META_ERROR 5      // bit 0: a look-back did not complete
+#define EX_META_ERROR 5      // bit 0: a look-back did not complete; bit 1: more instances than the binning buffer holds
 #define EX_META_TICKETS 8    // [0..3] depth passes, [5..6] tile passes
 
 struct GeometryState {

@@ -38,6 +38,35 @@ def get_default_flags() -> int:
     return _DEFAULT_FLAGS
 
 
+# Forward without any host wait (EX4DGS_FLAG_NO_HOST_WAIT): CUDA-graph capturable.  The binning buffer is sized from the
+# capacity hint (set_capacity_hint, or the calling thread's earlier frames), `num_rendered` is that capacity, and a frame
+# with more instances than the capacity is truncated and flagged on the device: check frame_overflowed() when the host
+# synchronises anyway.  Off by default (the default forward waits for the instance count while the frame is queued and
+# is always exact).
+_HOST_WAIT = True
+
+
+def set_host_wait(wait: bool) -> None:
+    global _HOST_WAIT
+    _HOST_WAIT = bool(wait)
+
+
+def get_host_wait() -> bool:
+    return _HOST_WAIT
+
+
+def set_capacity_hint(instances: int) -> None:
+    """Expected number of (Gaussian, tile) instances of the calling thread's next frames (0: forget the history)."""
+    _lib.load().ex4dgs_set_capacity_hint(int(instances))
+
+
+def frame_overflowed(out: torch.Tensor) -> bool:
+    """Did the frame that produced `out` (an output of the rasterizer that requires grad) have more instances than its
+    binning buffer held?  Only possible with set_host_wait(False).  Waits for the device."""
+    word = getattr(out.grad_fn, "overflow_word", None)
+    return bool(int(word.item()) & 2) if word is not None else False
+
+
 def last_inexact_thresholds() -> int:
     """Diagnostics of the calling thread's last forward: visible Gaussians whose exact alpha >= 1/255 threshold could not
     be established (csrc/preprocess.cu alpha_threshold); 0 on everything observed so far."""
@@ -182,6 +211,8 @@ def _forward_impl(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, s
     lib = _lib.load()
     dev = means3D.device
     flags = int(getattr(rs, "_flags", _DEFAULT_FLAGS))
+    if not _HOST_WAIT:
+        flags |= _lib.FLAG_NO_HOST_WAIT
 
     args = (rs.bg, means3D, dir3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
             cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
@@ -271,6 +302,11 @@ def _forward_impl(ctx, means3D, means2D, dir3D, sh, colors_precomp, opacities, s
         ctx.set_materialize_grads(False)
     ctx.raster_settings = rs
     ctx.num_rendered = int(R)
+    if flags & _lib.FLAG_NO_HOST_WAIT:
+        # device word meta[5] of the geometry buffer (bit 1: the tile lists were truncated), see frame_overflowed()
+        _, off, _, _ = _lib.describe_buffers(P, 0, W, H)["meta"]
+        a = ((geomBuffer.data_ptr() + 255) & ~255) - geomBuffer.data_ptr()
+        ctx.overflow_word = geomBuffer[a + off + 20:a + off + 24].view(torch.int32)
     ctx.flags = flags
     ctx.segmented = seg is not None
     ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c,

@@ -14,8 +14,9 @@
  *     0-element tensor, which is nullptr: rasterize_points.cu:103-130, forward.cu:218,254).
  *   - matrices are 16 floats in the reference's transposed storage (auxiliary.h:68-87).
  *   - all work is enqueued on `stream` (a cudaStream_t cast to void*; NULL = legacy default stream,
- *     which is what the reference uses).  ex4dgs_forward performs ONE blocking 4-byte read-back
- *     (num_rendered) exactly like rasterizer_impl.cu:299.
+ *     which is what the reference uses).  ex4dgs_forward reads num_rendered back like
+ *     rasterizer_impl.cu:299, but waits for it only after the whole frame is queued (the instance
+ *     count stays on the device for the kernels); with EX4DGS_FLAG_NO_HOST_WAIT it does not wait at all.
  *   - functions return a negative ex4dgs_status on failure; ex4dgs_last_error() has the message.
  *   - the library is re-entrant per device/stream: no global mutable state besides the
  *     thread-local error string.
@@ -57,6 +58,13 @@ typedef enum ex4dgs_status {
  * ex4dgs_sh_segments holding the four gradient outputs (every element written).  M must be 16.
  * Gaussians [0, n_static) are the static ones (static first, as the reference concatenates). */
 #define EX4DGS_FLAG_SH_SEGMENTED 2u
+/* Forward without any host wait (CUDA-graph capturable): the binning buffer is sized from the capacity hint
+ * (ex4dgs_set_capacity_hint, or the largest instance count this thread has seen + 25 %; EX4DGS_ERR_INVALID without
+ * one), num_rendered is NOT read back: the return value is that capacity - an upper bound of the instance count,
+ * which ex4dgs_backward accepts as R.  If the frame has more instances than the capacity, the tile lists are
+ * truncated and bit 1 of the device word `meta[5]` of the geometry buffer (ex4dgs_describe_buffers: "meta") is
+ * set - check it whenever the host synchronises anyway (e.g. with the loss) and redo the frame without the flag. */
+#define EX4DGS_FLAG_NO_HOST_WAIT 4u
 typedef struct ex4dgs_sh_segments {
     int n_static;
     float* dc_static;      /* [n_static, 1, 3]        */
@@ -86,6 +94,11 @@ typedef void* (*ex4dgs_alloc_fn)(void* user, size_t nbytes);
  *     out_color [3,H,W], out_depth [H,W], out_acc [H,W], out_flow [3,H,W], out_idx [H,W] (int32,
  *     -1 = no contributor), radii [P] (int32, 0 = culled)
  */
+/* Sizing hint for the calling thread's next forwards: expected number of (Gaussian, tile) instances.  The binning
+ * buffer is requested with 25 % on top before the count of the frame is known; 0 forgets the history (the next forward
+ * then waits for the count before it sizes the buffer, like the reference). */
+void ex4dgs_set_capacity_hint(int instances);
+
 int ex4dgs_forward(
     ex4dgs_alloc_fn geometryBuffer, void* geometry_user,
     ex4dgs_alloc_fn binningBuffer, void* binning_user,
