@@ -25,17 +25,25 @@
 
 namespace {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kBins = 256;                       // 8-bit digits
+// shape of a pass: CTAs of THREADS threads take tiles of THREADS * ITEMS pairs; MINBLOCKS resident CTAs per SM
+#ifndef EX_SORT_THREADS_DEPTH
+#define EX_SORT_THREADS_DEPTH 512
+#endif
 #ifndef EX_SORT_ITEMS_DEPTH
-#define EX_SORT_ITEMS_DEPTH 16                   // keys per thread and tile: 4096 (depth, id) pairs per tile
+#define EX_SORT_ITEMS_DEPTH 8
+#endif
+#ifndef EX_SORT_MINBLOCKS_DEPTH
+#define EX_SORT_MINBLOCKS_DEPTH 2
+#endif
+#ifndef EX_SORT_THREADS_TILE
+#define EX_SORT_THREADS_TILE 256
 #endif
 #ifndef EX_SORT_ITEMS_TILE
-#define EX_SORT_ITEMS_TILE 16                    // 4096 (tile, id) pairs per tile
+#define EX_SORT_ITEMS_TILE 16
 #endif
-#ifndef EX_SORT_MINBLOCKS
-#define EX_SORT_MINBLOCKS 3                      // resident CTAs per SM the pass kernel is compiled for (register cap 85)
+#ifndef EX_SORT_MINBLOCKS_TILE
+#define EX_SORT_MINBLOCKS_TILE 3
 #endif
 #ifndef EX_SORT_WINDOW
 #define EX_SORT_WINDOW 8                         // status words a look-back step loads at once
@@ -60,7 +68,7 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
 // ---- digit histograms of all passes in one read of the keys -------------------------------------
 // DROP: keys equal to EX_INVISIBLE_KEY are not counted; *n_valid receives the number of counted keys.
 template <typename KeyT, int NPASS, bool DROP>
-__global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ count_ptr,
+__global__ void __launch_bounds__(1024) radix_hist_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ count_ptr,
                                                          uint32_t cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ n_valid)
 {
     constexpr int KPV = 16 / (int)sizeof(KeyT);          // keys per 128-bit load
@@ -107,31 +115,43 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict_
 // ~200 cycles on 32 distinct digits, 30 us of an 86 us tile pass; nine ballots + bit logic cost 45 instructions.)
 // FIRST: the values are the indices, keys equal to EX_INVISIBLE_KEY are dropped (`hist` does not count them).
 // !WRITE_KEYS (last pass of a sort whose keys are not needed afterwards): side_out[g] = side_src[value] rides along.
-template <typename KeyT, int ITEMS, bool FIRST, bool WRITE_KEYS>
-__global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_kernel(
+template <typename KeyT, int THREADS, int ITEMS>
+struct PassSmem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr int kMaskWords = 2 * WARPS * kBins;
+    static constexpr int kRawWords = TILE > kMaskWords ? TILE : kMaskWords;
+    // cnt[WARPS][256] | raw[kRawWords] (lane masks while ranking, then the values in sorted order) | delta[256] | part[2][8] | ticket | key[TILE]
+    static constexpr size_t kBytes = sizeof(uint32_t) * (WARPS * kBins + kRawWords + kBins + 16 + 4) + sizeof(KeyT) * TILE;
+};
+
+template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool FIRST, bool WRITE_KEYS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ count_ptr, uint32_t cap, int shift,
     const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket_ctr,
     uint32_t* __restrict__ err, const uint32_t* __restrict__ side_src, uint32_t* __restrict__ side_out)
 {
-    constexpr int TILE = kSortThreads * ITEMS;
-    constexpr int kMaskWords = 2 * kSortWarps * kBins;
-    __shared__ uint32_t s_cnt[kSortWarps][kBins];     // per-warp digit counts, then the warp's first local position per digit
-    __shared__ uint32_t s_delta[kBins];               // (global position) - (position in the sorted tile) of a digit's items
-    __shared__ KeyT s_key[TILE];                      // the tile in sorted order
-    __shared__ uint32_t s_raw[TILE > kMaskWords ? TILE : kMaskWords];   // lane masks while ranking, then the values in sorted order
-    __shared__ uint32_t s_part[2][kSortWarps];
-    __shared__ uint32_t s_ticket;
+    using L = PassSmem<KeyT, THREADS, ITEMS>;
+    constexpr int WARPS = L::WARPS, TILE = L::TILE;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* const s_cnt = smem;                               // [WARPS][256] per-warp digit counts, then the warp's first local position per digit
+    uint32_t* const s_raw = s_cnt + WARPS * kBins;
+    uint32_t* const s_delta = s_raw + L::kRawWords;             // [256] (global position) - (position in the sorted tile) of a digit's items
+    uint32_t* const s_part = s_delta + kBins;                   // [2][8]
+    uint32_t* const s_ticket = s_part + 16;
+    KeyT* const s_key = reinterpret_cast<KeyT*>(s_ticket + 4);  // [TILE] the tile in sorted order
     uint32_t* const s_val = s_raw;
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
-    for (int i = tid; i < kSortWarps * kBins; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
-    for (int i = tid; i < kMaskWords; i += kSortThreads) s_raw[i] = 0;
-    const uint32_t ghist = __ldg(hist + tid);                              // items of digit `tid` in the whole array
+    const bool owner = tid < kBins;                             // thread `tid` owns digit `tid`
+    if (tid == 0) *s_ticket = atomicAdd(ticket_ctr, 1u);
+    for (int i = tid; i < WARPS * kBins; i += THREADS) s_cnt[i] = 0;
+    for (int i = tid; i < L::kMaskWords; i += THREADS) s_raw[i] = 0;
+    const uint32_t ghist = owner ? __ldg(hist + tid) : 0u;      // items of digit `tid` in the whole array
     const uint32_t n = count_ptr ? min(__ldg(count_ptr), cap) : cap;
     __syncthreads();
-    const uint32_t ticket = s_ticket;
+    const uint32_t ticket = *s_ticket;
     if ((uint64_t)ticket * TILE >= n) return;
     const uint32_t tile_base = ticket * TILE;
     const uint32_t warp_base = tile_base + warp * (32 * ITEMS) + lane;
@@ -149,20 +169,21 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
     }
     // rank inside the warp (two mask arrays, alternating: the clear of round i cannot meet the ORs of round i + 1)
     const uint32_t lane_bit = 1u << lane, lt = lane_bit - 1u;
+    uint32_t* const my_cnt = s_cnt + warp * kBins;
     auto rank_rounds = [&](auto all_c) {
         constexpr bool ALL = decltype(all_c)::value;
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const bool ok = ALL || ((valid >> i) & 1u);
             const uint32_t d = (key[i] >> shift) & 255u;
-            uint32_t* const mask = s_raw + ((i & 1) * kSortWarps + warp) * kBins + d;
+            uint32_t* const mask = s_raw + ((i & 1) * WARPS + warp) * kBins + d;
             if (ok) atomicOr(mask, lane_bit);
             __syncwarp();
             const uint32_t peers = ok ? *mask : 0u;
-            const uint32_t before = s_cnt[warp][d];
+            const uint32_t before = my_cnt[d];
             __syncwarp();
             if (ok && (peers & lt) == 0u) {                 // the lowest lane of the group
-                s_cnt[warp][d] = before + __popc(peers);
+                my_cnt[d] = before + __popc(peers);
                 *mask = 0u;
             }
             pos[i] = before + __popc(peers & lt);
@@ -170,17 +191,19 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
     };
     if (all_valid) rank_rounds(std::true_type{}); else rank_rounds(std::false_type{});
     __syncthreads();
-    // thread `tid` owns digit `tid`: exclusive offsets of the warps, the tile's count
+    // exclusive offsets of the warps, the tile's count of the digit
     uint32_t cnt = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; w++) {
-        const uint32_t c = s_cnt[w][tid];
-        s_cnt[w][tid] = cnt;
-        cnt += c;
-    }
-    // publish as early as possible: the tiles behind wait for this
     uint32_t* const my_status = status + (size_t)ticket * kBins + tid;
-    st_status(my_status, (ticket == 0 ? kFlagPrefix : kFlagAgg) | cnt);
+    if (owner) {
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const uint32_t c = s_cnt[w * kBins + tid];
+            s_cnt[w * kBins + tid] = cnt;
+            cnt += c;
+        }
+        // publish as early as possible: the tiles behind wait for this
+        st_status(my_status, (ticket == 0 ? kFlagPrefix : kFlagAgg) | cnt);
+    }
     // exclusive scans over the digits: position of the digit inside the sorted tile / inside the whole output
     uint32_t ia = cnt, ib = ghist;
 #pragma unroll
@@ -188,47 +211,48 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
         const uint32_t ta = __shfl_up_sync(full, ia, d), tb = __shfl_up_sync(full, ib, d);
         if (lane >= d) { ia += ta; ib += tb; }
     }
-    if (lane == 31) { s_part[0][warp] = ia; s_part[1][warp] = ib; }
+    if (owner && lane == 31) { s_part[warp] = ia; s_part[8 + warp] = ib; }
     __syncthreads();
     uint32_t wa = 0, wb = 0, n_tile = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) {
-        const uint32_t a = s_part[0][w], b = s_part[1][w];
+    for (int w = 0; w < 8; w++) {
+        const uint32_t a = s_part[w], b = s_part[8 + w];
         if (w < warp) { wa += a; wb += b; }
         n_tile += a;
     }
-    const uint32_t tile_start = wa + ia - cnt;      // first position of digit `tid` in the sorted tile
-    const uint32_t glob_start = wb + ib - ghist;    // first position of digit `tid` in the output
-    // chained look-back: items of digit `tid` in all earlier tiles
-    // (kWindow independent loads in flight per step)
-    uint32_t prefix = 0;
-    if (ticket != 0) {
-        constexpr int kWindow = EX_SORT_WINDOW;
-        int t = (int)ticket - 1, spins = 0;
-        bool done = false;
-        while (!done) {
-            uint32_t v[kWindow];
+    if (owner) {
+        const uint32_t tile_start = wa + ia - cnt;      // first position of digit `tid` in the sorted tile
+        const uint32_t glob_start = wb + ib - ghist;    // first position of digit `tid` in the output
+        // chained look-back: items of digit `tid` in all earlier tiles (kWindow independent loads in flight per step)
+        uint32_t prefix = 0;
+        if (ticket != 0) {
+            constexpr int kWindow = EX_SORT_WINDOW;
+            int t = (int)ticket - 1, spins = 0;
+            bool done = false;
+            while (!done) {
+                uint32_t v[kWindow];
 #pragma unroll
-            for (int k = 0; k < kWindow; k++) v[k] = t - k >= 0 ? ld_status(status + (size_t)(t - k) * kBins + tid) : kFlagPrefix;
+                for (int k = 0; k < kWindow; k++) v[k] = t - k >= 0 ? ld_status(status + (size_t)(t - k) * kBins + tid) : kFlagPrefix;
 #pragma unroll
-            for (int k = 0; k < kWindow; k++) {
-                if (!done) {
-                    const uint32_t f = v[k] & kFlagMask;
-                    if (f == 0) {                    // not published yet: read again from here
-                        if (++spins > kSpinLimit) { atomicOr(err, 1u); done = true; }
-                        break;
+                for (int k = 0; k < kWindow; k++) {
+                    if (!done) {
+                        const uint32_t f = v[k] & kFlagMask;
+                        if (f == 0) {                    // not published yet: read again from here
+                            if (++spins > kSpinLimit) { atomicOr(err, 1u); done = true; }
+                            break;
+                        }
+                        prefix += v[k] & kValMask;
+                        --t;
+                        if (f == kFlagPrefix) done = true;
                     }
-                    prefix += v[k] & kValMask;
-                    --t;
-                    if (f == kFlagPrefix) done = true;
                 }
             }
+            st_status(my_status, kFlagPrefix | ((prefix + cnt) & kValMask));
         }
-        st_status(my_status, kFlagPrefix | ((prefix + cnt) & kValMask));
-    }
-    s_delta[tid] = glob_start + prefix - tile_start;
+        s_delta[tid] = glob_start + prefix - tile_start;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) s_cnt[w][tid] += tile_start;
+        for (int w = 0; w < WARPS; w++) s_cnt[w * kBins + tid] += tile_start;
+    }
     __syncthreads();
     // scatter into the sorted tile (the values are fetched only now: fewer live registers while ranking) ...
 #pragma unroll
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
         if ((valid >> i) & 1u) {
             const uint32_t idx = warp_base + i * 32;
             const uint32_t d = (key[i] >> shift) & 255u;
-            const uint32_t lp = s_cnt[warp][d] + pos[i];
+            const uint32_t lp = my_cnt[d] + pos[i];
             s_key[lp] = (KeyT)key[i];
             s_val[lp] = FIRST ? idx : __ldg(vals_in + idx);
         }
@@ -245,7 +269,7 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
     // ... and from there to the output: consecutive threads write consecutive addresses within a digit
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-        const uint32_t p = i * kSortThreads + tid;
+        const uint32_t p = i * THREADS + tid;
         if (p < n_tile) {
             const KeyT k = s_key[p];
             const uint32_t g = s_delta[((uint32_t)k >> shift) & 255u] + p;
@@ -257,6 +281,28 @@ __global__ void __launch_bounds__(kSortThreads, EX_SORT_MINBLOCKS) radix_pass_ke
     }
 }
 
+template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool FIRST, bool WRITE_KEYS>
+cudaError_t launch_pass(int grid, cudaStream_t s, const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
+                        const uint32_t* count_ptr, uint32_t cap, int shift, const uint32_t* hist, uint32_t* status, uint32_t* ticket,
+                        uint32_t* err, const uint32_t* side_src = nullptr, uint32_t* side_out = nullptr)
+{
+    constexpr size_t bytes = PassSmem<KeyT, THREADS, ITEMS>::kBytes;
+    auto kernel = radix_pass_kernel<KeyT, THREADS, ITEMS, MINBLOCKS, FIRST, WRITE_KEYS>;
+    if (bytes > 48 * 1024) {
+        // once per device: a new device (or thread) simply sets the attribute again
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_dev != dev) {
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return e;
+            configured_dev = dev;
+        }
+    }
+    kernel<<<grid, THREADS, bytes, s>>>(keys_in, vals_in, keys_out, vals_out, count_ptr, cap, shift, hist, status, ticket, err, side_src, side_out);
+    return cudaSuccess;
+}
+
 // Sums of tiles_touched (in depth order) over 32 / 256 / 16384 consecutive Gaussians and their total R: with them a
 // warp of the duplicate kernel finds its first output position from < 100 words (rasterizer_impl.cu:295 runs an
 // inclusive scan over all P Gaussians).
@@ -264,23 +310,39 @@ __global__ void __launch_bounds__(256) touched_sums_kernel(const uint32_t* __res
                                                            uint32_t* __restrict__ warp_sum, uint32_t* __restrict__ block_sum,
                                                            uint32_t* __restrict__ super_sum, uint32_t* __restrict__ total)
 {
-    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_w[8][8];          // [256-block of this CTA][warp]
     const uint32_t n_vis = __ldg(n_vis_ptr);
-    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
-    if (blockIdx.x * 256u >= n_vis) return;
-    const uint32_t w = __reduce_add_sync(0xffffffffu, j < n_vis ? touched_in_order[j] : 0u);
-    if ((threadIdx.x & 31) == 0) {
-        warp_sum[j >> 5] = w;
-        s_w[threadIdx.x >> 5] = w;
+    const uint32_t base = blockIdx.x * 2048u;
+    if (base >= n_vis) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t j = base + i * 256u + threadIdx.x;
+        v[i] = j < n_vis ? touched_in_order[j] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t j = base + i * 256u + threadIdx.x;
+        const uint32_t w = __reduce_add_sync(0xffffffffu, v[i]);
+        if (lane == 0) {
+            if ((j & ~31u) < n_vis) warp_sum[j >> 5] = w;
+            s_w[i][warp] = w;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         uint32_t b = 0;
+        if (lane < 8) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) b += s_w[k];
-        block_sum[blockIdx.x] = b;
-        atomicAdd(super_sum + (blockIdx.x >> 6), b);
-        atomicAdd(total, b);
+            for (int k = 0; k < 8; k++) b += s_w[lane][k];
+            if (base + lane * 256u < n_vis) block_sum[blockIdx.x * 8 + lane] = b;
+        }
+        b = __reduce_add_sync(0xffffffffu, b);
+        if (lane == 0) {
+            atomicAdd(super_sum + (blockIdx.x >> 3), b);
+            atomicAdd(total, b);
+        }
     }
 }
 
@@ -461,8 +523,8 @@ uint32_t higher_msb(uint32_t n)
 //   block_sum[ceil(P / 256)], warp_sum[ceil(P / 32)]
 namespace {
 constexpr int kDepthPasses = 4;
-constexpr int kDepthTile = kSortThreads * EX_SORT_ITEMS_DEPTH;
-constexpr int kTileTile = kSortThreads * EX_SORT_ITEMS_TILE;
+constexpr int kDepthTile = EX_SORT_THREADS_DEPTH * EX_SORT_ITEMS_DEPTH;
+constexpr int kTileTile = EX_SORT_THREADS_TILE * EX_SORT_ITEMS_TILE;
 
 struct SortScratch {
     uint32_t *hist, *super_sum, *depth_status, *block_sum, *warp_sum;
@@ -515,22 +577,26 @@ cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s)
     const SortScratch sc = sort_scratch(g.temp, P);
     uint32_t* const n_vis = g.meta + EX_META_NVIS;
     uint32_t* const err = g.meta + EX_META_ERROR;
-    radix_hist_kernel<uint32_t, kDepthPasses, true><<<148 * 3, 512, 0, s>>>(g.key_in, nullptr, (uint32_t)P, sc.hist, n_vis);
+    radix_hist_kernel<uint32_t, kDepthPasses, true><<<148, 1024, 0, s>>>(g.key_in, nullptr, (uint32_t)P, sc.hist, n_vis);
     const int grid = (int)sc.depth_tiles;
     // ping-pong between (key_a, val_a) and (key_b, order): the last pass leaves the ids in `order`, writes no keys and
-    // gathers tiles_touched into key_b (depth order) for the duplicate kernel's scan
-    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, true, true><<<grid, kSortThreads, 0, s>>>(
-        g.key_in, nullptr, g.key_a, g.val_a, nullptr, (uint32_t)P, 0, sc.hist, sc.depth_status, g.meta + EX_META_TICKETS + 0, err, nullptr, nullptr);
-    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, true><<<grid, kSortThreads, 0, s>>>(
-        g.key_a, g.val_a, g.key_b, g.order, n_vis, (uint32_t)P, 8, sc.hist + kBins, sc.depth_status + sc.depth_tiles * kBins,
-        g.meta + EX_META_TICKETS + 1, err, nullptr, nullptr);
-    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, true><<<grid, kSortThreads, 0, s>>>(
-        g.key_b, g.order, g.key_a, g.val_a, n_vis, (uint32_t)P, 16, sc.hist + 2 * kBins, sc.depth_status + 2 * sc.depth_tiles * kBins,
-        g.meta + EX_META_TICKETS + 2, err, nullptr, nullptr);
-    radix_pass_kernel<uint32_t, EX_SORT_ITEMS_DEPTH, false, false><<<grid, kSortThreads, 0, s>>>(
-        g.key_a, g.val_a, nullptr, g.order, n_vis, (uint32_t)P, 24, sc.hist + 3 * kBins, sc.depth_status + 3 * sc.depth_tiles * kBins,
-        g.meta + EX_META_TICKETS + 3, err, g.tiles_touched, g.key_b);
-    touched_sums_kernel<<<(P + 255) / 256, 256, 0, s>>>(n_vis, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.meta + EX_META_TOTAL);
+    // gathers tiles_touched into key_b (depth order) for the duplicate kernel
+    constexpr int T = EX_SORT_THREADS_DEPTH, I = EX_SORT_ITEMS_DEPTH, M = EX_SORT_MINBLOCKS_DEPTH;
+    const size_t st = sc.depth_tiles * kBins;
+    uint32_t* const tk = g.meta + EX_META_TICKETS;
+    cudaError_t e = launch_pass<uint32_t, T, I, M, true, true>(grid, s, g.key_in, nullptr, g.key_a, g.val_a, nullptr, (uint32_t)P, 0,
+                                                               sc.hist, sc.depth_status, tk + 0, err);
+    if (e == cudaSuccess)
+        e = launch_pass<uint32_t, T, I, M, false, true>(grid, s, g.key_a, g.val_a, g.key_b, g.order, n_vis, (uint32_t)P, 8,
+                                                        sc.hist + kBins, sc.depth_status + st, tk + 1, err);
+    if (e == cudaSuccess)
+        e = launch_pass<uint32_t, T, I, M, false, true>(grid, s, g.key_b, g.order, g.key_a, g.val_a, n_vis, (uint32_t)P, 16,
+                                                        sc.hist + 2 * kBins, sc.depth_status + 2 * st, tk + 2, err);
+    if (e == cudaSuccess)
+        e = launch_pass<uint32_t, T, I, M, false, false>(grid, s, g.key_a, g.val_a, nullptr, g.order, n_vis, (uint32_t)P, 24,
+                                                         sc.hist + 3 * kBins, sc.depth_status + 3 * st, tk + 3, err, g.tiles_touched, g.key_b);
+    if (e != cudaSuccess) return e;
+    touched_sums_kernel<<<(P + 2047) / 2048, 256, 0, s>>>(n_vis, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.meta + EX_META_TOTAL);
     return cudaGetLastError();
 }
 
@@ -574,17 +640,21 @@ cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, c
     const int src = passes & 1;
     const int grid = (cap + kTileTile - 1) / kTileTile;
     const size_t st = (size_t)grid * kBins;
+    constexpr int T = EX_SORT_THREADS_TILE, I = EX_SORT_ITEMS_TILE, M = EX_SORT_MINBLOCKS_TILE;
+    uint32_t* const tk = g.meta + EX_META_TICKETS;
     if (passes == 2) {
-        radix_hist_kernel<uint16_t, 2, false><<<148 * 3, 512, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
-            b.tile[0], b.val[0], b.tile[1], b.val[1], total, (uint32_t)cap, 0, sc.hist + 4 * kBins, b.status, g.meta + EX_META_TICKETS + 5, err, nullptr, nullptr);
-        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
-            b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 8, sc.hist + 5 * kBins, b.status + st, g.meta + EX_META_TICKETS + 6, err, nullptr, nullptr);
+        radix_hist_kernel<uint16_t, 2, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
+        e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[0], b.val[0], b.tile[1], b.val[1], total, (uint32_t)cap, 0,
+                                                        sc.hist + 4 * kBins, b.status, tk + 5, err);
+        if (e == cudaSuccess)
+            e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 8,
+                                                            sc.hist + 5 * kBins, b.status + st, tk + 6, err);
     } else {
-        radix_hist_kernel<uint16_t, 1, false><<<148 * 3, 512, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-        radix_pass_kernel<uint16_t, EX_SORT_ITEMS_TILE, false, true><<<grid, kSortThreads, 0, s>>>(
-            b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 0, sc.hist + 4 * kBins, b.status, g.meta + EX_META_TICKETS + 5, err, nullptr, nullptr);
+        radix_hist_kernel<uint16_t, 1, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
+        e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 0,
+                                                        sc.hist + 4 * kBins, b.status, tk + 5, err);
     }
+    if (e != cudaSuccess) return e;
     const int groups = (cap + 7) / 8;
     tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(total, (uint32_t)cap, b.tile[0], img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu, err);
     return cudaGetLastError();
