@@ -35,6 +35,12 @@ class RAdamTensor(C.Structure):
                 ("numel", C.c_size_t), ("lr", C.c_double), ("step", C.c_longlong)]
 
 
+class GatherJob(C.Structure):
+    """ex4dgs_gather_job (include/ex4dgs_raster.h)."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("dst", C.c_void_p), ("index", C.c_void_p),
+                ("row_bytes", C.c_size_t), ("n_a", C.c_longlong), ("n_out", C.c_longlong)]
+
+
 class StatsArrays(C.Structure):
     """ex4dgs_stats_arrays (include/ex4dgs_raster.h)."""
     _fields_ = [(n, C.c_void_p) for n in ("max_radii2D", "min_radii2D", "xyz_gradient_accum", "denom", "error_accum",
@@ -96,6 +102,7 @@ SIGNATURES = {
                                       _P]),
     "ex4dgs_radam_step": (_I, [C.POINTER(RAdamTensor), _I, _D, _D, _D, _D, _P]),
     "ex4dgs_radam_step_ex": (_I, [C.POINTER(RAdamTensor), _I, _D, _D, _D, _D, C.c_uint, C.c_uint, _P, _P]),
+    "ex4dgs_gather_rows": (_I, [C.POINTER(GatherJob), _I, _P]),
     "ex4dgs_radam_scalars": (_I, [_D, C.c_longlong, _D, _D, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
     "ex4dgs_iteration_stats": (_I, [_I, _I, _P, _P, _P, _F, _I, C.POINTER(StatsArrays), C.POINTER(StatsArrays), _P]),
     "ex4dgs_regularizer_scratch_bytes": (C.c_size_t, []),

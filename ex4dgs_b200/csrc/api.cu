@@ -662,6 +662,32 @@ int ex4dgs_radam_step(const ex4dgs_radam_tensor* tensors, int n, double beta1, d
     return ex4dgs_radam_step_ex(tensors, n, beta1, beta2, eps, grad_scale, 0u, 0u, nullptr, stream);
 }
 
+int ex4dgs_gather_rows(const ex4dgs_gather_job* jobs, int n, void* stream)
+{
+    g_err[0] = 0;
+    if (n < 0 || n > EX4DGS_GATHER_MAX_JOBS || (n > 0 && !jobs))
+        return fail(EX4DGS_ERR_INVALID, "gather_rows: n=%d outside [0, %d]", n, EX4DGS_GATHER_MAX_JOBS);
+    GatherJob d[EX_GATHER_MAX_JOBS];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const ex4dgs_gather_job& j = jobs[i];
+        if (j.n_out == 0) continue;
+        if (j.n_out < 0 || j.n_a < 0 || j.n_a > j.n_out || j.n_out > 0xFFFFFFFFLL)
+            return fail(EX4DGS_ERR_INVALID, "gather_rows: job %d has n_a=%lld n_out=%lld", i, j.n_a, j.n_out);
+        if (j.row_bytes == 0 || (j.row_bytes & 3) != 0 || j.row_bytes > 0x3FFFFFFCu)
+            return fail(EX4DGS_ERR_INVALID, "gather_rows: job %d row_bytes=%zu (must be a positive multiple of 4)", i, j.row_bytes);
+        if (!j.dst || (j.n_a > 0 && !j.a)) return fail(EX4DGS_ERR_INVALID, "gather_rows: job %d has a NULL pointer", i);
+        if (((uintptr_t)j.a | (uintptr_t)j.b | (uintptr_t)j.dst) & 3) return fail(EX4DGS_ERR_INVALID, "gather_rows: job %d is not 4-byte aligned", i);
+        d[m].a = (const uint32_t*)j.a; d[m].b = (const uint32_t*)j.b; d[m].dst = (uint32_t*)j.dst; d[m].index = j.index;
+        d[m].words = (unsigned)(j.row_bytes / 4); d[m].n_a = (unsigned)j.n_a; d[m].n_out = (unsigned)j.n_out; d[m].vec4 = 0;
+        m++;
+    }
+    cudaError_t e = launch_gather_rows(d, m, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(EX4DGS_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(e));
+    if (m > 0) g_launches += 1;
+    return EX4DGS_OK;
+}
+
 size_t ex4dgs_l1_scratch_bytes(void) { return l1_scratch_bytes(); }
 
 int ex4dgs_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out_loss, void* stream)

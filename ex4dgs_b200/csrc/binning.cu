@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(1024) radix_hist_kernel(const KeyT* __restrict
 // not depend on the order in which the hardware serialises conflicting lanes - and read the mask of their digit back:
 // lanes with the same digit, 12 instructions per key.  (MATCH.ANY resolves one group of equal values per iteration:
 // ~200 cycles on 32 distinct digits, 30 us of an 86 us tile pass; nine ballots + bit logic cost 45 instructions.)
-// FIRST: the values are the indices, keys equal to EX_INVISIBLE_KEY are dropped (`hist` does not count them).
+// DROP: keys equal to the all-ones key (EX_INVISIBLE_KEY / the dump tile 0xFFFF) are dropped (`hist` does not count them:
+// `count_ptr` items in, fewer out).  IOTA: the values are the indices themselves.
 // !WRITE_KEYS (last pass of a sort whose keys are not needed afterwards): side_out[g] = side_src[value] rides along.
 template <typename KeyT, int THREADS, int ITEMS>
 struct PassSmem {
@@ -125,7 +126,7 @@ struct PassSmem {
     static constexpr size_t kBytes = sizeof(uint32_t) * (WARPS * kBins + kRawWords + kBins + 16 + 4) + sizeof(KeyT) * TILE;
 };
 
-template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool FIRST, bool WRITE_KEYS>
+template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool DROP, bool IOTA, bool WRITE_KEYS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ count_ptr, uint32_t cap, int shift,
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
     if ((uint64_t)ticket * TILE >= n) return;
     const uint32_t tile_base = ticket * TILE;
     const uint32_t warp_base = tile_base + warp * (32 * ITEMS) + lane;
-    const bool all_valid = !FIRST && (uint64_t)tile_base + TILE <= n;
+    const bool all_valid = !DROP && (uint64_t)tile_base + TILE <= n;
 
     uint32_t key[ITEMS], pos[ITEMS];
     uint32_t valid = 0;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
         const uint32_t idx = warp_base + i * 32;
         bool ok = all_valid || idx < n;
         key[i] = ok ? (uint32_t)__ldg(keys_in + idx) : 0u;
-        if (FIRST) ok = ok && key[i] != EX_INVISIBLE_KEY;
+        if (DROP) ok = ok && key[i] != (uint32_t)(KeyT)EX_INVISIBLE_KEY;
         valid |= (ok ? 1u : 0u) << i;
     }
     // rank inside the warp (two mask arrays, alternating: the clear of round i cannot meet the ORs of round i + 1)
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
             const uint32_t d = (key[i] >> shift) & 255u;
             const uint32_t lp = my_cnt[d] + pos[i];
             s_key[lp] = (KeyT)key[i];
-            s_val[lp] = FIRST ? idx : __ldg(vals_in + idx);
+            s_val[lp] = IOTA ? idx : __ldg(vals_in + idx);
         }
     }
     __syncthreads();
@@ -281,13 +282,13 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) radix_pass_kernel(
     }
 }
 
-template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool FIRST, bool WRITE_KEYS>
+template <typename KeyT, int THREADS, int ITEMS, int MINBLOCKS, bool DROP, bool IOTA, bool WRITE_KEYS>
 cudaError_t launch_pass(int grid, cudaStream_t s, const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
                         const uint32_t* count_ptr, uint32_t cap, int shift, const uint32_t* hist, uint32_t* status, uint32_t* ticket,
                         uint32_t* err, const uint32_t* side_src = nullptr, uint32_t* side_out = nullptr)
 {
     constexpr size_t bytes = PassSmem<KeyT, THREADS, ITEMS>::kBytes;
-    auto kernel = radix_pass_kernel<KeyT, THREADS, ITEMS, MINBLOCKS, FIRST, WRITE_KEYS>;
+    auto kernel = radix_pass_kernel<KeyT, THREADS, ITEMS, MINBLOCKS, DROP, IOTA, WRITE_KEYS>;
     if (bytes > 48 * 1024) {
         // once per device: a new device (or thread) simply sets the attribute again
         static thread_local int configured_dev = -1;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* 
             keep = !(cull && cull_test(s_ctx[warp][src], tx, ty, pad));
         }
         // culled instances keep their slot (the count is the full rectangle) but are keyed to
-        // the dump tile 0xFFFF, which the stable tile sort moves behind every real tile
+        // the dump tile 0xFFFF, which the first pass of the tile sort drops
         if (item < total && wbase + item < cap) {      // cap: capacity of the buffer, sized before R is known (api.cu)
             tile_out[wbase + item] = keep ? tile : (uint16_t)0xFFFF;
             val_out[wbase + item] = idv;
@@ -437,14 +438,14 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* 
 }
 
 // ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
-// eight 16-bit keys per thread from one 128-bit load.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ total_ptr, uint32_t cap, const uint16_t* __restrict__ tiles,
-                                                          uint2* __restrict__ ranges, uint32_t dump, uint32_t* __restrict__ err)
+// eight 16-bit keys per thread from one 128-bit load.  `listed` = entries of the sorted list (the instances the exact
+// tile test kept, at most the buffer's capacity), `total` = R.
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ listed_ptr, const uint32_t* __restrict__ total_ptr, uint32_t cap,
+                                                          const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges, uint32_t* __restrict__ err)
 {
-    const uint32_t total = __ldg(total_ptr);
-    const int L = (int)min(total, cap);
+    const int L = (int)min(__ldg(listed_ptr), cap);
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0 && total > cap) atomicOr(err, 2u);      // the lists are truncated (EX4DGS_FLAG_NO_HOST_WAIT: nobody else notices)
+    if (g == 0 && __ldg(total_ptr) > cap) atomicOr(err, 2u);      // the lists are truncated (EX4DGS_FLAG_NO_HOST_WAIT: nobody else notices)
     const int base = g * 8;
     if (base >= L) return;
     uint16_t t[8];
@@ -462,12 +463,12 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
         if (idx < L) {
             const uint32_t cur = t[k];
             if (idx == 0) {
-                if (cur != dump) ranges[cur].x = 0;
+                ranges[cur].x = 0;
             } else if (cur != prev) {
-                ranges[prev].y = idx;                 // prev is never the dump tile (it sorts last)
-                if (cur != dump) ranges[cur].x = idx;
+                ranges[prev].y = idx;
+                ranges[cur].x = idx;
             }
-            if (idx == L - 1 && cur != dump) ranges[cur].y = L;
+            if (idx == L - 1) ranges[cur].y = L;
             prev = cur;
         }
     }
@@ -548,8 +549,9 @@ SortScratch sort_scratch(char* base, int P)
 }
 int tile_sort_passes(int grid_x, int grid_y, unsigned flags)
 {
+    (void)flags;                                          // the dump tile 0xFFFF is dropped by the first pass: it needs no bits
     const int bit = (int)higher_msb((uint32_t)(grid_x * grid_y));
-    return ((flags & 1u) != 0 || bit > 8) ? 2 : 1;        // with culling the dump tile 0xFFFF needs all 16 bits
+    return bit > 8 ? 2 : 1;
 }
 }  // namespace
 
@@ -584,16 +586,16 @@ cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s)
     constexpr int T = EX_SORT_THREADS_DEPTH, I = EX_SORT_ITEMS_DEPTH, M = EX_SORT_MINBLOCKS_DEPTH;
     const size_t st = sc.depth_tiles * kBins;
     uint32_t* const tk = g.meta + EX_META_TICKETS;
-    cudaError_t e = launch_pass<uint32_t, T, I, M, true, true>(grid, s, g.key_in, nullptr, g.key_a, g.val_a, nullptr, (uint32_t)P, 0,
+    cudaError_t e = launch_pass<uint32_t, T, I, M, true, true, true>(grid, s, g.key_in, nullptr, g.key_a, g.val_a, nullptr, (uint32_t)P, 0,
                                                                sc.hist, sc.depth_status, tk + 0, err);
     if (e == cudaSuccess)
-        e = launch_pass<uint32_t, T, I, M, false, true>(grid, s, g.key_a, g.val_a, g.key_b, g.order, n_vis, (uint32_t)P, 8,
+        e = launch_pass<uint32_t, T, I, M, false, false, true>(grid, s, g.key_a, g.val_a, g.key_b, g.order, n_vis, (uint32_t)P, 8,
                                                         sc.hist + kBins, sc.depth_status + st, tk + 1, err);
     if (e == cudaSuccess)
-        e = launch_pass<uint32_t, T, I, M, false, true>(grid, s, g.key_b, g.order, g.key_a, g.val_a, n_vis, (uint32_t)P, 16,
+        e = launch_pass<uint32_t, T, I, M, false, false, true>(grid, s, g.key_b, g.order, g.key_a, g.val_a, n_vis, (uint32_t)P, 16,
                                                         sc.hist + 2 * kBins, sc.depth_status + 2 * st, tk + 2, err);
     if (e == cudaSuccess)
-        e = launch_pass<uint32_t, T, I, M, false, false>(grid, s, g.key_a, g.val_a, nullptr, g.order, n_vis, (uint32_t)P, 24,
+        e = launch_pass<uint32_t, T, I, M, false, false, false>(grid, s, g.key_a, g.val_a, nullptr, g.order, n_vis, (uint32_t)P, 24,
                                                          sc.hist + 3 * kBins, sc.depth_status + 3 * st, tk + 3, err, g.tiles_touched, g.key_b);
     if (e != cudaSuccess) return e;
     touched_sums_kernel<<<(P + 2047) / 2048, 256, 0, s>>>(n_vis, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.meta + EX_META_TOTAL);
@@ -605,6 +607,7 @@ cudaError_t binning_reset_instances(const GeometryState& g, int P, cudaStream_t 
 {
     const SortScratch sc = sort_scratch(g.temp, P);
     cudaError_t e = cudaMemsetAsync(g.meta + EX_META_TICKETS + 5, 0, 2 * sizeof(uint32_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.meta + EX_META_LISTED, 0, sizeof(uint32_t), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(sc.hist + 4 * kBins, 0, 2 * kBins * sizeof(uint32_t), s);
     return e;
 }
@@ -636,26 +639,33 @@ cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, c
     const uint32_t* const total = g.meta + EX_META_TOTAL;
     uint32_t* const err = g.meta + EX_META_ERROR;
     const bool cull = (flags & 1u) != 0;
+    // entries of the sorted list: with the exact tile test, what the histogram kernel counted (it skips the dump tile)
+    const uint32_t* const listed = cull ? g.meta + EX_META_LISTED : total;
     const int passes = tile_sort_passes(grid_x, grid_y, flags);
-    const int src = passes & 1;
     const int grid = (cap + kTileTile - 1) / kTileTile;
     const size_t st = (size_t)grid * kBins;
     constexpr int T = EX_SORT_THREADS_TILE, I = EX_SORT_ITEMS_TILE, M = EX_SORT_MINBLOCKS_TILE;
     uint32_t* const tk = g.meta + EX_META_TICKETS;
-    if (passes == 2) {
-        radix_hist_kernel<uint16_t, 2, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-        e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[0], b.val[0], b.tile[1], b.val[1], total, (uint32_t)cap, 0,
-                                                        sc.hist + 4 * kBins, b.status, tk + 5, err);
-        if (e == cudaSuccess)
-            e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 8,
-                                                            sc.hist + 5 * kBins, b.status + st, tk + 6, err);
+    // the first pass reads the min(R, cap) emitted pairs and (exact tile culling) drops the dump-tile ones on the fly
+    const int src = passes & 1, dst = src ^ 1;
+    if (cull) {
+        if (passes == 2) radix_hist_kernel<uint16_t, 2, true><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, g.meta + EX_META_LISTED);
+        else radix_hist_kernel<uint16_t, 1, true><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, g.meta + EX_META_LISTED);
     } else {
-        radix_hist_kernel<uint16_t, 1, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-        e = launch_pass<uint16_t, T, I, M, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], total, (uint32_t)cap, 0,
-                                                        sc.hist + 4 * kBins, b.status, tk + 5, err);
+        if (passes == 2) radix_hist_kernel<uint16_t, 2, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
+        else radix_hist_kernel<uint16_t, 1, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
     }
+    if (cull)
+        e = launch_pass<uint16_t, T, I, M, true, false, true>(grid, s, b.tile[src], b.val[src], b.tile[dst], b.val[dst], total, (uint32_t)cap, 0,
+                                                              sc.hist + 4 * kBins, b.status, tk + 5, err);
+    else
+        e = launch_pass<uint16_t, T, I, M, false, false, true>(grid, s, b.tile[src], b.val[src], b.tile[dst], b.val[dst], total, (uint32_t)cap, 0,
+                                                               sc.hist + 4 * kBins, b.status, tk + 5, err);
+    if (e == cudaSuccess && passes == 2)
+        e = launch_pass<uint16_t, T, I, M, false, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], listed, (uint32_t)cap, 8,
+                                                               sc.hist + 5 * kBins, b.status + st, tk + 6, err);
     if (e != cudaSuccess) return e;
     const int groups = (cap + 7) / 8;
-    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(total, (uint32_t)cap, b.tile[0], img.ranges, cull ? 0xFFFFu : 0xFFFFFFFFu, err);
+    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(listed, total, (uint32_t)cap, b.tile[0], img.ranges, err);
     return cudaGetLastError();
 }

@@ -114,6 +114,7 @@ struct Carver {
 #define EX_META_NVIS 3       // visible Gaussians (depth histogram kernel)
 #define EX_META_TOTAL 4      // R: (Gaussian, tile) instances (touched_sums_kernel)
 #define EX_META_ERROR 5      // bit 0: a look-back did not complete; bit 1: more instances than the binning buffer holds
+#define EX_META_LISTED 6     // entries of the sorted (tile, id) list with exact tile culling: instances the test kept, at most the capacity (tile histogram kernel)
 #define EX_META_TICKETS 8    // [0..3] depth passes, [5..6] tile passes
 
 struct GeometryState {
@@ -287,6 +288,18 @@ struct RAdamTensorDesc {
 };
 cudaError_t launch_radam(const RAdamTensorDesc* tensors, int n, double beta1, double beta2, double eps, double grad_scale,
                          int* nan_flags, cudaStream_t s);
+
+// row gathers of densification / pruning (compact.cu)
+#define EX_GATHER_MAX_JOBS 64
+struct GatherJob {            // dst[r] = r < n_a ? a[index ? index[r] : r] : (b ? b[r - n_a] : 0),  r in [0, n_out), rows of `words` 4-byte words
+    const uint32_t* a;
+    const uint32_t* b;
+    uint32_t* dst;
+    const long long* index;
+    unsigned words, n_a, n_out;
+    int vec4;                 // 128-bit accesses possible (filled by the launcher)
+};
+cudaError_t launch_gather_rows(const GatherJob* jobs, int n, cudaStream_t s);
 
 size_t l1_scratch_bytes();
 cudaError_t launch_l1_forward(size_t n, const float* a, const float* b, char* scratch, float* out, cudaStream_t s);

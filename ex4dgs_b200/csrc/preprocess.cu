@@ -627,18 +627,22 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
 
 // ---------------------------------------------------------------------------------------------
 // Same math, B200 memory layout: 128 Gaussians per CTA, every [P,3] / [P,16,3] tensor crosses
-// HBM with fully coalesced 128-bit accesses through a shared-memory staging area (rows padded to
-// 49 floats: conflict-free for the per-thread row accesses), the 192-byte SH row is read and its
-// gradient written in place in that staging area (no 48+48 register arrays -> 3x the occupancy).
+// HBM with fully coalesced 128-bit accesses through a shared-memory staging area, the 192-byte SH
+// row is read and its gradient written in place there (no 48+48 register arrays -> 3x the occupancy).
+// Contiguous SH ([P,16,3]): the block's rows are requested with 16-byte cp.async (LDGSTS: no register
+// staging, all twelve requests of a thread in flight at once) into rows padded to 52 floats - 16-byte
+// aligned, and 13 float4 per row is odd, so the per-thread LDS.128 / STS.128 of the compute phase are
+// conflict-free - and everything that does not need the row (accumulator line, conic -> cov3D ->
+// scale / rotation, mean2D -> mean3D) runs while they are in flight.
 // Handles M == 16 (degree-3 layout) and M == 0 (precomputed colours); other M use the kernel above.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBT = 128;        // threads = Gaussians per CTA
-constexpr int kRow = 49;        // padded SH row (floats)
+constexpr int kRow = 52;        // padded SH row (floats)
 
 template <bool SEG>
 __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __grid_constant__ PreprocessBwdParams p)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* s_cam = smem;                       // 36 (+4 pad)
     float* s_o3 = smem + 40;                   // 5 x [kBT*3]: mean2D, color, dir, mean3D, scale
     float* s_sh = s_o3 + 5 * kBT * 3;          // [kBT][kRow]   (only when M == 16)
@@ -668,10 +672,8 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
             const float* rs = p.seg.rest[seg_i] + seg_li0 * 45;
             const int nd = nvalid * 3, nr = nvalid * 45;
             if (((reinterpret_cast<uintptr_t>(dc) | reinterpret_cast<uintptr_t>(rs)) & 15) == 0 && (nvalid & 3) == 0) {
-                for (int f4 = tid; f4 < nd / 4; f4 += kBT)
-                    reinterpret_cast<float4*>(s_dc)[f4] = __ldg(reinterpret_cast<const float4*>(dc) + f4);
-                for (int f4 = tid; f4 < nr / 4; f4 += kBT)
-                    reinterpret_cast<float4*>(s_rest)[f4] = __ldg(reinterpret_cast<const float4*>(rs) + f4);
+                for (int f4 = tid; f4 < nd / 4; f4 += kBT) cp_async16(reinterpret_cast<float4*>(s_dc) + f4, reinterpret_cast<const float4*>(dc) + f4);
+                for (int f4 = tid; f4 < nr / 4; f4 += kBT) cp_async16(reinterpret_cast<float4*>(s_rest) + f4, reinterpret_cast<const float4*>(rs) + f4);
             } else {
                 for (int f = tid; f < nd; f += kBT) s_dc[f] = __ldg(dc + f);
                 for (int f = tid; f < nr; f += kBT) s_rest[f] = __ldg(rs + f);
@@ -692,17 +694,21 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)base * 48);
         const int n4 = nvalid * 12;
         for (int f = tid; f < n4; f += kBT) {
-            const float4 v = __ldg(src + f);
-            const int row = f / 12, col = (f % 12) * 4;
-            float* d = s_sh + row * kRow + col;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            const int row = f / 12, col = f % 12;
+            cp_async16(s_sh + row * kRow + col * 4, src + f);
         }
     }
-    __syncthreads();
+    cp_async_commit();
+    __syncthreads();                          // camera constants
     const float* view = s_cam;
     const float* pr = s_cam + 16;
     const float* cam = s_cam + 32;
 
+    // ---- phase A (the SH rows are still in flight): accumulator line, conic -> cov3D -> scale / rotation, mean2D -> mean3D
+    bool vis = false;
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float ox = 0.f, oy = 0.f, oz = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
     if (idx < p.P) {
         const GradAcc g = gacc_load(p.gacc, p.rec, idx, p.W, p.H);
         s_o3[0 * kBT * 3 + 3 * tid + 0] = g.g0.x; s_o3[0 * kBT * 3 + 3 * tid + 1] = g.g0.y; s_o3[0 * kBT * 3 + 3 * tid + 2] = g.g0.z;
@@ -710,14 +716,10 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         s_o3[2 * kBT * 3 + 3 * tid + 0] = g.g3.x; s_o3[2 * kBT * 3 + 3 * tid + 1] = g.g3.y; s_o3[2 * kBT * 3 + 3 * tid + 2] = g.g3.z;
         p.dL_dopacity[idx] = g.g0.w;
 
-        float dmean[3] = {0.f, 0.f, 0.f};
         float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float dscale[3] = {0.f, 0.f, 0.f};
         float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-        // coefficient k of this thread's row lives at (k == 0 ? row0 : row)[3 * k + c]
-        float* row = SEG ? s_rest + 45 * tid - 3 : s_sh + tid * kRow;
-        float* row0 = SEG ? s_dc + 3 * tid : row;
-        if (p.radii[idx] > 0) {
+        vis = p.radii[idx] > 0;
+        if (vis) {
             const float mx = __ldg(p.means3D + 3 * idx), my = __ldg(p.means3D + 3 * idx + 1), mz = __ldg(p.means3D + 3 * idx + 2);
             float cov3D[6];
             float sx = 0, sy = 0, sz = 0;
@@ -732,42 +734,89 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
             }
             bwd_conic_to_cov3d(p, view, mx, my, mz, cov3D, g.g1.x, g.g1.y, g.g1.z, dcov);
             bwd_mean2d_to_mean3d(pr, mx, my, mz, g.g0.x, g.g0.y, g.g0.z, dmean);
-            if (has_sh) {   // SH backward in place on the staged row (backward.cu:20-139)
-                const float ox = mx - cam[0], oy = my - cam[1], oz = mz - cam[2];
-                const float len = sqrtf(ox * ox + oy * oy + oz * oz);
-                const float x = ox / len, y = oy / len, z = oz / len;
-                const uint8_t cl = p.clamped[idx];
-                const float d0 = (cl & 1) ? 0.f : g.g2.x, d1 = (cl & 2) ? 0.f : g.g2.y, d2 = (cl & 4) ? 0.f : g.g2.z;
-                const int nb = (p.D + 1) * (p.D + 1);
-                float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    if (k < nb) {
-                        float b, bx, by, bz;
-                        sh_basis_and_grad(p.D, x, y, z, k, b, bx, by, bz);
-                        float* rk = (k == 0) ? row0 : row;
-                        const float s = rk[3 * k] * d0 + rk[3 * k + 1] * d1 + rk[3 * k + 2] * d2;
-                        ddx += bx * s; ddy += by * s; ddz += bz * s;
-                        rk[3 * k] = b * d0; rk[3 * k + 1] = b * d1; rk[3 * k + 2] = b * d2;
-                    } else {
-                        float* rk = (k == 0) ? row0 : row;
-                        rk[3 * k] = 0.f; rk[3 * k + 1] = 0.f; rk[3 * k + 2] = 0.f;
-                    }
-                }
-                bwd_dir_to_mean(ox, oy, oz, ddx, ddy, ddz, dmean);
-            }
             if (p.scales != nullptr) bwd_cov3d_to_scale_rot(q, sx, sy, sz, p.scale_modifier, dcov, dscale, drot);
-        } else if (has_sh) {
-#pragma unroll
-            for (int k = 0; k < 48; k++) ((k < 3) ? row0 : row)[k] = 0.f;
+            if (has_sh) {
+                ox = mx - cam[0]; oy = my - cam[1]; oz = mz - cam[2];
+                const uint8_t cl = p.clamped[idx];
+                d0 = (cl & 1) ? 0.f : g.g2.x; d1 = (cl & 2) ? 0.f : g.g2.y; d2 = (cl & 4) ? 0.f : g.g2.z;
+            }
         }
-        s_o3[3 * kBT * 3 + 3 * tid + 0] = dmean[0]; s_o3[3 * kBT * 3 + 3 * tid + 1] = dmean[1]; s_o3[3 * kBT * 3 + 3 * tid + 2] = dmean[2];
-        s_o3[4 * kBT * 3 + 3 * tid + 0] = dscale[0]; s_o3[4 * kBT * 3 + 3 * tid + 1] = dscale[1]; s_o3[4 * kBT * 3 + 3 * tid + 2] = dscale[2];
         if (p.dL_dcov3D != nullptr) {
 #pragma unroll
             for (int i = 0; i < 6; i++) p.dL_dcov3D[6 * idx + i] = dcov[i];
         }
         if (p.dL_drot != nullptr) reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
+    }
+    cp_async_wait_all();
+    __syncthreads();                          // SH rows
+
+    // ---- phase B: SH backward in place on the staged row (backward.cu:20-139)
+    if (idx < p.P) {
+        if (has_sh) {
+            const int nb = (p.D + 1) * (p.D + 1);
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (vis) {
+                const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+                x = ox / len; y = oy / len; z = oz / len;
+            }
+            if (SEG) {
+                // coefficient k of this thread's row lives at (k == 0 ? row0 : row)[3 * k + c]
+                float* row = s_rest + 45 * tid - 3;
+                float* row0 = s_dc + 3 * tid;
+                if (vis) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        float* rk = (k == 0) ? row0 : row;
+                        if (k < nb) {
+                            float b, bx, by, bz;
+                            sh_basis_and_grad(p.D, x, y, z, k, b, bx, by, bz);
+                            const float s = rk[3 * k] * d0 + rk[3 * k + 1] * d1 + rk[3 * k + 2] * d2;
+                            ddx += bx * s; ddy += by * s; ddz += bz * s;
+                            rk[3 * k] = b * d0; rk[3 * k + 1] = b * d1; rk[3 * k + 2] = b * d2;
+                        } else {
+                            rk[3 * k] = 0.f; rk[3 * k + 1] = 0.f; rk[3 * k + 2] = 0.f;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 48; k++) ((k < 3) ? row0 : row)[k] = 0.f;
+                }
+            } else {
+                // four coefficients (three 16-byte words) at a time
+                float4* r4 = reinterpret_cast<float4*>(s_sh + tid * kRow);
+                if (vis) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 q0 = r4[3 * c], q1 = r4[3 * c + 1], q2 = r4[3 * c + 2];
+                        const float v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                        float o[12];
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int k = 4 * c + kk;
+                            if (k < nb) {
+                                float b, bx, by, bz;
+                                sh_basis_and_grad(p.D, x, y, z, k, b, bx, by, bz);
+                                const float s = v[3 * kk] * d0 + v[3 * kk + 1] * d1 + v[3 * kk + 2] * d2;
+                                ddx += bx * s; ddy += by * s; ddz += bz * s;
+                                o[3 * kk] = b * d0; o[3 * kk + 1] = b * d1; o[3 * kk + 2] = b * d2;
+                            } else {
+                                o[3 * kk] = 0.f; o[3 * kk + 1] = 0.f; o[3 * kk + 2] = 0.f;
+                            }
+                        }
+                        r4[3 * c] = make_float4(o[0], o[1], o[2], o[3]);
+                        r4[3 * c + 1] = make_float4(o[4], o[5], o[6], o[7]);
+                        r4[3 * c + 2] = make_float4(o[8], o[9], o[10], o[11]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 12; c++) r4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (vis) bwd_dir_to_mean(ox, oy, oz, ddx, ddy, ddz, dmean);
+        }
+        s_o3[3 * kBT * 3 + 3 * tid + 0] = dmean[0]; s_o3[3 * kBT * 3 + 3 * tid + 1] = dmean[1]; s_o3[3 * kBT * 3 + 3 * tid + 2] = dmean[2];
+        s_o3[4 * kBT * 3 + 3 * tid + 0] = dscale[0]; s_o3[4 * kBT * 3 + 3 * tid + 1] = dscale[1]; s_o3[4 * kBT * 3 + 3 * tid + 2] = dscale[2];
     }
     __syncthreads();
 
@@ -807,9 +856,8 @@ __global__ void __launch_bounds__(kBT, 4) preprocess_bwd_staged_kernel(const __g
         float4* dst = reinterpret_cast<float4*>(p.dL_dsh + (size_t)base * 48);
         const int n4 = nvalid * 12;
         for (int f = tid; f < n4; f += kBT) {
-            const int row = f / 12, col = (f % 12) * 4;
-            const float* s = s_sh + row * kRow + col;
-            dst[f] = make_float4(s[0], s[1], s[2], s[3]);
+            const int row = f / 12, col = f % 12;
+            dst[f] = *reinterpret_cast<const float4*>(s_sh + row * kRow + col * 4);
         }
     }
 }

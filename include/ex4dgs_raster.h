@@ -296,6 +296,30 @@ int ex4dgs_radam_step_ex(const ex4dgs_radam_tensor* tensors, int n, double beta1
  * torch/optim/radam.py's expressions. */
 int ex4dgs_radam_scalars(double lr, long long step, double beta1, double beta2, float* S, float* U, int* rectified);
 
+/* ---- tensor surgery of densification / pruning ----------------------
+ * Replaces, in ONE launch for all tensors, the per-tensor boolean-mask gathers and concatenations the reference
+ * performs on its 15 parameter tensors, both optimizer moments of each and the per-Gaussian statistics:
+ *   CGaussianModel._prune_optimizer / prune_points       (scene/c_gaussian_model.py:693-763)   x[mask]
+ *   CGaussianModel.cat_tensors_to_optimizer              (:765-787)                            torch.cat((x, extension)), zero moments
+ *   densify_and_clone / densify_and_split                (:874-1017)                           extension = x[selected](.repeat(N))
+ * One job copies rows of `row_bytes` bytes (a multiple of 4):
+ *   dst[r] = r < n_a ? a[index ? index[r] : r] : (b ? b[r - n_a] : 0)        for r in [0, n_out)
+ * (pruning: index = the kept rows, n_a = n_out; concatenation: index NULL, n_a = rows of a, b = the extension or NULL
+ * for zero rows; cloning: index = [0..n) ++ selected, n_a = n_out for parameters, n_a = n for the moments).
+ * All pointers are device pointers, `index` is int64 as torch.nonzero produces it and is not range-checked;
+ * dst must not overlap a or b.  At most EX4DGS_GATHER_MAX_JOBS jobs per call. */
+#define EX4DGS_GATHER_MAX_JOBS 64
+typedef struct ex4dgs_gather_job {
+    const void* a;
+    const void* b;
+    void* dst;
+    const long long* index;
+    size_t row_bytes;
+    long long n_a;
+    long long n_out;
+} ex4dgs_gather_job;
+int ex4dgs_gather_rows(const ex4dgs_gather_job* jobs, int n, void* stream);
+
 /* ---- per-iteration statistics (SURVEY.md section 8, row N4 "stats updates") -----------------------
  * Replaces, in ONE launch without host synchronisation, the bookkeeping train.py:196-215 performs after
  * loss.backward() through boolean-mask indexing (~60 PyTorch kernels, a nonzero() + host wait per mask):

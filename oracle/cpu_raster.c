@@ -403,15 +403,19 @@ void or_get_state(void* h, float* depths, float* means2D, float* cov3D, float* c
     if (n_contrib) memcpy(n_contrib, c->n_contrib, 4 * HW);
 }
 
-static inline void atomic_addf(float* p, float v)
+/* The reference adds the per-pixel terms with float atomicAdd in whatever order the hardware schedules them
+ * (backward.cu:604-672): every summation order is "the reference".  The oracle accumulates them in double and rounds
+ * once at the end - the value all those orders scatter around - which also makes it reproducible from run to run
+ * although its tiles are processed by OpenMP threads in arbitrary order. */
+static inline void atomic_addf(double* p, float v)
 {
 #pragma omp atomic
-    *p += v;
+    *p += (double)v;
 }
 
 /* backward.cu:426-682 */
 static void or_render_bwd(Ctx* c, const float* dpix, const float* ddepth, const float* dflow, const float* dacc,
-                          float* dmean2D /*[P,3]*/, float* dconic /*[P,4]*/, float* ddir, float* dopac, float* dcol)
+                          double* dmean2D /*[P,3]*/, double* dconic /*[P,4]*/, double* ddir, double* dopac, double* dcol)
 {
     const int W = c->W, H = c->H;
     const size_t HW = (size_t)W * H;
@@ -619,7 +623,17 @@ int or_backward(void* h, const float* dpix, const float* ddepth, const float* df
     memset(dcov3D, 0, 24 * P); if (c->M) memset(dsh, 0, 12 * P * (size_t)c->M); memset(dscale, 0, 12 * P);
     memset(drot, 0, 16 * P); memset(ddir, 0, 12 * P); memset(dconic, 0, 16 * P);
     if (!c->P) return 0;
-    or_render_bwd(c, dpix, ddepth, dflow, dacc, dmean2D, dconic, ddir, dopac, dcol);
+    {
+        double* a = (double*)calloc(14 * P, sizeof(double));      /* dmean2D[3P] | dconic[4P] | ddir[3P] | dopac[P] | dcol[3P] */
+        if (!a) return -1;
+        or_render_bwd(c, dpix, ddepth, dflow, dacc, a, a + 3 * P, a + 7 * P, a + 10 * P, a + 11 * P);
+        for (size_t i = 0; i < 3 * P; i++) dmean2D[i] = (float)a[i];
+        for (size_t i = 0; i < 4 * P; i++) dconic[i] = (float)a[3 * P + i];
+        for (size_t i = 0; i < 3 * P; i++) ddir[i] = (float)a[7 * P + i];
+        for (size_t i = 0; i < P; i++) dopac[i] = (float)a[10 * P + i];
+        for (size_t i = 0; i < 3 * P; i++) dcol[i] = (float)a[11 * P + i];
+        free(a);
+    }
     or_preprocess_bwd(c, dmean2D, dconic, dcol, dmean3D, dcov3D, dsh, dscale, drot);
     return 0;
 }

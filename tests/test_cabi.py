@@ -134,3 +134,24 @@ def test_training_side_entry_points_reject_bad_arguments_before_touching_cuda(bu
     t[0].step = 0
     assert lib.ex4dgs_radam_step_ex(t, 1, 0.9, 0.999, 1e-8, 1.0, 0, 0, None, None) < 0 and "step" in _lib.last_error()
     assert lib.ex4dgs_regularizer_scratch_bytes() >= 2 * 8 and lib.ex4dgs_l1_scratch_bytes() >= 8
+
+
+def test_gather_rows_rejects_bad_jobs_before_touching_cuda(built):
+    """ex4dgs_gather_rows (densification / pruning row gathers): host-side validation of the job table."""
+    from ex4dgs_b200 import _lib
+    lib = _lib.load()
+    fbuf = (ctypes.c_float * 12)()
+    f = ctypes.addressof(fbuf)
+    j = (_lib.GatherJob * 1)()
+    assert lib.ex4dgs_gather_rows(j, 0, None) == 0                                           # empty table
+    assert lib.ex4dgs_gather_rows(j, 65, None) < 0 and "outside" in _lib.last_error()
+    j[0].a, j[0].dst, j[0].row_bytes, j[0].n_a, j[0].n_out = f, f, 12, 0, 0
+    assert lib.ex4dgs_gather_rows(j, 1, None) == 0                                           # no output rows: nothing to do
+    j[0].n_a, j[0].n_out = 3, 2
+    assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "n_a" in _lib.last_error()
+    j[0].n_a, j[0].n_out, j[0].row_bytes = 1, 1, 6
+    assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "multiple of 4" in _lib.last_error()
+    j[0].row_bytes, j[0].dst = 12, None
+    assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "NULL" in _lib.last_error()
+    j[0].dst, j[0].a = f, f + 2
+    assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "aligned" in _lib.last_error()

@@ -60,8 +60,8 @@ def test_every_sizing_path_gives_the_same_lists(built, cull):
     d = it["depths"][it["point_list"]].view(np.uint32).astype(np.int64)
     key = (it["tile_sorted"].astype(np.int64) << 32) | d
     assert (np.diff(key) >= 0).all()
-    real = it["tile_sorted"][1:] != 0xFFFF               # several culled instances of one Gaussian share the dump tile
-    assert (np.diff(it["point_list"].astype(np.int64))[(np.diff(key) == 0) & real] > 0).all()
+    assert (it["tile_sorted"] != 0xFFFF).all()           # rejected instances (dump tile) never reach the sorted list
+    assert (np.diff(it["point_list"].astype(np.int64))[np.diff(key) == 0] > 0).all()
 
 
 def test_nothing_visible_and_tiny_scenes(built):

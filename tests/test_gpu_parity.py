@@ -57,14 +57,14 @@ def _check_ints(a, b, cull=0):
     assert np.array_equal(ia["means2D"][vis].view(np.uint32), ib["means2D"][vis].view(np.uint32))
 
 
-def _check_floats(a, b, grads=True):
+def _check_floats(a, b, grads=True, rerun=None, rerun_ref=None):
+    """rerun / rerun_ref: callables that render the frame again (U.run_impl) - see U.assert_grads_close."""
     for k in ("color", "depth", "acc", "flow"):
         scale = max(1.0, float(np.abs(b[k]).max()))
         assert float(np.abs(a[k] - b[k]).max()) <= RGB_TOL * scale, k
     if grads:
-        for k, g in b["grads"].items():
-            e = U.rel_err(a["grads"][k], g, U.grad_floor(g))
-            assert e <= GRAD_RTOL, (k, e)
+        U.assert_grads_close(a["grads"], b["grads"], GRAD_RTOL, rerun=(lambda: rerun()["grads"]) if rerun else None,
+                             rerun_ref=(lambda: rerun_ref()["grads"]) if rerun_ref else None)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -73,7 +73,7 @@ def test_against_cpu_oracle(built, name, cull):
     ours = U.run_impl(U.ours_module(), sc, kind="ours", **kw)
     orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", **kw)
     _check_ints(ours, orc, cull)
-    _check_floats(ours, orc)
+    _check_floats(ours, orc, rerun=lambda: U.run_impl(U.ours_module(), sc, kind="ours", **kw))
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -89,7 +89,7 @@ def test_against_reference_golden(built, name, cull):
     ref["inter"]["R"] = int(ref["inter"]["R"])
     ref["grads"] = {k[5:]: g[k] for k in g.files if k.startswith("grad_")}
     _check_ints(ours, ref, cull)
-    _check_floats(ours, ref)
+    _check_floats(ours, ref, rerun=lambda: U.run_impl(U.ours_module(), sc, kind="ours", **kw))
     if cull:
         return
     # the reference's 64-bit keys are (tile << 32 | depth bits) of our lists
@@ -104,7 +104,7 @@ def test_config1_against_oracle(built, cfg, kw, cull):
     ours = U.run_impl(U.ours_module(), sc, kind="ours", grad_kind="all")
     orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", grad_kind="all")
     _check_ints(ours, orc, cull)
-    _check_floats(ours, orc)
+    _check_floats(ours, orc, rerun=lambda: U.run_impl(U.ours_module(), sc, kind="ours", grad_kind="all"))
 
 
 @pytest.mark.parametrize("cfg", ["C1d", "C2"])
@@ -118,7 +118,8 @@ def test_live_against_compiled_reference(built, cfg, cull):
     r = U.run_impl(ref, sc, kind="ref", grads=True, grad_kind="all")
     _check_ints(ours, r, cull)
     assert np.array_equal(ours["color"].view(np.uint32), r["color"].view(np.uint32)), "image not bit-identical"
-    _check_floats(ours, r, grads=grads)
+    _check_floats(ours, r, grads=grads, rerun=lambda: U.run_impl(U.ours_module(), sc, kind="ours", grads=True, grad_kind="all"),
+                  rerun_ref=lambda: U.run_impl(ref, sc, kind="ref", grads=True, grad_kind="all"))
 
 
 def test_full_size_properties(built):
@@ -210,7 +211,7 @@ def test_edge_cases(built, cull):
     a = U.run_impl(mod, sc3, kind="ours")
     b = U.run_impl(U.oracle_module(), sc3, dev="cpu", kind="oracle")
     _check_ints(a, b, cull)
-    _check_floats(a, b)
+    _check_floats(a, b, rerun=lambda: U.run_impl(mod, sc3, kind="ours"))
 
 
 def test_mark_visible(built):
@@ -274,7 +275,7 @@ def test_setting_variants_against_oracle(built, variant, cull):
     ours = run(U.ours_module(), "cuda", "ours")
     orc = run(U.oracle_module(), "cpu", "oracle")
     _check_ints(ours, orc, cull)
-    _check_floats(ours, orc)
+    _check_floats(ours, orc, rerun=lambda: run(U.ours_module(), "cuda", "ours"))
 
 
 def test_debug_flag_and_error_paths(built):
@@ -554,6 +555,4 @@ def test_nine_coefficient_sh_rows_against_oracle(built, cull):
     assert np.array_equal(ra, rb)
     assert float(np.abs(ca - cb).max()) <= RGB_TOL
     assert ga["shs"].shape == (1200, 9, 3)
-    for k, g in gb.items():
-        e = U.rel_err(ga[k], g, U.grad_floor(g))
-        assert e <= GRAD_RTOL, (k, e)
+    U.assert_grads_close(ga, gb, GRAD_RTOL, rerun=lambda: run(mod, "cuda")[2])
