@@ -138,15 +138,16 @@ GeometryState carve_geometry(void* base, int P, size_t temp_bytes)
 // Layout of the binning buffer: two sets of (ids, tiles) of `cap` entries each (BinningState), then the look-back
 // words of the tile sort.  The sorted id list (point_list, all the backward needs) is at offset 0 whatever `cap` is,
 // so a buffer sized for a guess cap >= R can be filled and sorted before R is known on the host.
-BinningState carve_binning(void* base, int cap, size_t status_bytes)
+BinningState carve_binning(void* base, int cap, size_t status_bytes, int key_bytes)
 {
     BinningState b;
     const size_t m = (size_t)(cap > 0 ? cap : 0);
     Carver c(base);
+    b.key_bytes = key_bytes;
     b.val[0] = c.take<uint32_t>(m);
-    b.tile[0] = c.take<uint16_t>(m);
+    b.tile[0] = c.take<char>(m * (size_t)key_bytes);
     b.val[1] = c.take<uint32_t>(m);
-    b.tile[1] = c.take<uint16_t>(m);
+    b.tile[1] = c.take<char>(m * (size_t)key_bytes);
     b.status = reinterpret_cast<uint32_t*>(c.take<char>(status_bytes));
     b.total = c.off + 256;
     return b;
@@ -209,7 +210,8 @@ void ex4dgs_forward_geometry(int* batch, int* warps)
 }
 
 size_t ex4dgs_geometry_bytes(int P) { return carve_geometry(nullptr, P, binning_geometry_scratch_bytes(P > 0 ? P : 1)).total; }
-size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, binning_status_bytes(R)).total; }
+// upper bound over all image sizes (32-bit tile keys, four tile passes); the forward asks for what the frame's image needs
+size_t ex4dgs_binning_bytes(int R) { return carve_binning(nullptr, R, binning_status_bytes(R, 4), 4).total; }
 size_t ex4dgs_image_bytes(int width, int height) { return carve_image(nullptr, width, height).total; }
 
 int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_desc* out, int max)
@@ -217,7 +219,9 @@ int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_de
     // the binning buffer is laid out from its capacity: the one of the calling thread's last forward when that covers R
     const int cap = g_last_cap >= R ? g_last_cap : R;
     const GeometryState g = carve_geometry(nullptr, P, binning_geometry_scratch_bytes(P > 0 ? P : 1));
-    const BinningState b = carve_binning(nullptr, cap, binning_status_bytes(cap));
+    const int gx = (width + EX_TILE - 1) / EX_TILE, gy = (height + EX_TILE - 1) / EX_TILE;
+    const int key_bytes = binning_tile_key_bytes(gx, gy);
+    const BinningState b = carve_binning(nullptr, cap, binning_status_bytes(cap, binning_tile_passes(gx, gy)), key_bytes);
     const ImageState im = carve_image(nullptr, width, height);
     const size_t n = (size_t)P, r = (size_t)(R > 0 ? R : 0), px = (size_t)width * height;
     const size_t tiles = (size_t)((width + EX_TILE - 1) / EX_TILE) * ((height + EX_TILE - 1) / EX_TILE);
@@ -229,7 +233,7 @@ int ex4dgs_describe_buffers(int P, int R, int width, int height, ex4dgs_array_de
         {"clamped", 0, (size_t)g.clamped, 1, n},
         {"gacc", 0, (size_t)g.gacc, sizeof(GradAcc), n},
         {"meta", 0, (size_t)g.meta, 4, 64},
-        {"tile_sorted", 1, (size_t)b.tile[0], 2, r},
+        {"tile_sorted", 1, (size_t)b.tile[0], (size_t)key_bytes, r},
         {"point_list", 1, (size_t)b.val[0], 4, r},
         {"final_T", 2, (size_t)im.final_T, 4, px},
         {"n_contrib", 2, (size_t)im.n_contrib, 4, px},
@@ -292,8 +296,9 @@ int ex4dgs_forward(
             return fail(EX4DGS_ERR_INVALID, "SH degree %d needs %d coefficients, got M=%d", D, (D + 1) * (D + 1), M);
     }
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
-    if ((long long)grid_x * grid_y > 65535)
-        return fail(EX4DGS_ERR_UNSUPPORTED, "more than 65535 tiles (%dx%d) is not supported (16-bit tile keys)", grid_x, grid_y);
+    if ((long long)grid_x * grid_y > 0x3fffffffLL)
+        return fail(EX4DGS_ERR_UNSUPPORTED, "more than 2^30-1 tiles (%dx%d) is not supported", grid_x, grid_y);
+    const int tile_passes = binning_tile_passes(grid_x, grid_y), key_bytes = binning_tile_key_bytes(grid_x, grid_y);
 
     // image-sized scratch
     const size_t img_bytes = carve_image(nullptr, width, height).total;
@@ -336,7 +341,7 @@ int ex4dgs_forward(
     };
 
     if (P <= 0) {
-        void* bin_base = binningBuffer(binning_user, carve_binning(nullptr, 0, binning_status_bytes(0)).total);
+        void* bin_base = binningBuffer(binning_user, carve_binning(nullptr, 0, binning_status_bytes(0, tile_passes), key_bytes).total);
         if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer returned NULL");
         CK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)grid_x * grid_y, s));
         prof.mark();
@@ -418,11 +423,11 @@ int ex4dgs_forward(
     for (int attempt = 0; attempt < 2; attempt++) {
         if (attempt == 1) CK(binning_reset_instances(geom, P, s));
         if (cap > 0 || attempt == 1) {
-            const size_t status_bytes = binning_status_bytes(cap);
-            const size_t bin_bytes = carve_binning(nullptr, cap, status_bytes).total;
+            const size_t status_bytes = binning_status_bytes(cap, tile_passes);
+            const size_t bin_bytes = carve_binning(nullptr, cap, status_bytes, key_bytes).total;
             void* bin_base = binningBuffer(binning_user, bin_bytes);
             if (!bin_base) return fail(EX4DGS_ERR_ALLOC, "binningBuffer(%zu) returned NULL", bin_bytes);
-            bin = carve_binning(align256(bin_base), cap, status_bytes);
+            bin = carve_binning(align256(bin_base), cap, status_bytes, key_bytes);
         }
         if (cap > 0) {
             CK(binning_duplicate(geom, bin, radii, P, cap, grid_x, grid_y, flags, s));
@@ -501,7 +506,7 @@ int ex4dgs_backward(
     const int grid_x = (width + EX_TILE - 1) / EX_TILE, grid_y = (height + EX_TILE - 1) / EX_TILE;
     // the CUB temp areas are the last sub-arrays and are not used by the backward
     const GeometryState geom = carve_geometry(align256(geom_buffer), P, 0);
-    const BinningState bin = carve_binning(align256(binning_buffer), 0, 0);      // the sorted id list is at offset 0
+    const BinningState bin = carve_binning(align256(binning_buffer), 0, 0, 2);   // the sorted id list is at offset 0
     const ImageState img = carve_image(align256(image_buffer), width, height);
 
     PreprocessBwdParams bp;

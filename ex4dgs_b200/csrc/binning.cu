@@ -359,13 +359,14 @@ constexpr int kDupThreads = 256;
 // The warp's first output position is the number of items of all earlier Gaussians, summed from the three levels of
 // touched_sums_kernel; warps are independent (no barrier, no chain).  The rectangle is recomputed from the stored
 // record with the same inline functions on the same floats as in the preprocess kernel (its area IS tiles_touched).
+template <typename KeyT>
 __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* __restrict__ n_vis_ptr, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ touched_in_order,
                                                                 const uint32_t* __restrict__ warp_sum, const uint32_t* __restrict__ block_sum,
                                                                 const uint32_t* __restrict__ super_sum,
                                                                 const SplatRec* __restrict__ rec, const int* __restrict__ radii,
                                                                 int grid_x, int grid_y, unsigned flags, const float* __restrict__ pad_ptr,
-                                                                uint16_t* __restrict__ tile_out, uint32_t* __restrict__ val_out, uint32_t cap)
+                                                                KeyT* __restrict__ tile_out, uint32_t* __restrict__ val_out, uint32_t cap)
 {
     __shared__ CullCtx s_ctx[kDupThreads / 32][32];
     __shared__ int s_prefix[kDupThreads / 32][32];
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* 
     for (int base = 0; base < total; base += 32) {
         const int item = base + lane;
         bool keep = false;
-        uint16_t tile = 0;
+        KeyT tile = 0;
         uint32_t idv = 0;
         if (item < total) {
             const int src = expand_owner(s_prefix[warp], item);
@@ -425,40 +426,46 @@ __global__ void __launch_bounds__(kDupThreads) duplicate_kernel(const uint32_t* 
             const int w = s_ctx[warp][src].w;
             const int ty = s_ctx[warp][src].y0 + local / w, tx = s_ctx[warp][src].x0 + local % w;
             idv = s_ctx[warp][src].id;
-            tile = (uint16_t)(ty * grid_x + tx);
+            tile = (KeyT)(ty * grid_x + tx);
             keep = !(cull && cull_test(s_ctx[warp][src], tx, ty, pad));
         }
         // culled instances keep their slot (the count is the full rectangle) but are keyed to
-        // the dump tile 0xFFFF, which the first pass of the tile sort drops
+        // the dump tile (all ones: 0xFFFF / 0xFFFFFFFF), which the first pass of the tile sort drops
         if (item < total && wbase + item < cap) {      // cap: capacity of the buffer, sized before R is known (api.cu)
-            tile_out[wbase + item] = keep ? tile : (uint16_t)0xFFFF;
+            tile_out[wbase + item] = keep ? tile : (KeyT)EX_INVISIBLE_KEY;
             val_out[wbase + item] = idv;
         }
     }
 }
 
 // ranges[tile] = [first, last+1) of the tile's entries in the sorted list (rasterizer_impl.cu:118-140);
-// eight 16-bit keys per thread from one 128-bit load.  `listed` = entries of the sorted list (the instances the exact
-// tile test kept, at most the buffer's capacity), `total` = R.
+// eight 16-bit (four 32-bit) keys per thread from one 128-bit load.  `listed` = entries of the sorted list (the instances
+// the exact tile test kept, at most the buffer's capacity), `total` = R.
+template <typename KeyT>
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ listed_ptr, const uint32_t* __restrict__ total_ptr, uint32_t cap,
-                                                          const uint16_t* __restrict__ tiles, uint2* __restrict__ ranges, uint32_t* __restrict__ err)
+                                                          const KeyT* __restrict__ tiles, uint2* __restrict__ ranges, uint32_t* __restrict__ err)
 {
+    constexpr int KPV = 16 / (int)sizeof(KeyT);
     const int L = (int)min(__ldg(listed_ptr), cap);
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0 && __ldg(total_ptr) > cap) atomicOr(err, 2u);      // the lists are truncated (EX4DGS_FLAG_NO_HOST_WAIT: nobody else notices)
-    const int base = g * 8;
+    const int base = g * KPV;
     if (base >= L) return;
-    uint16_t t[8];
-    if (base + 8 <= L) {
+    uint32_t t[KPV];
+    if (base + KPV <= L) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(tiles) + g);
-        t[0] = v.x & 0xffff; t[1] = v.x >> 16; t[2] = v.y & 0xffff; t[3] = v.y >> 16;
-        t[4] = v.z & 0xffff; t[5] = v.z >> 16; t[6] = v.w & 0xffff; t[7] = v.w >> 16;
+        if (sizeof(KeyT) == 2) {
+            t[0] = v.x & 0xffff; t[1] = v.x >> 16; t[2 % KPV] = v.y & 0xffff; t[3 % KPV] = v.y >> 16;
+            t[4 % KPV] = v.z & 0xffff; t[5 % KPV] = v.z >> 16; t[6 % KPV] = v.w & 0xffff; t[7 % KPV] = v.w >> 16;
+        } else {
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
     } else {
-        for (int k = 0; k < 8; k++) t[k] = (base + k < L) ? tiles[base + k] : 0;
+        for (int k = 0; k < KPV; k++) t[k] = (base + k < L) ? (uint32_t)tiles[base + k] : 0u;
     }
     uint32_t prev = (base == 0) ? 0xffffffffu : (uint32_t)tiles[base - 1];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < KPV; k++) {
         const int idx = base + k;
         if (idx < L) {
             const uint32_t cur = t[k];
@@ -517,7 +524,7 @@ uint32_t higher_msb(uint32_t n)
 
 // ---- host side -------------------------------------------------------------------------------------
 // Scratch words behind GeometryState::meta.  Zeroed together with it at the start of every forward:
-//   hist[6][256]                     digit histograms: 4 depth passes, 2 tile passes
+//   hist[8][256]                     digit histograms: 4 depth passes, up to 4 tile passes
 //   super_sum[ceil(P / 16384)]       sums of tiles_touched (depth order) over 16384 Gaussians
 //   depth_status[4][tiles][256]      look-back words of the depth passes
 // not zeroed (fully written before they are read):
@@ -539,7 +546,7 @@ SortScratch sort_scratch(char* base, int P)
     uint32_t* w = reinterpret_cast<uint32_t*>(base);
     sc.depth_tiles = (n + kDepthTile - 1) / kDepthTile;
     sc.hist = w;
-    sc.super_sum = sc.hist + 6 * kBins;
+    sc.super_sum = sc.hist + 8 * kBins;
     sc.depth_status = sc.super_sum + up((n + 16383) / 16384 + 1);
     sc.block_sum = sc.depth_status + (size_t)kDepthPasses * sc.depth_tiles * kBins;
     sc.zero_words = (size_t)(sc.block_sum - w);
@@ -547,22 +554,25 @@ SortScratch sort_scratch(char* base, int P)
     sc.words = (size_t)(sc.warp_sum - w) + up((n + 31) / 32);
     return sc;
 }
-int tile_sort_passes(int grid_x, int grid_y, unsigned flags)
+// 8-bit passes over the bits of the largest tile id (the dump tile 0xFF..FF is dropped by the first pass: it needs no bits)
+int tile_sort_passes(int grid_x, int grid_y)
 {
-    (void)flags;                                          // the dump tile 0xFFFF is dropped by the first pass: it needs no bits
     const int bit = (int)higher_msb((uint32_t)(grid_x * grid_y));
-    return bit > 8 ? 2 : 1;
+    return bit <= 8 ? 1 : (bit + 7) / 8;
 }
 }  // namespace
 
 size_t binning_geometry_scratch_bytes(int P) { return sort_scratch(nullptr, P).words * sizeof(uint32_t) + 256; }
 size_t binning_geometry_zero_bytes(int P) { return sort_scratch(nullptr, P).zero_words * sizeof(uint32_t); }
-size_t binning_status_bytes(int cap)
+int binning_tile_passes(int grid_x, int grid_y) { return tile_sort_passes(grid_x, grid_y); }
+// 16-bit tile keys while every tile id (and the all-ones dump key) fits, 32-bit keys for images of more than 65535 tiles
+int binning_tile_key_bytes(int grid_x, int grid_y) { return (long long)grid_x * grid_y > 65535 ? 4 : 2; }
+size_t binning_status_bytes(int cap, int passes)
 {
     const size_t tiles = ((size_t)(cap > 0 ? cap : 0) + kTileTile - 1) / kTileTile;
-    return 2 * tiles * kBins * sizeof(uint32_t) + 256;
+    return (size_t)passes * tiles * kBins * sizeof(uint32_t) + 256;
 }
-int binning_duplicate_set(int grid_x, int grid_y, unsigned flags) { return tile_sort_passes(grid_x, grid_y, flags) & 1; }
+int binning_duplicate_set(int grid_x, int grid_y) { return tile_sort_passes(grid_x, grid_y) & 1; }
 
 // `out` must have been zeroed by the caller
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s)
@@ -606,9 +616,9 @@ cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s)
 cudaError_t binning_reset_instances(const GeometryState& g, int P, cudaStream_t s)
 {
     const SortScratch sc = sort_scratch(g.temp, P);
-    cudaError_t e = cudaMemsetAsync(g.meta + EX_META_TICKETS + 5, 0, 2 * sizeof(uint32_t), s);
+    cudaError_t e = cudaMemsetAsync(g.meta + EX_META_TICKETS + 5, 0, 4 * sizeof(uint32_t), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(g.meta + EX_META_LISTED, 0, sizeof(uint32_t), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(sc.hist + 4 * kBins, 0, 2 * kBins * sizeof(uint32_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc.hist + 4 * kBins, 0, 4 * kBins * sizeof(uint32_t), s);
     return e;
 }
 
@@ -619,53 +629,76 @@ cudaError_t binning_duplicate(const GeometryState& g, const BinningState& b, con
 {
     if (P <= 0) return cudaSuccess;
     const SortScratch sc = sort_scratch(g.temp, P);
-    const int set = binning_duplicate_set(grid_x, grid_y, flags);
-    duplicate_kernel<<<(P + kDupThreads - 1) / kDupThreads, kDupThreads, 0, s>>>(
-        g.meta + EX_META_NVIS, g.order, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum, g.rec, radii, grid_x, grid_y, flags,
-        reinterpret_cast<const float*>(g.meta), b.tile[set], b.val[set], (uint32_t)(cap > 0 ? cap : 0));
+    const int set = binning_duplicate_set(grid_x, grid_y);
+    const int grid = (P + kDupThreads - 1) / kDupThreads;
+    const float* const pad = reinterpret_cast<const float*>(g.meta);
+    const uint32_t c = (uint32_t)(cap > 0 ? cap : 0);
+    if (b.key_bytes == 2)
+        duplicate_kernel<uint16_t><<<grid, kDupThreads, 0, s>>>(g.meta + EX_META_NVIS, g.order, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum,
+                                                                g.rec, radii, grid_x, grid_y, flags, pad,
+                                                                static_cast<uint16_t*>(b.tile[set]), b.val[set], c);
+    else
+        duplicate_kernel<uint32_t><<<grid, kDupThreads, 0, s>>>(g.meta + EX_META_NVIS, g.order, g.key_b, sc.warp_sum, sc.block_sum, sc.super_sum,
+                                                                g.rec, radii, grid_x, grid_y, flags, pad,
+                                                                static_cast<uint32_t*>(b.tile[set]), b.val[set], c);
     return cudaGetLastError();
 }
 
 // stable sort of the min(R, cap) pairs by tile into set 0 (point_list, tile_sorted), per-tile ranges
+namespace {
+template <typename KeyT>
+cudaError_t sort_ranges(const GeometryState& g, const BinningState& b, const ImageState& img, int P, int cap, int passes, bool cull, cudaStream_t s)
+{
+    const SortScratch sc = sort_scratch(g.temp, P);
+    const uint32_t* const total = g.meta + EX_META_TOTAL;
+    uint32_t* const err = g.meta + EX_META_ERROR;
+    // entries of the sorted list: with the exact tile test, what the histogram kernel counted (it skips the dump tile)
+    const uint32_t* const listed = cull ? g.meta + EX_META_LISTED : total;
+    const int grid = (cap + kTileTile - 1) / kTileTile;
+    const size_t st = (size_t)grid * kBins;
+    constexpr int T = EX_SORT_THREADS_TILE, I = EX_SORT_ITEMS_TILE, M = EX_SORT_MINBLOCKS_TILE;
+    uint32_t* const tk = g.meta + EX_META_TICKETS;
+    uint32_t* const hist = sc.hist + 4 * kBins;
+    KeyT* const tile[2] = {static_cast<KeyT*>(b.tile[0]), static_cast<KeyT*>(b.tile[1])};
+    int cur = passes & 1;                                   // the duplicate kernel's set; the last pass ends in set 0
+    uint32_t* const n_listed = cull ? g.meta + EX_META_LISTED : nullptr;
+    switch (passes * 2 + (cull ? 1 : 0)) {
+        case 2: radix_hist_kernel<KeyT, 1, false><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 3: radix_hist_kernel<KeyT, 1, true><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 4: radix_hist_kernel<KeyT, 2, false><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 5: radix_hist_kernel<KeyT, 2, true><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 6: radix_hist_kernel<KeyT, 3, false><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 7: radix_hist_kernel<KeyT, 3, true><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        case 8: radix_hist_kernel<KeyT, 4, false><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+        default: radix_hist_kernel<KeyT, 4, true><<<148, 1024, 0, s>>>(tile[cur], total, (uint32_t)cap, hist, n_listed); break;
+    }
+    cudaError_t e = cudaSuccess;
+    for (int p = 0; p < passes && e == cudaSuccess; p++, cur ^= 1) {
+        // the first pass reads the min(R, cap) emitted pairs and (exact tile culling) drops the dump-tile ones on the fly
+        if (p == 0 && cull)
+            e = launch_pass<KeyT, T, I, M, true, false, true>(grid, s, tile[cur], b.val[cur], tile[cur ^ 1], b.val[cur ^ 1], total, (uint32_t)cap, 0,
+                                                              hist, b.status, tk + 5, err);
+        else
+            e = launch_pass<KeyT, T, I, M, false, false, true>(grid, s, tile[cur], b.val[cur], tile[cur ^ 1], b.val[cur ^ 1], p == 0 ? total : listed,
+                                                               (uint32_t)cap, 8 * p, hist + p * kBins, b.status + p * st, tk + 5 + p, err);
+    }
+    if (e != cudaSuccess) return e;
+    constexpr int KPV = 16 / (int)sizeof(KeyT);
+    const int groups = (cap + KPV - 1) / KPV;
+    tile_ranges_kernel<KeyT><<<(groups + 255) / 256, 256, 0, s>>>(listed, total, (uint32_t)cap, tile[0], img.ranges, err);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t binning_sort_ranges(const GeometryState& g, const BinningState& b, const ImageState& img, int P, int cap,
                                 int grid_x, int grid_y, unsigned flags, cudaStream_t s)
 {
     const int tiles = grid_x * grid_y;
     cudaError_t e = cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, s);
     if (e != cudaSuccess || cap <= 0 || P <= 0) return e;
-    e = cudaMemsetAsync(b.status, 0, binning_status_bytes(cap) - 256, s);
+    const int passes = tile_sort_passes(grid_x, grid_y);
+    e = cudaMemsetAsync(b.status, 0, binning_status_bytes(cap, passes) - 256, s);
     if (e != cudaSuccess) return e;
-    const SortScratch sc = sort_scratch(g.temp, P);
-    const uint32_t* const total = g.meta + EX_META_TOTAL;
-    uint32_t* const err = g.meta + EX_META_ERROR;
     const bool cull = (flags & 1u) != 0;
-    // entries of the sorted list: with the exact tile test, what the histogram kernel counted (it skips the dump tile)
-    const uint32_t* const listed = cull ? g.meta + EX_META_LISTED : total;
-    const int passes = tile_sort_passes(grid_x, grid_y, flags);
-    const int grid = (cap + kTileTile - 1) / kTileTile;
-    const size_t st = (size_t)grid * kBins;
-    constexpr int T = EX_SORT_THREADS_TILE, I = EX_SORT_ITEMS_TILE, M = EX_SORT_MINBLOCKS_TILE;
-    uint32_t* const tk = g.meta + EX_META_TICKETS;
-    // the first pass reads the min(R, cap) emitted pairs and (exact tile culling) drops the dump-tile ones on the fly
-    const int src = passes & 1, dst = src ^ 1;
-    if (cull) {
-        if (passes == 2) radix_hist_kernel<uint16_t, 2, true><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, g.meta + EX_META_LISTED);
-        else radix_hist_kernel<uint16_t, 1, true><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, g.meta + EX_META_LISTED);
-    } else {
-        if (passes == 2) radix_hist_kernel<uint16_t, 2, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-        else radix_hist_kernel<uint16_t, 1, false><<<148, 1024, 0, s>>>(b.tile[src], total, (uint32_t)cap, sc.hist + 4 * kBins, nullptr);
-    }
-    if (cull)
-        e = launch_pass<uint16_t, T, I, M, true, false, true>(grid, s, b.tile[src], b.val[src], b.tile[dst], b.val[dst], total, (uint32_t)cap, 0,
-                                                              sc.hist + 4 * kBins, b.status, tk + 5, err);
-    else
-        e = launch_pass<uint16_t, T, I, M, false, false, true>(grid, s, b.tile[src], b.val[src], b.tile[dst], b.val[dst], total, (uint32_t)cap, 0,
-                                                               sc.hist + 4 * kBins, b.status, tk + 5, err);
-    if (e == cudaSuccess && passes == 2)
-        e = launch_pass<uint16_t, T, I, M, false, false, true>(grid, s, b.tile[1], b.val[1], b.tile[0], b.val[0], listed, (uint32_t)cap, 8,
-                                                               sc.hist + 5 * kBins, b.status + st, tk + 6, err);
-    if (e != cudaSuccess) return e;
-    const int groups = (cap + 7) / 8;
-    tile_ranges_kernel<<<(groups + 255) / 256, 256, 0, s>>>(listed, total, (uint32_t)cap, b.tile[0], img.ranges, err);
-    return cudaGetLastError();
+    return b.key_bytes == 2 ? sort_ranges<uint16_t>(g, b, img, P, cap, passes, cull, s) : sort_ranges<uint32_t>(g, b, img, P, cap, passes, cull, s);
 }

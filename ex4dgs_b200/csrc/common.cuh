@@ -115,7 +115,7 @@ struct Carver {
 #define EX_META_TOTAL 4      // R: (Gaussian, tile) instances (touched_sums_kernel)
 #define EX_META_ERROR 5      // bit 0: a look-back did not complete; bit 1: more instances than the binning buffer holds
 #define EX_META_LISTED 6     // entries of the sorted (tile, id) list with exact tile culling: instances the test kept, at most the capacity (tile histogram kernel)
-#define EX_META_TICKETS 8    // [0..3] depth passes, [5..6] tile passes
+#define EX_META_TICKETS 8    // [0..3] depth passes, [5..8] tile passes
 
 struct GeometryState {
     uint32_t* key_in;         // [P] depth bits, EX_INVISIBLE_KEY when culled
@@ -137,7 +137,8 @@ struct GeometryState {
 // offset 0) and holds the sorted lists at the end; the duplicate kernel writes set 0 when the tile sort has two
 // passes (0 -> 1 -> 0) and set 1 when it has one.
 struct BinningState {
-    uint16_t* tile[2];        // [cap]; tile[0] = sorted tile ids at the end
+    void* tile[2];            // [cap] uint16 tile ids (uint32 when the image has more than 65535 tiles); tile[0] = sorted tile ids at the end
+    int key_bytes;            // 2 or 4
     uint32_t* val[2];         // [cap]; val[0] = point_list: Gaussian ids by (tile, depth, id) == reference point_list
     uint32_t* status;         // look-back words of the tile passes
     size_t total;
@@ -152,7 +153,7 @@ struct ImageState {
 };
 
 GeometryState carve_geometry(void* base, int P, size_t temp_bytes);
-BinningState carve_binning(void* base, int cap, size_t status_bytes);
+BinningState carve_binning(void* base, int cap, size_t status_bytes, int key_bytes);
 ImageState carve_image(void* base, int width, int height);
 
 // ---- kernel parameter blocks ---------------------------------------------------------------------
@@ -346,8 +347,10 @@ cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s);
 cudaError_t launch_subpixel_absmax(const float* subpixel_offset, size_t n, uint32_t* out, cudaStream_t s);
 size_t binning_geometry_scratch_bytes(int P);      // sort scratch behind GeometryState::meta ...
 size_t binning_geometry_zero_bytes(int P);         // ... and how much of it has to be zero at the start of a forward
-size_t binning_status_bytes(int cap);              // look-back words of the tile passes for a buffer of `cap` instances
-int binning_duplicate_set(int grid_x, int grid_y, unsigned flags);
+size_t binning_status_bytes(int cap, int passes);  // look-back words of `passes` tile passes for a buffer of `cap` instances
+int binning_tile_passes(int grid_x, int grid_y);   // 8-bit passes of the tile sort (1 .. 4)
+int binning_tile_key_bytes(int grid_x, int grid_y);    // 2, or 4 for images of more than 65535 tiles
+int binning_duplicate_set(int grid_x, int grid_y);
 // depth order of the visible Gaussians -> g.order, their number -> meta[EX_META_NVIS], the instance count R ->
 // meta[EX_META_TOTAL]; returns cudaError
 cudaError_t binning_depth_order(const GeometryState& g, int P, cudaStream_t s);

@@ -133,7 +133,7 @@ def _our_intermediates(grad_fn, P, W, H) -> Dict[str, np.ndarray]:
         # are counted in R but dropped by the first pass of the tile sort
         listed = int(out["ranges"][:, 1].max())
         out["point_list"] = view("point_list", np.uint32)[:listed]
-        out["tile_sorted"] = view("tile_sorted", np.uint16)[:listed]
+        out["tile_sorted"] = view("tile_sorted", np.uint16 if desc["tile_sorted"][2] == 2 else np.uint32)[:listed]
     else:
         out["point_list"] = np.zeros(0, np.uint32)
         out["tile_sorted"] = np.zeros(0, np.uint16)

@@ -222,3 +222,45 @@ def test_forward_without_host_wait_flags_a_truncated_frame(built):
     finally:
         ex4dgs_b200.set_host_wait(True)
         ex4dgs_b200.set_capacity_hint(0)
+
+
+def test_more_than_65535_tiles_against_oracle(built):
+    """4112 x 4112 pixels = 257 x 257 = 66 049 tiles: tile ids no longer fit 16-bit keys (and 0xFFFF is a real tile), so the
+    duplicate kernel emits 32-bit keys and the tile sort runs three 8-bit passes over them (the reference sorts 64-bit
+    keys whatever the image size, rasterizer_impl.cu:303-323).  Against the CPU oracle in both modes of the exact tile
+    culling: radii, tiles_touched, point_list, ranges and n_contrib bit-equal; images within 5e-4 (25-pixel splats: long
+    per-pixel sums through glibc's expf on the oracle side) with the arg-max id differing in at most 1e-6 of the 16.9 M
+    pixels (near-ties of two weights); gradients at 1e-3.  Against the compiled reference, when it is installed: the
+    image and the ids bit-identical."""
+    mod = U.ours_module()
+    sc = synth.make_scene(4000, 0, 4112, 4112, sigma_px=25.0, seed=synth.SEED + 77)
+    orc = U.run_impl(U.oracle_module(), sc, dev="cpu", kind="oracle", grad_kind="all")
+    assert (orc["inter"]["ranges"][65535:] != 0).any()
+    ref = U.reference_module()
+    r = U.run_impl(ref, sc, kind="ref", grads=False, intermediates=False) if ref is not None else None
+    old = mod.get_default_flags()
+    try:
+        for cull in (0, 1):
+            mod.set_default_flags(bool(cull))
+            ex4dgs_b200.set_capacity_hint(0)
+            ours = U.run_impl(mod, sc, kind="ours", grad_kind="all")
+            it, io = ours["inter"], orc["inter"]
+            assert it["tile_sorted"].dtype == np.uint32 and int(it["tile_sorted"].max()) > 65535
+            assert ours.get("inexact_thresholds", 0) == 0
+            assert np.array_equal(ours["radii"], orc["radii"])
+            assert float((ours["idxs"] != orc["idxs"]).mean()) <= 1e-6
+            if not cull:
+                for k in ("tiles_touched", "point_list", "ranges", "n_contrib"):
+                    assert it["R"] == io["R"] and np.array_equal(it[k], io[k]), k
+            for k in ("color", "depth", "acc", "flow"):
+                assert float(np.abs(ours[k] - orc[k]).max()) <= 5e-4 * max(1.0, float(np.abs(orc[k]).max())), k
+            U.assert_grads_close(ours["grads"], orc["grads"], 1e-3,
+                                 rerun=lambda: U.run_impl(mod, sc, kind="ours", grad_kind="all", intermediates=False)["grads"])
+            if r is not None:
+                assert np.array_equal(ours["color"].view(np.uint32), r["color"].view(np.uint32)), "image not bit-identical"
+                assert np.array_equal(ours["idxs"], r["idxs"]) and np.array_equal(ours["radii"], r["radii"])
+            steady = U.run_impl(mod, sc, kind="ours", grad_kind="all")       # capacity from the previous frame
+            _same(steady, ours)
+    finally:
+        mod.set_default_flags(bool(old))
+        ex4dgs_b200.set_capacity_hint(0)
