@@ -713,6 +713,81 @@ def other_configs(mod, dev, K, W, cpu=True):
 
 
 
+def densify_leg(sc: synth.Scene, dev, impl: str, reps: int = 3):
+    """The tensor surgery of densification at this workload (row N4): the reference's UNMODIFIED CGaussianModel - its own
+    constructor, training_setup (torch.optim.RAdam over the 15 named groups, arguments/__init__.py:93-111 learning rates)
+    and one optimizer step so that both moments exist - runs `prune_points` on a random 10 % of the Gaussians and then
+    `densification_postfix` with 5 % cloned rows (scene/c_gaussian_model.py:715-844); reference arm: the class's own
+    `_prune_optimizer` / `cat_tensors_to_optimizer` (one x[mask] or torch.cat per tensor and per moment), our arm:
+    ex4dgs_b200.densify bound onto the same object (one ex4dgs_gather_rows launch per call).  Host wall clock incl. the
+    synchronisation the masks need, best of `reps`."""
+    from types import SimpleNamespace
+    cls = load_reference_model_class()
+    if cls is None:
+        return {"unavailable": "oracle/_ref/callers/scene/c_gaussian_model.py is missing"}
+    args = SimpleNamespace(
+        percent_dense=0.01, position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
+        position_lr_max_steps=30000, dynamic_position_lr_init=0.00016, dynamic_position_lr_final=0.000016,
+        dynamic_position_lr_delay_mult=0.01, dynamic_position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.05,
+        scaling_lr=0.005, rotation_lr=0.00001, disp_lr=0.0001, feature_motion_lr=0.0025, rotation_motion_lr=0.001,
+        opacity_motion_lr=0.05, opacity_motion_center_lr=0.001, opacity_motion_var_lr=0.0005)
+    m = reference_model(sc, dev, cls)
+    m.spatial_lr_scale = 1.0
+    m.keyframe_num = int(m._xyz_motion.shape[1])
+    prev = torch.cuda.current_device()
+    torch.cuda.set_device(dev)          # the class allocates with device="cuda"
+    try:
+        m.training_setup(args)
+        m.max_radii2D = torch.zeros(m._xyz.shape[0], device=dev)
+        m.min_radii2D = torch.ones(m._xyz.shape[0], device=dev) * 1000
+        m.motion_max_radii2D = torch.zeros(m._xyz_motion.shape[0], device=dev)
+        m.motion_min_radii2D = torch.ones(m._xyz_motion.shape[0], device=dev) * 1000
+        params = [g["params"][0] for g in m.optimizer.param_groups]
+        for p in params:
+            p.grad = torch.full_like(p, 1e-4)
+        m.optimizer.step()
+        m.optimizer.zero_grad(set_to_none=True)
+        del params
+        if impl == "ours":
+            from ex4dgs_b200 import densify
+            densify.install(m)
+        static_names = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation", "_xyz_disp")
+        dynamic_names = ("_xyz_motion", "_features_dc_motion", "_features_rest_motion", "_scaling_motion", "_opacity_motion",
+                         "_opacity_duration_center", "_opacity_duration_var", "_rotation_motion")
+        gen = torch.Generator(device=dev).manual_seed(5)
+        t_prune, t_cat = [], []
+        for _ in range(reps):
+            ms = torch.rand(m._xyz.shape[0], generator=gen, device=dev) < 0.1
+            md = torch.rand(m._xyz_motion.shape[0], generator=gen, device=dev) < 0.1
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            m.prune_points(ms, md)
+            torch.cuda.synchronize(dev)
+            t_prune.append((time.perf_counter() - t0) * 1e3)
+            sel_s = torch.nonzero(torch.rand(m._xyz.shape[0], generator=gen, device=dev) < 0.05).squeeze(1)
+            sel_d = torch.nonzero(torch.rand(m._xyz_motion.shape[0], generator=gen, device=dev) < 0.05).squeeze(1)
+            with torch.no_grad():
+                new = [getattr(m, n)[sel_s] for n in static_names] + [getattr(m, n)[sel_d] for n in dynamic_names]
+                # the two statistics densification_postfix does not reset are extended by its callers (c_gaussian_model.py:985-988,1008-1011)
+                for n, sel in (("xyz_error_min", sel_s), ("xyz_error_min_timestamp", sel_s),
+                               ("motion_xyz_error_min", sel_d), ("motion_xyz_error_min_timestamp", sel_d)):
+                    setattr(m, n, torch.cat([getattr(m, n), getattr(m, n)[sel]]))
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            m.densification_postfix(*new)
+            torch.cuda.synchronize(dev)
+            t_cat.append((time.perf_counter() - t0) * 1e3)
+            del new
+        n_par = sum(int(g["params"][0].numel()) for g in m.optimizer.param_groups)
+    finally:
+        torch.cuda.set_device(prev)
+    del m
+    torch.cuda.empty_cache()
+    return {"prune_points_ms": min(t_prune), "densification_postfix_ms": min(t_cat), "parameters": n_par, "reps": reps,
+            "what": "CGaussianModel.prune_points (10 % removed) and densification_postfix (5 % appended) on the reference class: "
+                    + ("ex4dgs_b200.densify bound on (one gather launch per call)" if impl == "ours" else "its own per-tensor x[mask] / torch.cat")}
+
+
 def config4_sweep(sc: synth.Scene, dev, rank: int, ws: int, frames: int = 300):
     """BASELINE.json config 4 in synthetic form, driver-visible: the render.py sweep (render.py:64-96) - `frames` frames,
     one timestamp each, forward only - sharded frame i -> rank i mod N.  The model goes through the reference's on-disk
@@ -1220,6 +1295,11 @@ def main():
         line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
                                 "sample": "the unmodified reference CUDA extension (oracle/_ref) on the same GPU - the reference "
                                           "path has no CPU implementation (rasterize_points.cu:80)"}
+    if ws == 1 and args.workload == "C3" and not (args.no_extra_configs or args.value_only or args.fwd_only or args.only_train_iter):
+        try:
+            line["densify_and_prune"] = densify_leg(sc, dev, "ours" if args.impl == "ours" else "reference")
+        except Exception as e:      # noqa: BLE001 - an extra leg must never cost the headline line
+            line["densify_and_prune"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     emit(line)
     if ws > 1:
         torch.distributed.destroy_process_group()

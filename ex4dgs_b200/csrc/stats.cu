@@ -79,7 +79,7 @@ constexpr int kRegMaxK = 64;          // keyframes per row the staged path holds
 
 // One warp per dynamic Gaussian row ([K,3] floats, contiguous) and one thread per static Gaussian; block
 // partial sums (double) go to part[2 * block + {0,1}].
-__global__ void __launch_bounds__(kRegThreads) regularizer_kernel(const __grid_constant__ RegParams p)
+__global__ void __launch_bounds__(kRegThreads, 6) regularizer_kernel(const __grid_constant__ RegParams p)
 {
     __shared__ double s_part[2][kRegWarps];
     __shared__ __align__(16) float s_row[kRegWarps][2][kRegMaxK * 3];
@@ -222,7 +222,7 @@ int regularizer_blocks()
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 8;
+    return sms * 12;      // two waves of the 6 resident CTAs per SM
 }
 
 cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s)

@@ -50,10 +50,15 @@ class _Jobs:
         self.keep: List[torch.Tensor] = []
 
     def add(self, a: torch.Tensor, n_out: int, index: Optional[torch.Tensor] = None, n_a: Optional[int] = None,
-            b: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Queue one job; returns the (still unwritten) output tensor of shape [n_out, *a.shape[1:]]."""
+            b: Optional[torch.Tensor] = None, rows: Optional[int] = None) -> torch.Tensor:
+        """Queue one job; returns the (still unwritten) output tensor of shape [n_out, *a.shape[1:]].
+        rows: number of rows the index was built for (the mask's length) - the kernel does not range-check the index,
+        so a source of another length is refused here, as torch refuses `x[mask]` with a mask of the wrong shape."""
         if not a.is_cuda:
             raise RuntimeError("ex4dgs_b200.densify is CUDA-only (no CPU fallback)")
+        if rows is not None and (a.dim() == 0 or a.shape[0] != rows):
+            raise IndexError("The shape of the mask [%d] at index 0 does not match the shape of the indexed tensor %s at index 0"
+                             % (rows, list(a.shape)))
         src = a.detach()
         if not src.is_contiguous():
             src = src.contiguous()
@@ -139,19 +144,21 @@ def _rebuild_group(optimizer, group, new_param: torch.Tensor, new_avg, new_sq) -
 
 def _prune(optimizer, static_mask: torch.Tensor, dynamic_mask: torch.Tensor, extra_static=(), extra_dynamic=()):
     idx = {False: _keep_index(static_mask), True: _keep_index(dynamic_mask)}
+    rows = {False: int(static_mask.numel()), True: int(dynamic_mask.numel())}
     jobs = _Jobs()
     planned = []
     for group in optimizer.param_groups:
-        index = idx[group["name"].startswith("motion_")]
+        dyn = group["name"].startswith("motion_")
+        index = idx[dyn]
         p = group["params"][0]
         n = int(index.numel())
         st = optimizer.state.get(p, None)
-        new_p = jobs.add(p, n, index=index)
-        new_avg = jobs.add(st["exp_avg"], n, index=index) if st is not None else None
-        new_sq = jobs.add(st["exp_avg_sq"], n, index=index) if st is not None else None
+        new_p = jobs.add(p, n, index=index, rows=rows[dyn])
+        new_avg = jobs.add(st["exp_avg"], n, index=index, rows=rows[dyn]) if st is not None else None
+        new_sq = jobs.add(st["exp_avg_sq"], n, index=index, rows=rows[dyn]) if st is not None else None
         planned.append((group, new_p, new_avg, new_sq))
-    outs_s = [jobs.add(t, int(idx[False].numel()), index=idx[False]) for t in extra_static]
-    outs_d = [jobs.add(t, int(idx[True].numel()), index=idx[True]) for t in extra_dynamic]
+    outs_s = [jobs.add(t, int(idx[False].numel()), index=idx[False], rows=rows[False]) for t in extra_static]
+    outs_d = [jobs.add(t, int(idx[True].numel()), index=idx[True], rows=rows[True]) for t in extra_dynamic]
     jobs.launch()
     optimizable_tensors = {}
     for group, new_p, new_avg, new_sq in planned:

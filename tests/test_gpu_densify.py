@@ -107,6 +107,23 @@ def test_prune_points_matches_the_reference_class(built):
     _assert_same(ref, ours)
 
 
+def test_mask_of_the_wrong_length_is_refused(built):
+    """torch refuses x[mask] when the mask's length differs from the tensor's; the gather kernel does not range-check its
+    index, so the drop-in must refuse it on the host too (a statistics tensor that was not extended after a densification)."""
+    sc = synth.make_scene(600, 400, 64, 48, seed=15)
+    ref, ours = _pair(sc)
+    for m in (ref, ours):
+        m.xyz_error_min = m.xyz_error_min[:-3]
+    ms, md = torch.zeros(600, dtype=torch.bool, device="cuda"), torch.zeros(400, dtype=torch.bool, device="cuda")
+    with pytest.raises(IndexError):
+        ref.prune_points(ms, md)
+    with pytest.raises(IndexError):
+        ours.prune_points(ms, md)
+    assert ours._xyz.shape[0] == 600 and ours.optimizer.param_groups[0]["params"][0] is ours._xyz      # nothing was touched
+    with pytest.raises(IndexError):
+        ours.prune_points(ms[:-1], md)
+
+
 def test_prune_everything_and_nothing(built):
     sc = synth.make_scene(700, 500, 64, 48, seed=12)
     ref, ours = _pair(sc)
