@@ -7,19 +7,22 @@
 // sorts on much less data (SURVEY.md section 7 "Sort traffic"):
 //   1. stable sort of the VISIBLE Gaussians by their 32 depth bits      -> order by (depth, id)
 //   2. emit the (tile, id) instances in that order, stable sort by the `bit`-bit tile id only
-//      (uint16 keys) -> (tile, depth, id), which is exactly the order of the reference's stable
-//      LSD sort with its emission order (= Gaussian index) as tie-break.
+//      (uint16 keys; uint32 keys and three or four passes for images of more than 65535 tiles)
+//      -> (tile, depth, id), which is exactly the order of the reference's stable LSD sort with its
+//      emission order (= Gaussian index) as tie-break.
 //
 // Both sorts are the one-sweep LSD radix sort below (8-bit digits, one kernel per digit: rank the
-// tile's keys with warp match, publish the tile's digit counts, chained look-back over the previous
+// tile's keys per warp through shared-memory lane masks, publish the tile's digit counts, chained look-back over the previous
 // tiles, scatter through shared memory).  It does what cub::DeviceRadixSort does, with three
 // differences that the pipeline needs: the item count is read from DEVICE memory (the number of
 // visible Gaussians / of instances is produced by the kernel in front, the host never waits for it
-// before launching), the first depth pass drops the culled Gaussians on the fly (P keys in, P_vis
-// pairs out: the later passes and the duplicate kernel only see visible ones), and the values of the
-// first pass are the indices themselves (no iota array).  The prefix sum of `tiles_touched` in depth
-// order (rasterizer_impl.cu:295 InclusiveSum) is fused into the duplicate kernel with the same
-// look-back, which also leaves the instance count R on the device.
+// before launching), the first pass of a sort can drop the all-ones key on the fly (depth sort: the
+// culled Gaussians - P keys in, P_vis pairs out, the later passes and the duplicate kernel only see
+// visible ones; tile sort: the instances the exact tile test rejected), and the values of the first
+// depth pass are the indices themselves (no iota array).  The prefix sum of `tiles_touched` in depth
+// order (rasterizer_impl.cu:295 InclusiveSum) is replaced by three levels of partial sums
+// (touched_sums_kernel, which also leaves the instance count R on the device) from which every warp
+// of the duplicate kernel adds up its own first output position.
 #include "common.cuh"
 #include <type_traits>
 
