@@ -7,7 +7,6 @@ after a prune, after a concatenation, and after the reference's whole `densify_a
 its random samples drawn from the same seed)."""
 import types
 
-import numpy as np
 import pytest
 import torch
 

@@ -11,13 +11,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 from ex4dgs_b200 import densify, synth  # noqa: E402
 from tests.test_gpu_densify import _model  # noqa: E402
 
 
-def timed(fn, sync=True):
+def timed(fn):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     fn()
