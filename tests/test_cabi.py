@@ -155,3 +155,18 @@ def test_gather_rows_rejects_bad_jobs_before_touching_cuda(built):
     assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "NULL" in _lib.last_error()
     j[0].dst, j[0].a = f, f + 2
     assert lib.ex4dgs_gather_rows(j, 1, None) < 0 and "aligned" in _lib.last_error()
+
+
+def test_describe_buffers_switches_to_32_bit_tile_keys_beyond_65535_tiles(built):
+    """Host-only layout query: 16-bit tile keys while every tile id and the all-ones dump key fit, 32-bit keys for larger
+    images; ex4dgs_binning_bytes is an upper bound for both."""
+    from ex4dgs_b200 import _lib
+    lib = _lib.load()
+    small = _lib.describe_buffers(1000, 5000, 1352, 1014)
+    large = _lib.describe_buffers(1000, 5000, 4112, 4112)         # 257 x 257 = 66 049 tiles
+    edge = _lib.describe_buffers(1000, 5000, 4080, 4112)          # 255 x 257 = 65 535 tiles: still 16-bit
+    assert small["tile_sorted"][2] == 2 and edge["tile_sorted"][2] == 2 and large["tile_sorted"][2] == 4
+    assert small["point_list"][1] == 0 and large["point_list"][1] == 0       # the sorted id list stays at offset 0
+    assert large["ranges"][3] == 66049
+    need = max(d["tile_sorted"][1] + d["tile_sorted"][2] * 5000 for d in (small, large))
+    assert lib.ex4dgs_binning_bytes(5000) >= need
