@@ -14,7 +14,7 @@
 //          motion_reg * mean_{i, k>=1} |xyz_motion[i,0] - xyz_motion[i,k]|
 //      (rot_reg is 0.0 in arguments/__init__.py:136 and `if opt.rot_reg > 0` never runs.)  The reference
 //      lets autograd run slice, sub, norm, mean and their backward over the [Nd,K,3] keyframe tensor
-//      (eight passes); here the tensor is read once and its gradient read-modify-written once, one warp per
+//      (eight passes); here the tensor is read once and its gradient read-modify-written once, one half-warp per
 //      [K,3] row, staged through shared memory so that both cross HBM as whole 128-bit lines.  Sums are
 //      reduced in a fixed order (per-block partials in double, then one block): bit-reproducible.
 #include "common.cuh"
@@ -77,12 +77,12 @@ constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
 constexpr int kRegMaxK = 64;          // keyframes per row the staged path holds (2 x 768 B per warp); more: direct path
 
-// One warp per dynamic Gaussian row ([K,3] floats, contiguous) and one thread per static Gaussian; block
+// One half-warp per dynamic Gaussian row ([K,3] floats, contiguous) and one thread per static Gaussian; block
 // partial sums (double) go to part[2 * block + {0,1}].
-__global__ void __launch_bounds__(kRegThreads, 6) regularizer_kernel(const __grid_constant__ RegParams p)
+__global__ void __launch_bounds__(kRegThreads, 5) regularizer_kernel(const __grid_constant__ RegParams p)
 {
     __shared__ double s_part[2][kRegWarps];
-    __shared__ __align__(16) float s_row[kRegWarps][2][kRegMaxK * 3];
+    __shared__ __align__(16) float s_row[kRegWarps][2][2][kRegMaxK * 3];     // [warp][half-warp][values | gradient]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const float gscale = p.dL_dloss ? __ldg(p.dL_dloss) : 1.0f;
@@ -111,33 +111,63 @@ __global__ void __launch_bounds__(kRegThreads, 6) regularizer_kernel(const __gri
         // 128-bit lines (a lane's own (x, y, z) triple sits at a 12-byte stride)
         const bool staged = (p.K <= kRegMaxK) && (row_f % 4 == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.xyz_motion) | reinterpret_cast<uintptr_t>(p.dL_dxyz_motion)) & 15) == 0;
-        float* sv = s_row[warp][0];
-        float* sg = s_row[warp][1];
-        for (long long i = wid; i < p.Nd; i += (long long)gridDim.x * kRegWarps) {
-            const float* row = p.xyz_motion + i * (long long)row_f;
-            float* grow = p.dL_dxyz_motion ? p.dL_dxyz_motion + i * (long long)row_f : nullptr;
-            float s0x = 0.f, s0y = 0.f, s0z = 0.f, sn = 0.f;
-            if (staged) {
-                const int n4 = row_f / 4;
-                for (int f = lane; f < n4; f += 32) {
-                    reinterpret_cast<float4*>(sv)[f] = __ldg(reinterpret_cast<const float4*>(row) + f);
-                    if (grow) reinterpret_cast<float4*>(sg)[f] = p.accumulate_motion ? reinterpret_cast<const float4*>(grow)[f]
-                                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                __syncwarp();
-                const float x0 = sv[0], y0 = sv[1], z0 = sv[2];
-                for (int k = 1 + lane; k < p.K; k += 32) {
-                    const float dx = x0 - sv[3 * k], dy = y0 - sv[3 * k + 1], dz = z0 - sv[3 * k + 2];
-                    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-                    sn += n;
-                    if (grow) {
-                        const float s = (n == 0.0f) ? 0.0f : c / n;
-                        const float gx = dx * s, gy = dy * s, gz = dz * s;     // d/d y_0 ; d/d y_k is the negative
-                        s0x += gx; s0y += gy; s0z += gz;
-                        sg[3 * k] -= gx; sg[3 * k + 1] -= gy; sg[3 * k + 2] -= gz;
+        if (staged) {
+            // one HALF-warp per row: two rows of a warp in flight at once (the kernel waits on its row loads - rows in
+            // flight per SM are what hides the latency), K - 1 keyframes over 16 lanes
+            const int hw = lane >> 4, hl = lane & 15;
+            float* sv = s_row[warp][hw][0];
+            float* sg = s_row[warp][hw][1];
+            const int n4 = row_f / 4;
+            for (long long pair = wid; 2 * pair < p.Nd; pair += (long long)gridDim.x * kRegWarps) {
+                const long long i = 2 * pair + hw;
+                const bool valid = i < p.Nd;
+                const float* row = p.xyz_motion + i * (long long)row_f;
+                float* grow = (p.dL_dxyz_motion && valid) ? p.dL_dxyz_motion + i * (long long)row_f : nullptr;
+                float s0x = 0.f, s0y = 0.f, s0z = 0.f, sn = 0.f;
+                if (valid) {
+                    for (int f = hl; f < n4; f += 16) {
+                        reinterpret_cast<float4*>(sv)[f] = __ldg(reinterpret_cast<const float4*>(row) + f);
+                        if (grow) reinterpret_cast<float4*>(sg)[f] = p.accumulate_motion ? reinterpret_cast<const float4*>(grow)[f]
+                                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-            } else {
+                __syncwarp();
+                if (valid) {
+                    const float x0 = sv[0], y0 = sv[1], z0 = sv[2];
+                    for (int k = 1 + hl; k < p.K; k += 16) {
+                        const float dx = x0 - sv[3 * k], dy = y0 - sv[3 * k + 1], dz = z0 - sv[3 * k + 2];
+                        const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+                        sn += n;
+                        if (grow) {
+                            const float s = (n == 0.0f) ? 0.0f : c / n;
+                            const float gx = dx * s, gy = dy * s, gz = dz * s;     // d/d y_0 ; d/d y_k is the negative
+                            s0x += gx; s0y += gy; s0z += gz;
+                            sg[3 * k] -= gx; sg[3 * k + 1] -= gy; sg[3 * k + 2] -= gz;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {          // within the half-warp
+                    s0x += __shfl_xor_sync(full, s0x, o);
+                    s0y += __shfl_xor_sync(full, s0y, o);
+                    s0z += __shfl_xor_sync(full, s0z, o);
+                    sn += __shfl_xor_sync(full, sn, o);
+                }
+                if (hl == 0 && valid) sum_motion += (double)sn;
+                if (grow) {
+                    if (hl == 0) { sg[0] += s0x; sg[1] += s0y; sg[2] += s0z; }
+                }
+                __syncwarp();
+                if (grow) {
+                    for (int f = hl; f < n4; f += 16) reinterpret_cast<float4*>(grow)[f] = reinterpret_cast<const float4*>(sg)[f];
+                }
+                __syncwarp();                      // the buffers are reused by the half-warp's next row
+            }
+        } else {
+            for (long long i = wid; i < p.Nd; i += (long long)gridDim.x * kRegWarps) {
+                const float* row = p.xyz_motion + i * (long long)row_f;
+                float* grow = p.dL_dxyz_motion ? p.dL_dxyz_motion + i * (long long)row_f : nullptr;
+                float s0x = 0.f, s0y = 0.f, s0z = 0.f, sn = 0.f;
                 const float x0 = __ldg(row), y0 = __ldg(row + 1), z0 = __ldg(row + 2);
                 for (int k = 1 + lane; k < p.K; k += 32) {
                     const float dx = x0 - __ldg(row + 3 * k), dy = y0 - __ldg(row + 3 * k + 1), dz = z0 - __ldg(row + 3 * k + 2);
@@ -151,25 +181,18 @@ __global__ void __launch_bounds__(kRegThreads, 6) regularizer_kernel(const __gri
                         else { grow[3 * k] = -gx; grow[3 * k + 1] = -gy; grow[3 * k + 2] = -gz; }
                     }
                 }
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s0x += __shfl_xor_sync(full, s0x, o);
-                s0y += __shfl_xor_sync(full, s0y, o);
-                s0z += __shfl_xor_sync(full, s0z, o);
-                sn += __shfl_xor_sync(full, sn, o);
-            }
-            if (lane == 0) sum_motion += (double)sn;
-            if (staged) {
-                if (grow) {
-                    if (lane == 0) { sg[0] += s0x; sg[1] += s0y; sg[2] += s0z; }
-                    __syncwarp();
-                    for (int f = lane; f < row_f / 4; f += 32) reinterpret_cast<float4*>(grow)[f] = reinterpret_cast<const float4*>(sg)[f];
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0x += __shfl_xor_sync(full, s0x, o);
+                    s0y += __shfl_xor_sync(full, s0y, o);
+                    s0z += __shfl_xor_sync(full, s0z, o);
+                    sn += __shfl_xor_sync(full, sn, o);
                 }
-                __syncwarp();                      // the buffers are reused by the warp's next row
-            } else if (lane == 0 && grow) {
-                if (p.accumulate_motion) { grow[0] += s0x; grow[1] += s0y; grow[2] += s0z; }
-                else { grow[0] = s0x; grow[1] = s0y; grow[2] = s0z; }
+                if (lane == 0) sum_motion += (double)sn;
+                if (lane == 0 && grow) {
+                    if (p.accumulate_motion) { grow[0] += s0x; grow[1] += s0y; grow[2] += s0z; }
+                    else { grow[0] = s0x; grow[1] = s0y; grow[2] = s0z; }
+                }
             }
         }
     }
@@ -222,7 +245,7 @@ int regularizer_blocks()
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 12;      // two waves of the 6 resident CTAs per SM
+    return sms * 10;      // two waves of the 5 resident CTAs per SM
 }
 
 cudaError_t launch_regularizers(RegParams p, float* out2, cudaStream_t s)
